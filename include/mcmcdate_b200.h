@@ -1,0 +1,125 @@
+/* mcmcdate_b200.h -- C ABI of the B200-native batched evaluator for McmcDate's hot path.
+ *
+ * The reference (dschrempf/mcmc-date) is pure Haskell with NO FFI today.  These entry
+ * points are what a `foreign import ccall` shim would bind so that the functions the `mcmc` sampler
+ * consumes keep their types (INTEGRATION.md shows the shim):
+ *
+ *   reference interface (file:line, relative to the reference repo)      -> replaced by
+ *   ------------------------------------------------------------------------------------------
+ *   priorFunction            app/Probability.hs:127-150   PriorFunction I        mcd_eval      (out[MCD_OUT_LNPRIOR])
+ *   priorFunctionCalibrationsConstraintsBraces  :46-63    (monitor, Monitor.hs)  mcd_eval      (out[MCD_OUT_LNA])
+ *   priorFunctionBirthDeath  :66-85                       (monitor)              mcd_eval      (out[MCD_OUT_LNB])
+ *   priorFunctionRelaxedMolecularClock  :96-124           (monitor)              mcd_eval      (out[MCD_OUT_LNC])
+ *   likelihoodFunction       app/Probability.hs:277-281   LikelihoodFunction I   mcd_eval      (out[MCD_OUT_LNLIK])
+ *   jacobianRootBranch       app/Probability.hs:408-410   JacobianFunction I     mcd_eval      (out[MCD_OUT_LNJAC])
+ *   htargetWith + `ad` grad  app/Hamiltonian.hs:72-92     HTarget IG             mcd_eval_grad (out[MCD_OUT_LNPOST], grad)
+ *   getMask                  app/Hamiltonian.hs:33-47                            mcd_mask
+ *   toVector / fromVectorWith app/Hamiltonian.hs:49-60    HStructure IG          mcd_to_vector / mcd_from_vector
+ *   getBranches+sumFirstTwo  app/Tools.hs:36-48           (branch order)         mcd_branch_index
+ *
+ * Conventions
+ *   - plain C types only; every call returns int: 0 = ok, < 0 = fatal (bad argument, CUDA error);
+ *     the message is available from mcd_last_error().  Per-chain domain problems never fail a call:
+ *     they set status[b] bits and yield -inf / NaN like the reference's `Log` arithmetic would.
+ *   - a state is the canonical flattening `toList (x :: I)` (app/State.hs:70-100):
+ *       [lambda, mu, H, h_0..h_{N-1}, m, v, r_0..r_{N-1}]        S = 5 + 2N doubles
+ *     with node heights h and rates r in pre-order (root first).  Batches are chain-major [B][S].
+ *   - the caller owns all in/out buffers; the library owns the handle and all device memory.
+ *   - one handle = one GPU.  Calls on one handle are serialised internally (mutex); use `safe`
+ *     foreign calls from Haskell.  No CPU fallback exists: without a CUDA device mcd_create fails.
+ */
+#ifndef MCMCDATE_B200_H
+#define MCMCDATE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcd_handle mcd_handle;
+
+/* RelaxedMolecularClockModel, app/Probability.hs:88-93 */
+enum { MCD_CLOCK_UNCORRELATED_GAMMA = 0, MCD_CLOCK_UNCORRELATED_LOGNORMAL = 1,
+       MCD_CLOCK_UNCORRELATED_WHITENOISE = 2, MCD_CLOCK_AUTOCORRELATED_LOGNORMAL = 3 };
+/* LikelihoodData, app/Probability.hs:210-235 (Sparse: not built yet) */
+enum { MCD_LIK_FULL = 0, MCD_LIK_UNIVARIATE = 1, MCD_LIK_NONE = 2 };
+/* per-chain status bits */
+enum { MCD_ST_REF_ERROR = 1,    /* the reference would have called `error` (abort); value -inf */
+       MCD_ST_ZERO = 2,         /* ln posterior = -inf (probability zero) */
+       MCD_ST_NAN = 4,          /* ln posterior is NaN */
+       MCD_ST_NEARCRIT = 8,     /* |lambda - mu| < 1e-6 (BirthDeath.hs:125-126) */
+       MCD_ST_LEAF_HEIGHT = 16  /* a leaf height != 0: HeightTree invariant violated */ };
+/* columns of one output row (MCD_OUT_COLS doubles per chain) */
+enum { MCD_OUT_LNA = 0,     /* calibrations * constraints * braces */
+       MCD_OUT_LNB = 1,     /* exponential(lambda) * exponential(mu) * birth-death */
+       MCD_OUT_LNC = 2,     /* exponential(m) * gamma(v) * relaxed clock */
+       MCD_OUT_LNPRIOR = 3, /* product' [A, B, C] */
+       MCD_OUT_LNLIK = 4, MCD_OUT_LNJAC = 5,
+       MCD_OUT_LNPOST = 6,  /* prior * likelihood * jacobian (the HMC target) */
+       MCD_OUT_COLS = 8 };
+
+typedef struct mcd_model_desc {
+  int32_t n_nodes;           /* N = 2n-1, strictly bifurcating, pre-order numbering, root = 0 */
+  const int32_t* parent;     /* [N], parent[0] = -1 */
+  int32_t clock_model;       /* MCD_CLOCK_* */
+  int32_t likelihood;        /* MCD_LIK_* */
+  const double* mean;        /* [K], K = N-2, branch order of mcd_branch_index */
+  const double* precision;   /* FULL: [K*K] row-major symmetric Sigma^-1; UNIVARIATE: [K] variances */
+  double logdet_sigma;       /* ln det Sigma (FULL) / sum ln variances (UNIVARIATE) */
+  double ht;                 /* mean root height for the rate-mean prior (app/Main.hs:394), > 0 */
+  int32_t n_cal;             /* calibrations (Calibration.hs:55-123) */
+  const int32_t* cal_node;   /* [n_cal] pre-order node index */
+  const double* cal_lo;      /* lower bound (absolute age); <= 0: none */
+  const double* cal_lo_p;    /* probability mass at the lower bound */
+  const double* cal_hi;      /* upper bound; +inf: none */
+  const double* cal_hi_p;
+  int32_t n_con;             /* constraints (Constraint.hs:61-74) */
+  const int32_t* con_young;
+  const int32_t* con_old;
+  const double* con_p;
+  int32_t n_brace;           /* braces (Brace.hs:54-59), CSR over nodes */
+  const int32_t* brace_off;  /* [n_brace+1] */
+  const int32_t* brace_node; /* [brace_off[n_brace]] */
+  const double* brace_sd;    /* [n_brace], > 0 */
+  int32_t device;            /* CUDA device ordinal */
+  int32_t max_batch;         /* capacity hint; buffers grow on demand */
+} mcd_model_desc;
+
+/* lifecycle */
+int mcd_create(const mcd_model_desc* desc, mcd_handle** out);
+void mcd_destroy(mcd_handle* h);
+const char* mcd_last_error(const mcd_handle* h); /* h may be NULL: error of the last failed mcd_create */
+
+/* model queries (host side, no GPU work) */
+int mcd_state_len(const mcd_handle* h);                  /* S = 5 + 2N */
+int mcd_dim(const mcd_handle* h);                        /* K */
+int mcd_branch_index(const mcd_handle* h, int32_t* out); /* [N] node -> k, root -1 */
+int mcd_mask(const mcd_handle* h, uint8_t* out);         /* [S] 1 = free under HMC (getMask) */
+int mcd_hmc_dim(const mcd_handle* h);                    /* D = number of free parameters */
+int mcd_to_vector(const mcd_handle* h, const double* state, double* theta);  /* theta[D], reversed order */
+int mcd_from_vector(const mcd_handle* h, const double* base_state, const double* theta, double* state_out);
+
+/* evaluation with HOST buffers (copies in and out are part of the call; chunks are pipelined) */
+int mcd_eval(mcd_handle* h, int32_t n_chains, const double* states /*[B][S]*/,
+             double* out /*[B][MCD_OUT_COLS]*/, int32_t* status /*[B]*/);
+int mcd_eval_grad(mcd_handle* h, int32_t n_chains, const double* states /*[B][S]*/,
+                  double* out /*[B][MCD_OUT_COLS]*/, double* grad /*[B][S], masked entries 0*/,
+                  int32_t* status /*[B]*/);
+
+/* evaluation with DEVICE buffers already resident in HBM (no copies); `stream` is a cudaStream_t
+ * or NULL.  Asynchronous: returns after enqueueing. */
+int mcd_eval_device(mcd_handle* h, int32_t n_chains, const double* d_states, double* d_out,
+                    int32_t* d_status, void* stream);
+int mcd_eval_grad_device(mcd_handle* h, int32_t n_chains, const double* d_states, double* d_out,
+                         double* d_grad, int32_t* d_status, void* stream);
+
+/* bookkeeping */
+int64_t mcd_kernel_launches(const mcd_handle* h); /* kernels launched by this handle so far */
+int mcd_synchronize(mcd_handle* h);
+const char* mcd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCMCDATE_B200_H */

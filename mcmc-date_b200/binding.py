@@ -1,0 +1,193 @@
+"""ctypes binding of the C ABI (include/mcmcdate_b200.h) -- the same entry points a Haskell
+`foreign import ccall` shim would bind.
+
+No CPU fallback: if libmcmcdate_b200.so is missing or no CUDA device is present, construction of an
+`Evaluator` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import model as _m
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcmcdate_b200.so")
+_LIB = None
+
+EXPORTS = [
+    "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
+    "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_device",
+    "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version",
+]
+
+
+class ModelDescC(C.Structure):
+    """struct mcd_model_desc"""
+    _fields_ = [
+        ("n_nodes", C.c_int32), ("parent", C.POINTER(C.c_int32)),
+        ("clock_model", C.c_int32), ("likelihood", C.c_int32),
+        ("mean", C.POINTER(C.c_double)), ("precision", C.POINTER(C.c_double)),
+        ("logdet_sigma", C.c_double), ("ht", C.c_double),
+        ("n_cal", C.c_int32), ("cal_node", C.POINTER(C.c_int32)),
+        ("cal_lo", C.POINTER(C.c_double)), ("cal_lo_p", C.POINTER(C.c_double)),
+        ("cal_hi", C.POINTER(C.c_double)), ("cal_hi_p", C.POINTER(C.c_double)),
+        ("n_con", C.c_int32), ("con_young", C.POINTER(C.c_int32)), ("con_old", C.POINTER(C.c_int32)),
+        ("con_p", C.POINTER(C.c_double)),
+        ("n_brace", C.c_int32), ("brace_off", C.POINTER(C.c_int32)), ("brace_node", C.POINTER(C.c_int32)),
+        ("brace_sd", C.POINTER(C.c_double)),
+        ("device", C.c_int32), ("max_batch", C.c_int32),
+    ]
+
+
+def load_library():
+    """dlopen the in-tree shared library and declare prototypes.  Raises if it is not built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, dp, ip, u8p = C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    L.mcd_create.argtypes = [C.POINTER(ModelDescC), C.POINTER(vp)]
+    L.mcd_destroy.argtypes = [vp]
+    L.mcd_destroy.restype = None
+    L.mcd_last_error.argtypes = [vp]
+    L.mcd_last_error.restype = C.c_char_p
+    L.mcd_version.restype = C.c_char_p
+    for f in ("mcd_state_len", "mcd_dim", "mcd_hmc_dim", "mcd_synchronize"):
+        getattr(L, f).argtypes = [vp]
+    L.mcd_branch_index.argtypes = [vp, ip]
+    L.mcd_mask.argtypes = [vp, u8p]
+    L.mcd_to_vector.argtypes = [vp, dp, dp]
+    L.mcd_from_vector.argtypes = [vp, dp, dp, dp]
+    L.mcd_eval.argtypes = [vp, i32, dp, dp, ip]
+    L.mcd_eval_grad.argtypes = [vp, i32, dp, dp, dp, ip]
+    L.mcd_eval_device.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.mcd_kernel_launches.argtypes = [vp]
+    L.mcd_kernel_launches.restype = C.c_int64
+    _LIB = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Evaluator:
+    """One model on one GPU (an `mcd_handle`)."""
+
+    def __init__(self, md: _m.ModelDesc, device: int = 0, max_batch: int = 0):
+        L = load_library()
+        self._L = L
+        self.md = md
+        prec = np.ascontiguousarray(md.precision, dtype=np.float64).reshape(-1)
+        self._keep = [prec]
+        d = ModelDescC()
+        d.n_nodes = md.n_nodes
+        d.parent = _ip(md.parent)
+        d.clock_model, d.likelihood = md.clock_model, md.likelihood
+        d.mean, d.precision = _dp(md.mean), _dp(prec)
+        d.logdet_sigma, d.ht = md.logdet_sigma, md.ht
+        d.n_cal, d.cal_node = md.n_cal, _ip(md.cal_node)
+        d.cal_lo, d.cal_lo_p, d.cal_hi, d.cal_hi_p = _dp(md.cal_lo), _dp(md.cal_lo_p), _dp(md.cal_hi), _dp(md.cal_hi_p)
+        d.n_con, d.con_young, d.con_old, d.con_p = md.n_con, _ip(md.con_young), _ip(md.con_old), _dp(md.con_p)
+        d.n_brace, d.brace_off, d.brace_node, d.brace_sd = md.n_brace, _ip(md.brace_off), _ip(md.brace_node), _dp(md.brace_sd)
+        d.device, d.max_batch = device, max_batch
+        h = C.c_void_p()
+        rc = L.mcd_create(C.byref(d), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("mcd_create failed: " + L.mcd_last_error(None).decode())
+        self.h = h
+        self.S = L.mcd_state_len(h)
+        self.K = L.mcd_dim(h)
+        self.D = L.mcd_hmc_dim(h)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.mcd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("mcmcdate_b200: " + self._L.mcd_last_error(self.h).decode())
+
+    # model queries -------------------------------------------------------------------------
+    def branch_index(self) -> np.ndarray:
+        out = np.empty(self.md.n_nodes, np.int32)
+        self._check(self._L.mcd_branch_index(self.h, _ip(out)))
+        return out
+
+    def mask(self) -> np.ndarray:
+        out = np.empty(self.S, np.uint8)
+        self._check(self._L.mcd_mask(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def to_vector(self, state: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(state, dtype=np.float64)
+        th = np.empty(self.D)
+        self._check(self._L.mcd_to_vector(self.h, _dp(x), _dp(th)))
+        return th
+
+    def from_vector(self, base_state: np.ndarray, theta: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(base_state, dtype=np.float64)
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        out = np.empty(self.S)
+        self._check(self._L.mcd_from_vector(self.h, _dp(x), _dp(th), _dp(out)))
+        return out
+
+    # host-buffer evaluation ----------------------------------------------------------------
+    def eval(self, states: np.ndarray, out: np.ndarray | None = None, status: np.ndarray | None = None):
+        X = np.ascontiguousarray(states, dtype=np.float64).reshape(-1, self.S)
+        B = X.shape[0]
+        out = np.empty((B, _m.OUT_COLS)) if out is None else out
+        status = np.empty(B, np.int32) if status is None else status
+        self._check(self._L.mcd_eval(self.h, B, _dp(X), _dp(out), _ip(status)))
+        return out, status
+
+    def eval_grad(self, states: np.ndarray, out: np.ndarray | None = None, grad: np.ndarray | None = None,
+                  status: np.ndarray | None = None):
+        X = np.ascontiguousarray(states, dtype=np.float64).reshape(-1, self.S)
+        B = X.shape[0]
+        out = np.empty((B, _m.OUT_COLS)) if out is None else out
+        grad = np.empty((B, self.S)) if grad is None else grad
+        status = np.empty(B, np.int32) if status is None else status
+        self._check(self._L.mcd_eval_grad(self.h, B, _dp(X), _dp(out), _dp(grad), _ip(status)))
+        return out, grad, status
+
+    # raw-pointer entry points (host or device addresses as ints) ---------------------------
+    def eval_grad_ptr(self, B: int, states_ptr: int, out_ptr: int, grad_ptr: int, status_ptr: int):
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        self._check(self._L.mcd_eval_grad(self.h, B, C.cast(states_ptr, dp), C.cast(out_ptr, dp), C.cast(grad_ptr, dp),
+                                          C.cast(status_ptr, ip)))
+
+    def eval_ptr(self, B: int, states_ptr: int, out_ptr: int, status_ptr: int):
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        self._check(self._L.mcd_eval(self.h, B, C.cast(states_ptr, dp), C.cast(out_ptr, dp), C.cast(status_ptr, ip)))
+
+    def eval_grad_device(self, B: int, d_states: int, d_out: int, d_grad: int, d_status: int, stream: int = 0):
+        self._check(self._L.mcd_eval_grad_device(self.h, B, d_states, d_out, d_grad, d_status, stream))
+
+    def eval_device(self, B: int, d_states: int, d_out: int, d_status: int, stream: int = 0):
+        self._check(self._L.mcd_eval_device(self.h, B, d_states, d_out, d_status, stream))
+
+    def kernel_launches(self) -> int:
+        return int(self._L.mcd_kernel_launches(self.h))
+
+    def synchronize(self):
+        self._check(self._L.mcd_synchronize(self.h))

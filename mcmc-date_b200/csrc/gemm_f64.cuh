@@ -77,7 +77,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
 // per thread.  Thread 0 doubles as the TMA producer.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f64_dmma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmX,
-                     double* __restrict__ Y, int nk, int ldy) {
+                     double* __restrict__ Y, int nk, int ldy, int bt_base) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)GEMM_STAGES * GEMM_STAGE_BYTES);
@@ -89,7 +89,7 @@ gemm_f64_dmma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
   const int wbt = (warp & 1) * 64;
   const int wpr = (warp >> 1) * 32;
   const int pr0 = blockIdx.x * GEMM_PR;
-  const int bt0 = blockIdx.y * GEMM_BT;
+  const int bt0 = bt_base + blockIdx.y * GEMM_BT;
 
   if (tid == 0) {
 #pragma unroll
@@ -206,11 +206,11 @@ inline cudaError_t gemm_f64_dmma_configure() {
                               (int)GEMM_SMEM_BYTES);
 }
 
-// Mp = P rows (mult of 128), Bp = chains (mult of 128), ldk = padded K (mult of 16)
+// Mp = P rows (mult of 128), ldk = padded K (mult of 16); chains [bt_base, bt_base + Bp), both mult of 128
 inline cudaError_t gemm_f64_dmma_launch(const CUtensorMap& tmP, const CUtensorMap& tmX, double* Y, int Mp, int Bp,
-                                        int ldk, int ldy, cudaStream_t st) {
+                                        int ldk, int ldy, cudaStream_t st, int bt_base = 0) {
   dim3 grid(Mp / GEMM_PR, Bp / GEMM_BT);
-  gemm_f64_dmma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmP, tmX, Y, ldk / GEMM_BK, ldy);
+  gemm_f64_dmma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmP, tmX, Y, ldk / GEMM_BK, ldy, bt_base);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,417 @@
+// mcd_api.cu -- C ABI (include/mcmcdate_b200.h) of the B200-native batched evaluator.
+//
+// Host-side mirror of the reference interface for this path (compiled code, like the reference):
+// handle = what `getMcmcProps` closes over (app/Main.hs:370-457); mcd_eval / mcd_eval_grad =
+// priorFunction / likelihoodFunction / jacobianRootBranch / HTarget evaluated for B states at once;
+// mcd_mask / mcd_to_vector / mcd_from_vector = getMask / toVector / fromVectorWith
+// (app/Hamiltonian.hs:33-60); mcd_branch_index = getBranches + sumFirstTwo (app/Tools.hs:36-48).
+//
+// There is no CPU fallback: every evaluation runs the three CUDA kernels
+//   residual_kernel -> gemm_f64_dmma_kernel -> posterior_kernel.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mcmcdate_b200.h"
+#include "gemm_f64.cuh"
+#include "posterior_kernels.cuh"
+
+using namespace mcd;
+
+namespace {
+
+std::string g_create_error;
+constexpr int N_STREAMS = 3;
+constexpr int SMALL_TREE_MAX_NODES = 96;  // warp-per-chain kernels up to this many nodes
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct mcd_handle {
+  int device = 0;
+  // host copies
+  int N = 0, K = 0, S = 0, D = 0, ldk = 0, Mp = 0, ldy = 0;
+  std::vector<int32_t> parent, child1, bidx;
+  std::vector<uint8_t> mask;
+  // device model
+  DevModel dm{};
+  DevBuf d_parent, d_child1, d_mu, d_var, d_P;
+  DevBuf d_cal_node, d_cal_lo, d_cal_hi, d_cal_slo, d_cal_shi, d_con_y, d_con_o, d_con_s, d_br_off, d_br_node, d_br_sd,
+      d_inc_off, d_inc_ent;
+  CUtensorMap tmP{}, tmX{};
+  // work buffers (capacity `cap` chains, multiple of 128)
+  int cap = 0;
+  DevBuf d_dx, d_y;               // internal: residuals and P.dx
+  DevBuf d_states, d_out, d_grad, d_status;  // staging for the host-buffer API
+  cudaStream_t streams[N_STREAMS] = {nullptr, nullptr, nullptr};
+  std::mutex mtx;
+  std::string err;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int fail(mcd_handle* h, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return -1;
+}
+#define CU_TRY(h, call)                                                                       \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(h, std::string(#call) + ": " + cudaGetErrorString(e__));                    \
+  } while (0)
+
+template <class T>
+int upload(mcd_handle* h, DevBuf& b, const T* src, size_t n) {
+  const size_t na = n ? n : 1;  // keep pointers valid for empty tables
+  CU_TRY(h, cudaMalloc(&b.p, na * sizeof(T)));
+  CU_TRY(h, cudaMemset(b.p, 0, na * sizeof(T)));
+  if (src && n) CU_TRY(h, cudaMemcpy(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
+  int need = (n_chains + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
+  if (need > h->cap) {
+    CU_TRY(h, cudaDeviceSynchronize());
+    for (DevBuf* b : {&h->d_dx, &h->d_y, &h->d_states, &h->d_out, &h->d_grad, &h->d_status}) {
+      if (b->p) cudaFree(b->p);
+      b->p = nullptr;
+    }
+    h->cap = need;
+    if (h->dm.lik == MCD_LIK_FULL) {
+      size_t ndx = (size_t)need * h->ldk, ny = (size_t)need * h->ldy;
+      CU_TRY(h, cudaMalloc(&h->d_dx.p, ndx * 8));
+      CU_TRY(h, cudaMemset(h->d_dx.p, 0, ndx * 8));  // k-padding columns and tail chains stay 0
+      CU_TRY(h, cudaMalloc(&h->d_y.p, ny * 8));
+      CU_TRY(h, cudaMemset(h->d_y.p, 0, ny * 8));
+      if (make_tile_map(&h->tmX, h->d_dx.as<double>(), need, h->ldk) != 0)
+        return fail(h, "cuTensorMapEncodeTiled failed for the residual matrix");
+    }
+  }
+  if (staging) {
+    if (!h->d_states.p) CU_TRY(h, cudaMalloc(&h->d_states.p, (size_t)h->cap * h->S * 8));
+    if (!h->d_out.p) CU_TRY(h, cudaMalloc(&h->d_out.p, (size_t)h->cap * MCD_OUT_COLS * 8));
+    if (!h->d_status.p) CU_TRY(h, cudaMalloc(&h->d_status.p, (size_t)h->cap * 4));
+    if (grad && !h->d_grad.p) CU_TRY(h, cudaMalloc(&h->d_grad.p, (size_t)h->cap * h->S * 8));
+  }
+  return 0;
+}
+
+// enqueue the three kernels for chains [c0, c0 + n) of the given device buffers; c0 % 128 == 0
+template <bool GRAD>
+int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
+            cudaStream_t st) {
+  const DevModel& M = h->dm;
+  const bool small = M.N <= SMALL_TREE_MAX_NODES;
+  const int cpb = small ? POST_THREADS / 32 : 1;
+  const int grid = (n + cpb - 1) / cpb;
+  const double* xs = d_states + (size_t)c0 * M.S;
+  double* dx = h->d_dx.as<double>() + (size_t)c0 * M.ldk;
+  const double* y = h->d_y.as<double>() + (size_t)c0 * M.ldy;
+  if (M.lik == MCD_LIK_FULL) {
+    if (small) residual_kernel<32><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
+    else residual_kernel<256><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
+    const int np = (n + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
+    CU_TRY(h, gemm_f64_dmma_launch(h->tmP, h->tmX, h->d_y.as<double>(), h->Mp, np, M.ldk, M.ldy, st, c0));
+    h->launches += 2;
+  }
+  const size_t smem = POST_SMEM_FIXED + (GRAD ? (size_t)cpb * M.N * 8 : 0);
+  double* o = d_out + (size_t)c0 * MCD_OUT_COLS;
+  double* g = GRAD ? d_grad + (size_t)c0 * M.S : nullptr;
+  int32_t* s = d_status + c0;
+  if (small) posterior_kernel<32, GRAD><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n);
+  else posterior_kernel<256, GRAD><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n);
+  h->launches += 1;
+  CU_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+template <bool GRAD>
+int eval_device(mcd_handle* h, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
+                void* stream) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (n <= 0) return 0;
+  if (!d_states || !d_out || !d_status || (GRAD && !d_grad)) return fail(h, "null device buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (ensure_capacity(h, n, false, GRAD)) return -1;
+  return enqueue<GRAD>(h, 0, n, d_states, d_out, d_grad, d_status, static_cast<cudaStream_t>(stream));
+}
+
+// host buffers: chunks of chains are copied in, evaluated and copied out on rotating streams so
+// that PCIe transfers in both directions overlap the kernels of neighbouring chunks
+template <bool GRAD>
+int eval_host(mcd_handle* h, int n, const double* states, double* out, double* grad, int32_t* status) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (n <= 0) return 0;
+  if (!states || !out || !status || (GRAD && !grad)) return fail(h, "null host buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (ensure_capacity(h, n, true, GRAD)) return -1;
+  const int S = h->S;
+  int chunk = 1024;  // chains per chunk (multiple of 128)
+  if ((size_t)chunk * S * 8 < (size_t)4 << 20) chunk = (int)(((size_t)4 << 20) / ((size_t)S * 8) / 128 + 1) * 128;
+  int ci = 0;
+  for (int c0 = 0; c0 < n; c0 += chunk, ++ci) {
+    const int m = std::min(chunk, n - c0);
+    cudaStream_t st = h->streams[ci % N_STREAMS];
+    double* d_x = h->d_states.as<double>();
+    CU_TRY(h, cudaMemcpyAsync(d_x + (size_t)c0 * S, states + (size_t)c0 * S, (size_t)m * S * 8, cudaMemcpyHostToDevice, st));
+    if (enqueue<GRAD>(h, c0, m, d_x, h->d_out.as<double>(), h->d_grad.as<double>(), h->d_status.as<int32_t>(), st)) return -1;
+    CU_TRY(h, cudaMemcpyAsync(out + (size_t)c0 * MCD_OUT_COLS, h->d_out.as<double>() + (size_t)c0 * MCD_OUT_COLS,
+                              (size_t)m * MCD_OUT_COLS * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(status + c0, h->d_status.as<int32_t>() + c0, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (GRAD)
+      CU_TRY(h, cudaMemcpyAsync(grad + (size_t)c0 * S, h->d_grad.as<double>() + (size_t)c0 * S, (size_t)m * S * 8,
+                                cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mcd_version(void) { return "mcmcdate_b200 0.1 (sm_100a)"; }
+
+const char* mcd_last_error(const mcd_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
+  if (!d || !out) return fail(nullptr, "mcd_create: null argument");
+  *out = nullptr;
+  const int N = d->n_nodes;
+  if (N < 3 || N % 2 == 0 || !d->parent) return fail(nullptr, "mcd_create: need a bifurcating tree with >= 2 leaves");
+  if (d->clock_model < 0 || d->clock_model > 3) return fail(nullptr, "mcd_create: unknown clock model");
+  if (d->likelihood < 0 || d->likelihood > 2) return fail(nullptr, "mcd_create: unknown likelihood kind");
+  if (!(d->ht > 0.0)) return fail(nullptr, "exponential: Rate is zero or negative.");  // exponential ht (Probability.hs:106)
+  // topology checks: pre-order (parent < child), strictly bifurcating
+  std::vector<int32_t> child0(N, -1), child1(N, -1);
+  if (d->parent[0] != -1) return fail(nullptr, "mcd_create: parent[0] must be -1");
+  for (int i = 1; i < N; ++i) {
+    int p = d->parent[i];
+    if (p < 0 || p >= i) return fail(nullptr, "mcd_create: nodes must be in pre-order (parent index < node index)");
+    if (child0[p] < 0) child0[p] = i;
+    else if (child1[p] < 0) child1[p] = i;
+    else return fail(nullptr, "birthDeathWith: Tree is multifurcating.");
+  }
+  for (int i = 0; i < N; ++i) {
+    if ((child0[i] < 0) != (child1[i] < 0)) return fail(nullptr, "mcd_create: unary nodes are not supported");
+    if (child0[i] >= 0 && child0[i] != i + 1) return fail(nullptr, "mcd_create: nodes must be in pre-order");
+  }
+  if (child0[0] < 0) return fail(nullptr, "getBranches: Root node is not bifurcating.");
+  for (int c = 0; c < d->n_cal; ++c) {
+    if (d->cal_node[c] < 0 || d->cal_node[c] >= N) return fail(nullptr, "mcd_create: calibration node out of range");
+    if (!(d->cal_lo_p[c] > 0 && d->cal_lo_p[c] < 1) && d->cal_lo[c] > 0) return fail(nullptr, "probabilityMass: out of (0,1)");
+    if (!(d->cal_hi_p[c] > 0 && d->cal_hi_p[c] < 1) && std::isfinite(d->cal_hi[c])) return fail(nullptr, "probabilityMass: out of (0,1)");
+  }
+  for (int c = 0; c < d->n_con; ++c) {
+    if (d->con_young[c] < 0 || d->con_young[c] >= N || d->con_old[c] < 0 || d->con_old[c] >= N)
+      return fail(nullptr, "mcd_create: constraint node out of range");
+    if (!(d->con_p[c] > 0 && d->con_p[c] < 1)) return fail(nullptr, "probabilityMass: out of (0,1)");
+  }
+  for (int b = 0; b < d->n_brace; ++b) {
+    if (!(d->brace_sd[b] > 0)) return fail(nullptr, "braceSoftF: Standard deviation is zero or negative.");
+    if (d->brace_off[b + 1] - d->brace_off[b] < 2) return fail(nullptr, "brace: need at least two nodes");
+    for (int j = d->brace_off[b]; j < d->brace_off[b + 1]; ++j)
+      if (d->brace_node[j] < 0 || d->brace_node[j] >= N) return fail(nullptr, "mcd_create: brace node out of range");
+  }
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, "mcd_create: no CUDA device (this library has no CPU fallback)");
+  if (d->device < 0 || d->device >= ndev) return fail(nullptr, "mcd_create: bad device ordinal");
+  mcd_handle* h = new mcd_handle();
+  auto bail = [&](const char* what) {
+    g_create_error = std::string(what) + (h->err.empty() ? "" : (": " + h->err));
+    delete h;
+    return -1;
+  };
+  h->device = d->device;
+  if (cudaSetDevice(h->device) != cudaSuccess) return bail("cudaSetDevice failed");
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, h->device);
+  if (prop.major != 10) return bail("mcd_create: this build targets sm_100a (B200) only");
+
+  const int K = N - 2;
+  h->N = N; h->K = K; h->S = 5 + 2 * N;
+  h->ldk = (K + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+  h->Mp = (K + GEMM_PR - 1) / GEMM_PR * GEMM_PR;
+  h->ldy = h->Mp;
+  h->parent.assign(d->parent, d->parent + N);
+  h->child1 = child1;
+  const int root_r = child1[0];
+  // branch order (closed form of getBranches + sumFirstTwo)
+  h->bidx.resize(N);
+  h->bidx[0] = -1;
+  for (int i = 1; i < N; ++i) h->bidx[i] = (i == 1 || i == root_r) ? 0 : (i < root_r ? i - 1 : i - 2);
+  // getMask (app/Hamiltonian.hs:33-47)
+  h->mask.assign(h->S, 1);
+  h->mask[2] = d->n_cal > 0 ? 1 : 0;
+  h->mask[3] = 0;
+  int n_inner_nonroot = 0;
+  for (int i = 0; i < N; ++i) {
+    if (child0[i] < 0) h->mask[3 + i] = 0;
+    else if (i > 0) ++n_inner_nonroot;
+  }
+  h->mask[5 + N] = 0;
+  h->D = 0;
+  for (uint8_t m : h->mask) h->D += m;
+
+  DevModel& M = h->dm;
+  M.N = N; M.K = K; M.S = h->S; M.ldk = h->ldk; M.ldy = h->ldy;
+  M.root_r = root_r; M.n_inner_nonroot = n_inner_nonroot;
+  M.clock = d->clock_model; M.lik = d->likelihood; M.hmc_free_H = d->n_cal > 0;
+  M.ht = d->ht; M.logdet = d->logdet_sigma;
+  M.lik_const = -(0.9189385332046727418 * (double)K);
+  if (upload(h, h->d_parent, h->parent.data(), N) || upload(h, h->d_child1, child1.data(), N)) return bail("upload topology");
+  M.parent = h->d_parent.as<int>(); M.child1 = h->d_child1.as<int>();
+  // likelihood data
+  std::vector<double> mu(h->ldk, 0.0);
+  if (d->likelihood != MCD_LIK_NONE) {
+    if (!d->mean || !d->precision) return bail("mcd_create: mean / precision missing");
+    std::memcpy(mu.data(), d->mean, K * 8);
+  }
+  if (upload(h, h->d_mu, mu.data(), h->ldk)) return bail("upload mean");
+  M.mu = h->d_mu.as<double>();
+  M.var = nullptr;
+  if (d->likelihood == MCD_LIK_UNIVARIATE) {
+    if (upload(h, h->d_var, d->precision, K)) return bail("upload variances");
+    M.var = h->d_var.as<double>();
+  } else if (d->likelihood == MCD_LIK_FULL) {
+    // P padded to [Mp][ldk]; symmetry is assumed by the reference (L.Herm, app/Probability.hs:166) and
+    // relied on here (gradient = -P dx), so it is checked
+    std::vector<double> P((size_t)h->Mp * h->ldk, 0.0);
+    for (int i = 0; i < K; ++i) {
+      for (int j = 0; j < K; ++j) {
+        const double a = d->precision[(size_t)i * K + j], b = d->precision[(size_t)j * K + i];
+        if (a != b && std::fabs(a - b) > 1e-12 * (std::fabs(a) + std::fabs(b))) return bail("mcd_create: precision matrix is not symmetric");
+        P[(size_t)i * h->ldk + j] = a;
+      }
+    }
+    if (upload(h, h->d_P, P.data(), P.size())) return bail("upload precision");
+    if (make_tile_map(&h->tmP, h->d_P.as<double>(), h->Mp, h->ldk) != 0) return bail("cuTensorMapEncodeTiled failed for the precision matrix");
+    if (gemm_f64_dmma_configure() != cudaSuccess) return bail("cudaFuncSetAttribute(gemm smem) failed");
+  }
+  // node prior tables
+  const double SQRT_2_OVER_PI = 0.7978845608028654;
+  std::vector<double> slo(d->n_cal), shi(d->n_cal), cs(d->n_con);
+  for (int c = 0; c < d->n_cal; ++c) { slo[c] = SQRT_2_OVER_PI * d->cal_lo_p[c]; shi[c] = SQRT_2_OVER_PI * d->cal_hi_p[c]; }
+  for (int c = 0; c < d->n_con; ++c) cs[c] = SQRT_2_OVER_PI * d->con_p[c];
+  std::vector<std::vector<int2>> inc(N);
+  for (int c = 0; c < d->n_cal; ++c) inc[d->cal_node[c]].push_back(make_int2(INC_CAL, c));
+  for (int c = 0; c < d->n_con; ++c) {
+    inc[d->con_young[c]].push_back(make_int2(INC_CON_YOUNG, c));
+    inc[d->con_old[c]].push_back(make_int2(INC_CON_OLD, c));
+  }
+  for (int b = 0; b < d->n_brace; ++b)
+    for (int j = d->brace_off[b]; j < d->brace_off[b + 1]; ++j) inc[d->brace_node[j]].push_back(make_int2(INC_BRACE, b));
+  std::vector<int> inc_off(N + 1, 0);
+  std::vector<int2> inc_ent;
+  for (int i = 0; i < N; ++i) {
+    inc_off[i] = (int)inc_ent.size();
+    inc_ent.insert(inc_ent.end(), inc[i].begin(), inc[i].end());
+  }
+  inc_off[N] = (int)inc_ent.size();
+  const int nbn = d->n_brace > 0 ? d->brace_off[d->n_brace] : 0;
+  std::vector<int> br_off0(1, 0);
+  if (upload(h, h->d_cal_node, d->cal_node, d->n_cal) || upload(h, h->d_cal_lo, d->cal_lo, d->n_cal) ||
+      upload(h, h->d_cal_hi, d->cal_hi, d->n_cal) || upload(h, h->d_cal_slo, slo.data(), d->n_cal) ||
+      upload(h, h->d_cal_shi, shi.data(), d->n_cal) || upload(h, h->d_con_y, d->con_young, d->n_con) ||
+      upload(h, h->d_con_o, d->con_old, d->n_con) || upload(h, h->d_con_s, cs.data(), d->n_con) ||
+      upload(h, h->d_br_off, d->n_brace > 0 ? d->brace_off : br_off0.data(), d->n_brace + 1) ||
+      upload(h, h->d_br_node, d->brace_node, nbn) || upload(h, h->d_br_sd, d->brace_sd, d->n_brace) ||
+      upload(h, h->d_inc_off, inc_off.data(), N + 1) || upload(h, h->d_inc_ent, inc_ent.data(), inc_ent.size()))
+    return bail("upload prior tables");
+  M.n_cal = d->n_cal; M.n_con = d->n_con; M.n_brace = d->n_brace;
+  M.cal_node = h->d_cal_node.as<int>(); M.cal_lo = h->d_cal_lo.as<double>(); M.cal_hi = h->d_cal_hi.as<double>();
+  M.cal_slo = h->d_cal_slo.as<double>(); M.cal_shi = h->d_cal_shi.as<double>();
+  M.con_y = h->d_con_y.as<int>(); M.con_o = h->d_con_o.as<int>(); M.con_s = h->d_con_s.as<double>();
+  M.br_off = h->d_br_off.as<int>(); M.br_node = h->d_br_node.as<int>(); M.br_sd = h->d_br_sd.as<double>();
+  M.inc_off = h->d_inc_off.as<int>(); M.inc_ent = h->d_inc_ent.as<int2>();
+
+  for (int i = 0; i < N_STREAMS; ++i)
+    if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
+  // posterior kernels may need > 48 KiB dynamic smem on large trees
+  const int post_smem = POST_SMEM_FIXED + (N <= SMALL_TREE_MAX_NODES ? (POST_THREADS / 32) * N * 8 : N * 8);
+  if (post_smem > 200 * 1024) return bail("mcd_create: tree too large for the gradient kernel's shared memory (N > 25000)");
+  cudaFuncSetAttribute(posterior_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (d->max_batch > 0 && ensure_capacity(h, d->max_batch, false, false)) return bail("allocating work buffers");
+  if (cudaDeviceSynchronize() != cudaSuccess) return bail("device error during create");
+  *out = h;
+  return 0;
+}
+
+void mcd_destroy(mcd_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < N_STREAMS; ++i)
+    if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+  delete h;
+}
+
+int mcd_state_len(const mcd_handle* h) { return h ? h->S : -1; }
+int mcd_dim(const mcd_handle* h) { return h ? h->K : -1; }
+int mcd_hmc_dim(const mcd_handle* h) { return h ? h->D : -1; }
+int mcd_branch_index(const mcd_handle* h, int32_t* out) {
+  if (!h || !out) return -1;
+  std::memcpy(out, h->bidx.data(), sizeof(int32_t) * h->N);
+  return 0;
+}
+int mcd_mask(const mcd_handle* h, uint8_t* out) {
+  if (!h || !out) return -1;
+  std::memcpy(out, h->mask.data(), h->S);
+  return 0;
+}
+// toVector (app/Hamiltonian.hs:49-53): free entries in REVERSED canonical order
+int mcd_to_vector(const mcd_handle* h, const double* state, double* theta) {
+  if (!h || !state || !theta) return -1;
+  int i = h->D - 1;
+  for (int j = 0; j < h->S; ++j)
+    if (h->mask[j]) theta[i--] = state[j];
+  return 0;
+}
+// fromVectorWith (app/Hamiltonian.hs:55-60)
+int mcd_from_vector(const mcd_handle* h, const double* base, const double* theta, double* out) {
+  if (!h || !base || !theta || !out) return -1;
+  int i = h->D - 1;
+  for (int j = 0; j < h->S; ++j) out[j] = h->mask[j] ? theta[i--] : base[j];
+  return 0;
+}
+
+int mcd_eval(mcd_handle* h, int32_t n, const double* states, double* out, int32_t* status) {
+  return eval_host<false>(h, n, states, out, nullptr, status);
+}
+int mcd_eval_grad(mcd_handle* h, int32_t n, const double* states, double* out, double* grad, int32_t* status) {
+  return eval_host<true>(h, n, states, out, grad, status);
+}
+int mcd_eval_device(mcd_handle* h, int32_t n, const double* d_states, double* d_out, int32_t* d_status, void* stream) {
+  return eval_device<false>(h, n, d_states, d_out, nullptr, d_status, stream);
+}
+int mcd_eval_grad_device(mcd_handle* h, int32_t n, const double* d_states, double* d_out, double* d_grad,
+                         int32_t* d_status, void* stream) {
+  return eval_device<true>(h, n, d_states, d_out, d_grad, d_status, stream);
+}
+int64_t mcd_kernel_launches(const mcd_handle* h) { return h ? h->launches : -1; }
+int mcd_synchronize(mcd_handle* h) {
+  if (!h) return -1;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaDeviceSynchronize());
+  return 0;
+}
+
+}  // extern "C"

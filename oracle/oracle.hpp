@@ -472,45 +472,61 @@ T clock_model(const Model& M, const StateView<T>& s, const std::vector<T>& t) {
 // after it are never evaluated (laziness).  Implemented inline below with early returns.
 // ----------------------------------------------------------------------------------------------
 template <class T>
+bool is_zero(T x) { return primal(x) == NEG_INF; }
+
+template <class T>
 struct Result {
   T lnA, lnB, lnC, lnPrior, lnLik, lnJac, lnPost;
   int status = 0;
 };
 
+// The three prior parts, each evaluated on its own (this is also how the reference's `prior`
+// monitor logs them, app/Monitor.hs:27-56).
+// A: priorFunctionCalibrationsConstraintsBraces (app/Probability.hs:46-63)
 template <class T>
-bool is_zero(T x) { return primal(x) == NEG_INF; }
+T eval_A(const Model& M, const StateView<T>& s) { return prior_node(M, s); }
+// B: priorFunctionBirthDeath (:66-85) = product' [exponential 1 la, exponential 1 mu, birthDeath ...]
+template <class T>
+T eval_B(const Model& M, const StateView<T>& s, const std::vector<T>& t, bool* nearcrit) {
+  const T Z(NEG_INF);
+  T e1 = prior_exponential(T(1.0), s.la());
+  if (is_zero(e1)) return Z;
+  T e2 = prior_exponential(T(1.0), s.mu());
+  if (is_zero(e2)) return Z;
+  BDTree<T> tr{&M.child0, &M.child1, &t};
+  T bd = birth_death_mrca(s.la(), s.mu(), T(1.0), tr, nearcrit);
+  if (is_zero(bd)) return Z;
+  return e1 + e2 + bd;
+}
+// C: priorFunctionRelaxedMolecularClock (:96-124) = product' [exponential ht m, gamma 1.5 (1/6) v, model]
+template <class T>
+T eval_C(const Model& M, const StateView<T>& s, const std::vector<T>& t) {
+  const T Z(NEG_INF);
+  T e = prior_exponential(T(M.ht), s.m());
+  if (is_zero(e)) return Z;
+  T g = prior_gamma(T(3.0 / 2.0), T(1.0 / 6.0), s.v());
+  if (is_zero(g)) return Z;
+  T c = clock_model(M, s, t);
+  if (is_zero(c)) return Z;
+  return e + g + c;
+}
 
-// priorFunction (app/Probability.hs:127-150) = product' [A, B, C]
+// priorFunction (app/Probability.hs:127-150) = product' [A, B, C]: factors after the first zero are
+// never evaluated, so an `error` (RefError) hiding behind a zero does not fire.
 template <class T>
 void eval_prior(const Model& M, const StateView<T>& s, const std::vector<T>& t, Result<T>& R) {
-  const T Z(NEG_INF), NaN(std::numeric_limits<double>::quiet_NaN());
-  R.lnA = R.lnB = R.lnC = NaN;  // NaN = "not evaluated" (lazy)
-  // A: priorFunctionCalibrationsConstraintsBraces (:46-63)
-  R.lnA = prior_node(M, s);
+  const T Z(NEG_INF);
+  bool errA = false, errB = false, errC = false, nc = false;
+  try { R.lnA = eval_A(M, s); } catch (const RefError&) { errA = true; R.lnA = Z; }
+  try { R.lnB = eval_B(M, s, t, &nc); } catch (const RefError&) { errB = true; R.lnB = Z; }
+  try { R.lnC = eval_C(M, s, t); } catch (const RefError&) { errC = true; R.lnC = Z; }
+  if (nc) R.status |= ST_NEARCRIT;
+  if (errA) { R.status |= ST_REF_ERROR; R.lnPrior = Z; return; }
   if (is_zero(R.lnA)) { R.lnPrior = Z; return; }
-  // B: priorFunctionBirthDeath (:66-85) = product' [exponential 1 la, exponential 1 mu, birthDeath ...]
-  {
-    T e1 = prior_exponential(T(1.0), s.la());
-    if (is_zero(e1)) { R.lnB = Z; R.lnPrior = Z; return; }
-    T e2 = prior_exponential(T(1.0), s.mu());
-    if (is_zero(e2)) { R.lnB = Z; R.lnPrior = Z; return; }
-    BDTree<T> tr{&M.child0, &M.child1, &t};
-    bool nc = false;
-    T bd = birth_death_mrca(s.la(), s.mu(), T(1.0), tr, &nc);
-    if (nc) R.status |= ST_NEARCRIT;
-    if (is_zero(bd)) { R.lnB = Z; R.lnPrior = Z; return; }
-    R.lnB = e1 + e2 + bd;
-  }
-  // C: priorFunctionRelaxedMolecularClock (:96-124)
-  {
-    T e = prior_exponential(T(M.ht), s.m());
-    if (is_zero(e)) { R.lnC = Z; R.lnPrior = Z; return; }
-    T g = prior_gamma(T(3.0 / 2.0), T(1.0 / 6.0), s.v());
-    if (is_zero(g)) { R.lnC = Z; R.lnPrior = Z; return; }
-    T c = clock_model(M, s, t);
-    if (is_zero(c)) { R.lnC = Z; R.lnPrior = Z; return; }
-    R.lnC = e + g + c;
-  }
+  if (errB) { R.status |= ST_REF_ERROR; R.lnPrior = Z; return; }
+  if (is_zero(R.lnB)) { R.lnPrior = Z; return; }
+  if (errC) { R.status |= ST_REF_ERROR; R.lnPrior = Z; return; }
+  if (is_zero(R.lnC)) { R.lnPrior = Z; return; }
   R.lnPrior = R.lnA + R.lnB + R.lnC;
 }
 
@@ -519,16 +535,10 @@ template <class T>
 Result<T> eval_state(const Model& M, const T* x, bool generic_lik) {
   Result<T> R;
   StateView<T> s{x, M.N};
-  const T Z(NEG_INF);
   for (int i = 0; i < M.N; ++i)
     if (M.child0[i] < 0 && primal(s.h(i)) != 0.0) R.status |= ST_LEAF_HEIGHT;
   std::vector<T> t = height_to_length(M, s);
-  try {
-    eval_prior(M, s, t, R);
-  } catch (const RefError&) {
-    R.status |= ST_REF_ERROR;
-    R.lnPrior = Z;
-  }
+  eval_prior(M, s, t, R);
   if (M.lik == LIK_NONE) {
     R.lnLik = T(0.0);
   } else {
@@ -551,12 +561,7 @@ inline Result<double> eval_state_double(const Model& M, const double* x, std::ve
   for (int i = 0; i < M.N; ++i)
     if (M.child0[i] < 0 && s.h(i) != 0.0) R.status |= ST_LEAF_HEIGHT;
   std::vector<double> t = height_to_length(M, s);
-  try {
-    eval_prior(M, s, t, R);
-  } catch (const RefError&) {
-    R.status |= ST_REF_ERROR;
-    R.lnPrior = NEG_INF;
-  }
+  eval_prior(M, s, t, R);
   if (M.lik == LIK_NONE) {
     R.lnLik = 0.0;
   } else {
