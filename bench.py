@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- log-posterior + gradient evaluations / second (batched chains).
+
+Workload (BASELINE.json configs[4], the one the north-star target is quoted on): synthetic 1000-leaf
+tree (N = 1999 nodes, K = 1997 MVN dimensions, dense precision matrix), 8192 chains PER GPU
+(weak scaling: chains are independent, the model is replicated, no data-path collective), uncorrelated
+log-normal clock, 16 calibrations / 8 constraints / 4 braces.  One "step" = one batched evaluation of
+ln prior (three parts), ln likelihood, ln Jacobian and the full HMC gradient for every chain.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+  value : chains/s with states resident in HBM (mcd_eval_grad_device), CUDA events, max over ranks
+  e2e   : chains/s through the host-buffer C-ABI call mcd_eval_grad (pinned host states in, ln-posterior
+          parts + gradient out; H2D and D2H copies inside the timed region)
+  roofline     : the FP64 contraction kernel (DMMA), algorithmic 2 K^2 flops per chain
+  cpu_baseline : the oracle's CPU port of the same evaluation on the box's host cores (bounded sample)
+
+--impl reference times the CPU implementation (oracle port; the Haskell reference cannot be built in
+this image) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_LEAVES = 1000
+CHAINS_PER_GPU = 8192
+METRIC = "log-posterior+gradient evals/sec (batched chains)"
+UNIT = "evals/s"
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 FP64 FMA/clk/SM x 1965 MHz = 37.2
+
+
+def workload_config(n_gpus, chains):
+    return {
+        "workload": "synthetic 1000-leaf tree (N=1999 nodes, K=1997, dense precision), "
+                    f"{chains} chains per GPU, value+gradient, uncorrelated log-normal clock, 16 cal / 8 con / 4 braces",
+        "n_leaves": N_LEAVES, "chains_per_gpu": chains, "global_chains": chains * n_gpus,
+        "parallelism": f"chains sharded over {n_gpus} GPU(s), model replicated",
+        "l2": "inputs larger than L2 (states 262 MB + residuals 131 MB + gradient 262 MB per step vs 126 MB L2)",
+    }
+
+
+def build_workload(chains, seed_offset=0):
+    from mcmc_date_b200 import synth
+    md, h = synth.synthetic_model(N_LEAVES, seed=synth.BASE_SEED + 4, n_cal=16, n_con=8, n_brace=4)
+    X = synth.synthetic_states(md, h, chains, seed=synth.BASE_SEED + 5 + seed_offset)
+    return md, X
+
+
+# --------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            txt, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            txt = ""
+        sm, smax, reasons = [], [], set()
+        for line in txt.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------- CPU arm
+def cpu_port_rate(md, X, threads, target_seconds=12.0):
+    """Time the oracle's CPU port (value + analytic gradient) on a bounded sample of X."""
+    from oracle import oracle as O
+    orc = O.Oracle(md)
+    probe = min(len(X), 4 * threads)
+    t0 = time.perf_counter()
+    orc.eval_grad(X[:probe], nthreads=threads)
+    dt = time.perf_counter() - t0
+    n = int(max(probe, min(len(X), probe * target_seconds / max(dt, 1e-6))))
+    t0 = time.perf_counter()
+    orc.eval_grad(X[:n], nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    threads = O.max_threads()
+    md, X = build_workload(CHAINS_PER_GPU)
+    orc = O.Oracle(md)
+    probe = 4 * threads
+    t0 = time.perf_counter()
+    orc.eval_grad(X[:probe], nthreads=threads)
+    rate0 = probe / (time.perf_counter() - t0)
+    budget = 150.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
+    n = int(max(threads, min(len(X), rate0 * min(budget, 15.0))))
+    for _ in range(args.warmup):
+        orc.eval_grad(X[:n], nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.eval_grad(X[:n], nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    cfg = workload_config(args.gpus, CHAINS_PER_GPU)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} of {CHAINS_PER_GPU} chains per step (bounded sample of the same workload); "
+                                   "oracle CPU port (C++ -O3 -march=native, std::thread over chains); the Haskell "
+                                   "reference cannot be built here (no GHC)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from mcmc_date_b200 import binding, model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.chains
+    md, X = build_workload(B, seed_offset=rank)
+    S, K = md.state_len, md.dim
+    ev = binding.Evaluator(md, device=local, max_batch=B)
+
+    d_states = torch.from_numpy(X).to(dev)
+    d_out = torch.empty((B, model.OUT_COLS), dtype=torch.float64, device=dev)
+    d_grad = torch.empty((B, S), dtype=torch.float64, device=dev)
+    d_status = torch.empty(B, dtype=torch.int32, device=dev)
+    gathered = torch.empty((world * B, 2), dtype=torch.float64, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step():
+        ev.eval_grad_device(B, d_states.data_ptr(), d_out.data_ptr(), d_grad.data_ptr(), d_status.data_ptr(),
+                            stream.cuda_stream)
+        if world > 1:  # MC3 swap statistics: (ln prior, ln likelihood) of every chain to every rank
+            dist.all_gather_into_tensor(gathered, d_out[:, 3:5].contiguous())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = ev.kernel_launches()
+    ev.set_kernel_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kms, ncalls = ev.kernel_times()
+    ev.set_kernel_timing(False)
+    launches = ev.kernel_launches() - launches0
+    # --- end-to-end through the host-buffer C ABI (pinned host memory, copies inside) ---------
+    h_states = torch.from_numpy(X).pin_memory()
+    h_out = torch.empty((B, model.OUT_COLS), dtype=torch.float64).pin_memory()
+    h_grad = torch.empty((B, S), dtype=torch.float64).pin_memory()
+    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        ev.eval_grad_ptr(B, h_states.data_ptr(), h_out.data_ptr(), h_grad.data_ptr(), h_status.data_ptr())
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # parity guard: the timed outputs are the real thing (finite, and equal through both entry points)
+    ok = bool(torch.isfinite(d_out[:, 6]).all().item()) and bool(
+        torch.allclose(d_out.cpu()[:, :7], h_out[:, :7], rtol=0, atol=0, equal_nan=True))
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    if rank == 0:
+        total = B * world
+        value = total * args.steps / (ms_max * 1e-3)
+        e2e_value = total * args.steps / (e2e_ms_max * 1e-3)
+        gemm_ms = kms[1] / max(1, ncalls)
+        flops_alg = 2.0 * K * K * B                      # 2 K^2 per chain, per launch
+        achieved = flops_alg / (gemm_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world, B),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8,
+                    "d2h_bytes_per_step": B * (S + model.OUT_COLS) * 8 + B * 4,
+                    "note": "mcd_eval_grad on pinned host buffers; per rank bytes"},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "kernel": "gemm_f64_dmma_kernel", "bound": "tensor", "achieved": achieved, "peak": FP64_NOMINAL_TFLOPS,
+                "unit": "TFLOP/s", "frac": achieved / FP64_NOMINAL_TFLOPS, "traffic": args.traffic,
+                "peak_source": "nominal FP64 (148 SMs x 64 FMA/clk x 1965 MHz); MEASURED_PEAKS.json has no FP64 entry; "
+                               "cublasDgemm on this shape measured 35.6 TFLOP/s executed (profiles/)",
+                "kernel_ms": gemm_ms, "algorithmic_flops_per_launch": flops_alg,
+                "step_share": {"residual_ms": kms[0] / max(1, ncalls), "contraction_ms": gemm_ms,
+                               "posterior_ms": kms[2] / max(1, ncalls)},
+            },
+            "clocks": clocks, "outputs_ok": ok,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as O
+            threads = O.max_threads()
+            rate, n, dt = cpu_port_rate(md, X, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{n} chains of the same workload in {dt:.1f} s (oracle CPU port, "
+                                              "std::thread over chains)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ev.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from ncu (profiles/), if known")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

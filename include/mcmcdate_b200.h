@@ -117,6 +117,10 @@ int mcd_eval_grad_device(mcd_handle* h, int32_t n_chains, const double* d_states
 /* bookkeeping */
 int64_t mcd_kernel_launches(const mcd_handle* h); /* kernels launched by this handle so far */
 int mcd_synchronize(mcd_handle* h);
+/* optional per-kernel timing with CUDA events on the launching stream (used by bench.py's roofline):
+ * ms[0] = residual kernel, ms[1] = FP64 contraction, ms[2] = posterior kernel, summed over n_calls */
+int mcd_set_kernel_timing(mcd_handle* h, int on);
+int mcd_kernel_times(mcd_handle* h, double* ms /*[3]*/, int64_t* n_calls);
 const char* mcd_version(void);
 
 #ifdef __cplusplus

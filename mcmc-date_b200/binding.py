@@ -20,7 +20,8 @@ _LIB = None
 EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
     "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_device",
-    "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version",
+    "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
+    "mcd_kernel_times",
 ]
 
 
@@ -70,6 +71,8 @@ def load_library():
     L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mcd_kernel_launches.argtypes = [vp]
     L.mcd_kernel_launches.restype = C.c_int64
+    L.mcd_set_kernel_timing.argtypes = [vp, C.c_int]
+    L.mcd_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_int64)]
     _LIB = L
     return L
 
@@ -188,6 +191,16 @@ class Evaluator:
 
     def kernel_launches(self) -> int:
         return int(self._L.mcd_kernel_launches(self.h))
+
+    def set_kernel_timing(self, on: bool):
+        self._check(self._L.mcd_set_kernel_timing(self.h, int(on)))
+
+    def kernel_times(self):
+        """-> (ms[3] summed over calls: residual, contraction, posterior; number of calls)"""
+        ms = np.zeros(3)
+        n = C.c_int64()
+        self._check(self._L.mcd_kernel_times(self.h, _dp(ms), C.byref(n)))
+        return ms, int(n.value)
 
     def synchronize(self):
         self._check(self._L.mcd_synchronize(self.h))

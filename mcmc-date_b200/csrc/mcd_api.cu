@@ -58,6 +58,9 @@ struct mcd_handle {
   std::mutex mtx;
   std::string err;
   int64_t launches = 0;
+  // optional per-kernel timing (CUDA events on the launching stream), see mcd_set_kernel_timing
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;  // 4 events per timed call: before K1, after K1, after GEMM, after K3
 };
 
 namespace {
@@ -121,13 +124,25 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   const double* xs = d_states + (size_t)c0 * M.S;
   double* dx = h->d_dx.as<double>() + (size_t)c0 * M.ldk;
   const double* y = h->d_y.as<double>() + (size_t)c0 * M.ldy;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (h->timing) {
+    for (int i = 0; i < 4; ++i) {
+      CU_TRY(h, cudaEventCreate(&ev[i]));
+      h->tev.push_back(ev[i]);
+    }
+    CU_TRY(h, cudaEventRecord(ev[0], st));
+  }
   if (M.lik == MCD_LIK_FULL) {
     if (small) residual_kernel<32><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
     else residual_kernel<256><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
+    if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
     const int np = (n + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
     CU_TRY(h, gemm_f64_dmma_launch(h->tmP, h->tmX, h->d_y.as<double>(), h->Mp, np, M.ldk, M.ldy, st, c0));
     h->launches += 2;
+  } else if (h->timing) {
+    CU_TRY(h, cudaEventRecord(ev[1], st));
   }
+  if (h->timing) CU_TRY(h, cudaEventRecord(ev[2], st));
   const size_t smem = POST_SMEM_FIXED + (GRAD ? (size_t)cpb * M.N * 8 : 0);
   double* o = d_out + (size_t)c0 * MCD_OUT_COLS;
   double* g = GRAD ? d_grad + (size_t)c0 * M.S : nullptr;
@@ -135,6 +150,7 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   if (small) posterior_kernel<32, GRAD><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n);
   else posterior_kernel<256, GRAD><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n);
   h->launches += 1;
+  if (h->timing) CU_TRY(h, cudaEventRecord(ev[3], st));
   CU_TRY(h, cudaGetLastError());
   return 0;
 }
@@ -407,6 +423,32 @@ int mcd_eval_grad_device(mcd_handle* h, int32_t n, const double* d_states, doubl
   return eval_device<true>(h, n, d_states, d_out, d_grad, d_status, stream);
 }
 int64_t mcd_kernel_launches(const mcd_handle* h) { return h ? h->launches : -1; }
+int mcd_set_kernel_timing(mcd_handle* h, int on) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  h->timing = on != 0;
+  return 0;
+}
+// Sum of per-kernel durations (ms) over all calls since timing was enabled / last read:
+// ms[0] = residual kernel, ms[1] = FP64 contraction, ms[2] = posterior kernel.  Synchronises.
+int mcd_kernel_times(mcd_handle* h, double* ms, int64_t* n_calls) {
+  if (!h || !ms || !n_calls) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaDeviceSynchronize());
+  ms[0] = ms[1] = ms[2] = 0.0;
+  *n_calls = (int64_t)h->tev.size() / 4;
+  for (size_t i = 0; i + 3 < h->tev.size(); i += 4) {
+    for (int j = 0; j < 3; ++j) {
+      float t = 0.f;
+      CU_TRY(h, cudaEventElapsedTime(&t, h->tev[i + j], h->tev[i + j + 1]));
+      ms[j] += t;
+    }
+  }
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  h->tev.clear();
+  return 0;
+}
 int mcd_synchronize(mcd_handle* h) {
   if (!h) return -1;
   CU_TRY(h, cudaSetDevice(h->device));
