@@ -1,0 +1,185 @@
+"""Host-side restatement of the reference's `prepare` step and of its auxiliary-data loaders --
+the data formats either side of the hot path.  numpy only.
+
+  prepare_from_treelist   app/Main.hs:159-307   tree list -> mean vector, Sigma^-1, ln det Sigma, mean tree
+  load_calibrations       lib/Mcmc/Tree/Prior/Node/Calibration.hs:186-319   CSV -> node index table
+  load_constraints        lib/Mcmc/Tree/Prior/Node/Constraint.hs:275-374    CSV -> node index table
+  load_braces             lib/Mcmc/Tree/Prior/Node/Brace.hs:152-192         JSON -> node index table
+  mean_root_height        lib/Mcmc/Tree/Prior/Node/Calibration.hs:324-339   getMeanRootHeight
+  initial_state           app/Definitions.hs:96-123                         initWith
+
+Restrictions (documented): the trees of the list must already be rooted at the outgroup
+and bifurcating (the reference re-roots with elynx `outgroup`, app/Main.hs:179-180; all of its own
+tests/*/data/test.treelist files already are); constraint redundancy/conflict pruning
+(Constraint.hs:306-374) is not restated -- constraints are taken as given.
+"""
+from __future__ import annotations
+
+import csv
+import io
+import json
+
+import numpy as np
+
+from . import model as _m
+from . import tree as _tree
+
+
+def _branches_row(parent, lengths):
+    """sumFirstTwo . getBranches (app/Tools.hs:36-48) for one tree."""
+    k = _tree.branch_index(parent)
+    row = np.zeros(len(parent) - 2)
+    np.add.at(row, k[1:], lengths[1:])
+    return row
+
+
+def prepare_from_treelist(text: str):
+    """-> dict(parent, names, mean, cov, precision, logdet_sigma, mean_lengths).
+    Drops the first len/6 trees (app/Main.hs:166-168), requires identical topology AND sub-tree
+    order (:184-190), mean/covariance like hmatrix meanCov (unbiased, 1/(n-1)), then invlndet (:230)."""
+    lines = [ln for ln in text.splitlines() if ln.strip()]
+    trees = [_tree.flatten_preorder(_tree.parse_newick(ln)) for ln in lines]
+    burn = len(trees) // 6
+    trees = trees[burn:]
+    parent, c0, c1, names, _ = trees[0]
+    for p, _, _, nm, _ in trees:
+        if not np.array_equal(p, parent) or nm != names:
+            raise ValueError("prepare: A single topology and equal sub tree orders are required.")
+    rows = np.array([_branches_row(p, ln) for p, _, _, _, ln in trees])
+    mean = rows.mean(axis=0)
+    cov = np.cov(rows, rowvar=False, ddof=1).reshape(len(mean), len(mean))
+    if np.min(np.diag(cov)) <= 0:
+        raise ValueError("prepare: Minimum variance is zero or negative.")
+    sign, logdet = np.linalg.slogdet(cov)
+    if sign != 1.0:
+        raise ValueError("prepare: Determinant of covariance matrix is negative?")
+    prec = np.linalg.inv(cov)
+    prec = 0.5 * (prec + prec.T)
+    all_len = np.array([ln for _, _, _, _, ln in trees]).mean(axis=0)  # mean tree incl. both root branches
+    return {"parent": parent, "names": names, "mean": mean, "cov": cov, "precision": prec,
+            "logdet_sigma": float(logdet), "mean_lengths": all_len}
+
+
+def _mrca(parent, names, leaf_a: str, leaf_b: str) -> int:
+    ia, ib = names.index(leaf_a), names.index(leaf_b)
+    anc = set()
+    x = ia
+    while x >= 0:
+        anc.add(x)
+        x = int(parent[x])
+    x = ib
+    while x not in anc:
+        x = int(parent[x])
+    return x
+
+
+def _opt(s):
+    s = s.strip()
+    return float(s) if s else None
+
+
+def load_calibrations(text: str, parent, names):
+    """CSV `Name,LeafA,LeafB,YoungAge,YoungProbabilityMass,OldAge,OldProbabilityMass` -> dict of arrays."""
+    node, lo, lop, hi, hip, nm = [], [], [], [], [], []
+    for row in csv.reader(io.StringIO(text)):
+        if not row or row[0].strip() == "Name":
+            continue
+        name, la, lb = row[0], row[1].strip(), row[2].strip()
+        a, pa, b, pb = (_opt(x) for x in row[3:7])
+        if (a is None) != (pa is None) or (b is None) != (pb is None) or (a is None and b is None):
+            raise ValueError(f"calibrationDataToCalibration: {name}: inconsistent boundaries")
+        if a is not None and b is not None and a >= b:
+            raise ValueError(f"calibrationDataToCalibration: {name}: Lower boundary larger equal upper boundary.")
+        nm.append(name)
+        node.append(_mrca(parent, names, la, lb))
+        lo.append(a if a is not None else 0.0)
+        lop.append(pa if pa is not None else 0.5)
+        hi.append(b if b is not None else np.inf)
+        hip.append(pb if pb is not None else 0.5)
+    return {"names": nm, "node": np.array(node, np.int32), "lo": np.array(lo), "lo_p": np.array(lop),
+            "hi": np.array(hi), "hi_p": np.array(hip)}
+
+
+def load_constraints(text: str, parent, names):
+    """CSV `Name,YoungerLeafA,YoungerLeafB,OlderLeafA,OlderLeafB,ProbabilityMass`."""
+    y, o, p, nm = [], [], [], []
+    for row in csv.reader(io.StringIO(text)):
+        if not row or row[0].strip() == "Name":
+            continue
+        nm.append(row[0])
+        y.append(_mrca(parent, names, row[1].strip(), row[2].strip()))
+        o.append(_mrca(parent, names, row[3].strip(), row[4].strip()))
+        p.append(float(row[5]))
+    return {"names": nm, "young": np.array(y, np.int32), "old": np.array(o, np.int32), "p": np.array(p)}
+
+
+def load_braces(text: str, parent, names):
+    """JSON list of {braceDataName, braceDataNodes: [[leafA, leafB], ...], braceDataStandardDeviation};
+    nodes sorted by index (Brace.hs:112)."""
+    off, idx, sd, nm = [0], [], [], []
+    for b in json.loads(text):
+        nodes = sorted(_mrca(parent, names, a, c) for a, c in b["braceDataNodes"])
+        if len(nodes) < 2:
+            raise ValueError("brace: need at least two nodes")
+        idx += nodes
+        off.append(len(idx))
+        sd.append(float(b["braceDataStandardDeviation"]))
+        nm.append(b["braceDataName"])
+    return {"names": nm, "off": np.array(off, np.int32), "node": np.array(idx, np.int32), "sd": np.array(sd)}
+
+
+def mean_root_height(cal) -> float:
+    """getMeanRootHeight: exactly one root calibration with a finite upper bound -> its mean, else 1.0."""
+    roots = [i for i, n in enumerate(cal["node"]) if n == 0]
+    if len(roots) != 1 or not np.isfinite(cal["hi"][roots[0]]):
+        return 1.0
+    i = roots[0]
+    return float((cal["lo"][i] + cal["hi"][i]) / 2.0) if cal["lo"][i] > 0 else float(cal["hi"][i] / 2.0)
+
+
+def ultrametric_heights(parent, lengths):
+    """makeUltrametric (extend terminal branches) + normalizeHeight + toHeightTreeUltrametric:
+    node height = longest path to a leaf below, divided by the root's; leaves 0."""
+    n = len(parent)
+    h = np.zeros(n)
+    for i in range(n - 1, 0, -1):
+        h[parent[i]] = max(h[parent[i]], h[i] + lengths[i])
+    c0, _ = _tree.children_from_parent(parent)
+    h[c0 < 0] = 0.0
+    return h / h[0]
+
+
+def initial_state(parent, mean_lengths):
+    """initWith (app/Definitions.hs:96-123): lambda = mu = H = m = v = 1, rates 1 with stem 0, heights
+    from the mean tree (zero branches replaced by the average)."""
+    ln = np.array(mean_lengths, float)
+    nz = ln[1:][ln[1:] > 0]
+    ln[1:][ln[1:] <= 0] = nz.mean() if len(nz) else 1.0
+    N = len(parent)
+    x = np.ones(5 + 2 * N)
+    x[3:3 + N] = ultrametric_heights(parent, ln)
+    x[5 + N] = 0.0
+    return x
+
+
+def model_from_files(treelist_text, calibrations_text=None, constraints_text=None, braces_text=None,
+                     clock_model=_m.UNCORRELATED_LOGNORMAL, likelihood=_m.LIK_FULL):
+    """Everything `getMcmcProps` assembles (app/Main.hs:370-457) -> (ModelDesc, prepared dict)."""
+    pr = prepare_from_treelist(treelist_text)
+    parent, names = pr["parent"], pr["names"]
+    cal = load_calibrations(calibrations_text, parent, names) if calibrations_text else None
+    con = load_constraints(constraints_text, parent, names) if constraints_text else None
+    br = load_braces(braces_text, parent, names) if braces_text else None
+    prec = pr["precision"] if likelihood == _m.LIK_FULL else np.diag(pr["cov"]).copy()
+    logdet = pr["logdet_sigma"] if likelihood == _m.LIK_FULL else float(np.sum(np.log(np.diag(pr["cov"]))))
+    kw = {}
+    if cal:
+        kw.update(cal_node=cal["node"], cal_lo=cal["lo"], cal_lo_p=cal["lo_p"], cal_hi=cal["hi"], cal_hi_p=cal["hi_p"])
+    if con:
+        kw.update(con_young=con["young"], con_old=con["old"], con_p=con["p"])
+    if br:
+        kw.update(brace_off=br["off"], brace_node=br["node"], brace_sd=br["sd"])
+    md = _m.ModelDesc(parent=parent, mean=pr["mean"], precision=prec, logdet_sigma=logdet, clock_model=clock_model,
+                      likelihood=likelihood, ht=mean_root_height(cal) if cal else 1.0, **kw)
+    pr.update(calibrations=cal, constraints=con, braces=br)
+    return md, pr

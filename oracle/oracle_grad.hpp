@@ -101,8 +101,34 @@ inline Result<double> eval_grad_double(const Model& M, const double* x, const ui
       else { *g_v += f_w * ti; G[i] += f_w * v; }
     }
   }
-  // birth-death B (telescoped closed form; exact also at la == mu)
-  {
+  // birth-death B
+  if (std::fabs(la - mu) < EPS_NEAR_CRITICAL) {
+    // near-critical regime: the reference switches to first-order formulas (BirthDeath.hs:90-126) whose
+    // value differs from the exact one by O(|la-mu|); differentiate THOSE (reverse sweep over the
+    // literal recursion; E is handed up from the LEFT child only, BirthDeath.hs:201-215)
+    *g_la += -1.0; *g_mu += -1.0;
+    const double d = la - mu;
+    std::vector<double> E(N + 1, 0.0);
+    for (int i = N - 1; i >= 1; --i) {  // children before parents; left child of i is i+1
+      const bool inner = M.child0[i] >= 0;
+      const double c = inner ? E[i + 1] : 0.0;
+      const double yy = (mu - c * la) * t[i];
+      E[i] = (c + yy) / (1.0 + yy);
+    }
+    double a = 0.0;  // adjoint of E_i
+    for (int i = 1; i < N; ++i) {
+      const bool inner = M.child0[i] >= 0;
+      if (i == M.child0[0] || i == M.child1[0]) a = 0.0;  // E of the root's children is unused
+      const double c = inner ? E[i + 1] : 0.0;
+      const double yy = (mu - c * la) * t[i];
+      const double gy = -2.0 / (1.0 + yy) + a * (1.0 - c) / ((1.0 + yy) * (1.0 + yy));
+      G[i] += -d / (1.0 - d * t[i]) + gy * (mu - c * la);
+      *g_la += -t[i] / (1.0 - d * t[i]) + gy * (-c * t[i]) + (inner ? 1.0 / la : 0.0);
+      *g_mu += t[i] / (1.0 - d * t[i]) + gy * t[i];
+      a = inner ? a / (1.0 + yy) + gy * (-la * t[i]) : 0.0;  // adjoint handed to the left child i+1
+    }
+  } else {
+    // telescoped closed form of the D/E recursion
     int n_inner_nonroot = 0;
     *g_la += -1.0; *g_mu += -1.0;
     LnP1 p0 = ln_p1(la, mu, s.h(0));

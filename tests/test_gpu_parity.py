@@ -1,0 +1,222 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs, against the committed golden vectors, and -- at BASELINE.json's full size -- through
+size-independent properties.  Tolerance: 1e-10 relative (north_star) for floating point, exact for
+index maps and status words."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mcmc_date_b200 import binding, model, synth
+from oracle import oracle as O
+from util import FIXTURES, TOL, grad_relerr, load_fixture, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _finite_rows(out):
+    return np.isfinite(out[:, 6])
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+@pytest.mark.parametrize("clock", [0, 1, 2, 3])
+def test_fixture_parity_value_gradient_status(name, clock):
+    """reference datasets (configs[0..3]): valid states, the reference's initial state, edge states"""
+    md, z = load_fixture(name, clock)
+    X = z["states"]
+    ev = binding.Evaluator(md)
+    out, grad, st = ev.eval_grad(X)
+    # committed golden vectors
+    assert np.array_equal(st, z[f"status_{clock}"]), (st, z[f"status_{clock}"])
+    assert relerr(out[:, :7], z[f"out_{clock}"]).max() < TOL
+    fin = _finite_rows(z[f"out_{clock}"])
+    assert fin.sum() >= int(z["n_valid"])
+    assert grad_relerr(grad[fin], z[f"grad_{clock}"][fin]).max() < TOL
+    # dual-number gradient truth of the first four states
+    assert grad_relerr(grad[:4], z[f"graddual_{clock}"]).max() < TOL
+    # live oracle
+    orc = O.Oracle(md)
+    oo, og, ost = orc.eval_grad(X)
+    assert np.array_equal(st, ost)
+    assert relerr(out[:, :7], oo).max() < TOL
+    assert grad_relerr(grad[fin], og[fin]).max() < TOL
+    # masked entries are exactly zero
+    assert (grad[:, orc.mask == 0] == 0).all()
+    # value-only entry point returns the same numbers
+    out2, st2 = ev.eval(X)
+    assert np.array_equal(out2[:, :7], out[:, :7], equal_nan=True) and np.array_equal(st2, st)
+    ev.close()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_index_maps_bit_exact(name):
+    md, z = load_fixture(name)
+    ev = binding.Evaluator(md)
+    orc = O.Oracle(md)
+    assert np.array_equal(ev.branch_index(), z["branch_index"])
+    assert np.array_equal(ev.branch_index(), orc.branch_index())
+    assert np.array_equal(ev.mask(), z["mask"])
+    x = z["states"][2]
+    th = ev.to_vector(x)
+    assert np.array_equal(th, orc.to_vector(x))
+    assert np.array_equal(ev.from_vector(x, th * 2), orc.from_vector(x, th * 2))
+    assert ev.D == int(z["mask"].sum())
+    ev.close()
+
+
+@pytest.mark.parametrize("lik", [model.LIK_UNIVARIATE, model.LIK_NONE])
+@pytest.mark.parametrize("clock", [1, 2])
+def test_other_likelihood_kinds(lik, clock):
+    md, z = load_fixture("24-leaves-braces", clock, likelihood=lik)
+    X = z["states"][: int(z["n_valid"])]
+    ev = binding.Evaluator(md)
+    out, grad, st = ev.eval_grad(X)
+    oo, og, ost = O.Oracle(md).eval_grad(X)
+    assert np.array_equal(st, ost)
+    assert relerr(out[:, :7], oo).max() < TOL and grad_relerr(grad, og).max() < TOL
+    ev.close()
+
+
+@pytest.mark.parametrize("n_leaves,B,clock", [(2, 5, 1), (3, 9, 0), (60, 300, 2), (200, 130, 3), (49, 257, 1)])
+def test_synthetic_trees_ragged_batches(n_leaves, B, clock):
+    """random topologies incl. the smallest trees (K = 1, 3), batches that are not multiples of the tile"""
+    md, h = synth.synthetic_model(n_leaves, seed=100 + n_leaves, clock_model=clock, n_cal=min(3, n_leaves - 1),
+                                  n_con=2 if n_leaves > 10 else 0, n_brace=1 if n_leaves > 10 else 0)
+    X = synth.synthetic_states(md, h, B)
+    ev = binding.Evaluator(md)
+    out, grad, st = ev.eval_grad(X)
+    oo, og, ost = O.Oracle(md).eval_grad(X, nthreads=4)
+    assert np.array_equal(st, ost)
+    assert relerr(out[:, :7], oo).max() < TOL and grad_relerr(grad, og).max() < TOL
+    ev.close()
+
+
+def test_thousand_leaf_tree_against_oracle():
+    """configs[4] shape at a batch the oracle finishes in seconds"""
+    md, h = synth.synthetic_model(1000, seed=synth.BASE_SEED + 4, n_cal=16, n_con=8, n_brace=4)
+    X = synth.synthetic_states(md, h, 300)
+    ev = binding.Evaluator(md)
+    out, grad, st = ev.eval_grad(X)
+    orc = O.Oracle(md)
+    oo, og, ost = orc.eval_grad(X, nthreads=8)
+    assert np.array_equal(st, ost) and (st == 0).all()
+    assert relerr(out[:, :7], oo).max() < TOL
+    assert grad_relerr(grad, og).max() < TOL
+    # gradient truth at this size: one dual-number pass along a random direction
+    u = np.random.default_rng(5).normal(size=md.state_len) * orc.mask
+    dd, _ = orc.dir_derivative(X[0], u)
+    assert abs(grad[0] @ u - dd) <= TOL * max(1.0, abs(dd))
+    ev.close()
+
+
+@pytest.fixture(scope="module")
+def full_size():
+    """BASELINE.json's full size: 1000-leaf tree, 8192 chains"""
+    md, h = synth.synthetic_model(1000, seed=synth.BASE_SEED + 4, n_cal=16, n_con=8, n_brace=4)
+    X = synth.synthetic_states(md, h, 8192, seed=synth.BASE_SEED + 5)
+    ev = binding.Evaluator(md, max_batch=8192)
+    out, grad, st = ev.eval_grad(X)
+    yield md, X, ev, out, grad, st
+    ev.close()
+
+
+def test_full_size_deterministic_and_chunk_invariant(full_size):
+    md, X, ev, out, grad, st = full_size
+    assert np.isfinite(out[:, :7]).all() and (st == 0).all()
+    out2, grad2, st2 = ev.eval_grad(X)
+    assert np.array_equal(out, out2) and np.array_equal(grad, grad2)            # bit-wise reproducible
+    # a chain's result does not depend on which batch / tile / chunk it travels in
+    sub = slice(1000, 1300)
+    o3, g3, _ = ev.eval_grad(X[sub])
+    assert np.array_equal(o3, out[sub]) and np.array_equal(g3, grad[sub])
+    perm = np.random.default_rng(0).permutation(len(X))[:2048]
+    o4, g4, _ = ev.eval_grad(X[perm])
+    assert np.array_equal(o4, out[perm]) and np.array_equal(g4, grad[perm])
+    o5, s5 = ev.eval(X)
+    assert np.array_equal(o5[:, :7], out[:, :7])
+
+
+def test_full_size_spot_check_against_oracle(full_size):
+    md, X, ev, out, grad, st = full_size
+    idx = np.random.default_rng(1).choice(len(X), size=24, replace=False)
+    oo, og, ost = O.Oracle(md).eval_grad(X[idx], nthreads=8)
+    assert relerr(out[idx, :7], oo).max() < TOL
+    assert grad_relerr(grad[idx], og).max() < TOL
+
+
+def test_full_size_gradient_is_the_derivative_of_the_value(full_size):
+    """central differences of the GPU's own ln posterior along random directions"""
+    md, X, ev, out, grad, st = full_size
+    mask = ev.mask().astype(float)
+    rng = np.random.default_rng(2)
+    idx = rng.choice(len(X), size=64, replace=False)
+    U = rng.normal(size=(64, md.state_len)) * mask
+    U /= np.linalg.norm(U, axis=1, keepdims=True)
+    eps = 1e-6
+    Xp, Xm = X[idx] + eps * U * np.abs(X[idx]), X[idx] - eps * U * np.abs(X[idx])
+    op, _ = ev.eval(Xp)
+    om, _ = ev.eval(Xm)
+    fd = (op[:, 6] - om[:, 6]) / (2 * eps)
+    an = np.einsum("ij,ij->i", grad[idx], U * np.abs(X[idx]))
+    assert np.abs(fd - an).max() <= 2e-5 * np.maximum(1.0, np.abs(an)).max()
+
+
+def test_full_size_quadratic_form_scaling(full_size):
+    """lnL is a quadratic form in the distances: scaling m by c scales d by c, so
+    lnL(c) - const = -1/2 (c d - mu)^T P (c d - mu) must be an exact parabola in c"""
+    md, X, ev, out, grad, st = full_size
+    N = md.n_nodes
+    Xs = np.repeat(X[:8], 3, axis=0)
+    c = np.tile([0.5, 1.0, 1.5], 8)
+    Xs[:, 3 + N] *= c
+    o, _ = ev.eval(Xs)
+    L = o[:, 4].reshape(8, 3)
+    second = L[:, 0] - 2 * L[:, 1] + L[:, 2]          # = -(0.5)^2 d^T P d  (constant second difference)
+    Xt = np.repeat(X[:8], 3, axis=0)
+    c2 = np.tile([1.0, 1.5, 2.0], 8)
+    Xt[:, 3 + N] *= c2
+    o2, _ = ev.eval(Xt)
+    L2 = o2[:, 4].reshape(8, 3)
+    second2 = L2[:, 0] - 2 * L2[:, 1] + L2[:, 2]
+    assert np.abs(second - second2).max() <= 1e-9 * np.abs(second).max()
+
+
+def test_device_entry_points_match_host_entry_points(full_size):
+    import torch
+    md, X, ev, out, grad, st = full_size
+    B = 2048
+    dev = torch.device("cuda", 0)
+    d_x = torch.from_numpy(X[:B]).to(dev)
+    d_out = torch.empty((B, model.OUT_COLS), dtype=torch.float64, device=dev)
+    d_grad = torch.empty((B, md.state_len), dtype=torch.float64, device=dev)
+    d_st = torch.empty(B, dtype=torch.int32, device=dev)
+    n0 = ev.kernel_launches()
+    ev.eval_grad_device(B, d_x.data_ptr(), d_out.data_ptr(), d_grad.data_ptr(), d_st.data_ptr(),
+                        torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert ev.kernel_launches() - n0 == 3          # residual, contraction, posterior
+    assert np.array_equal(d_out.cpu().numpy(), out[:B]) and np.array_equal(d_grad.cpu().numpy(), grad[:B])
+    assert np.array_equal(d_st.cpu().numpy(), st[:B])
+
+
+def test_error_behaviour():
+    md, z = load_fixture("12-leaves-variable-rate")
+    ev = binding.Evaluator(md)
+    L = binding.load_library()
+    # empty batch is fine; null buffers are an error with a message, not a crash
+    assert L.mcd_eval(ev.h, 0, None, None, None) == 0
+    assert L.mcd_eval(ev.h, 4, None, None, None) != 0 and b"null" in L.mcd_last_error(ev.h)
+    ev.close()
+    # model validation mirrors the reference's load-time `error`s
+    def expect_fail(**kw):
+        base = dict(parent=md.parent, mean=md.mean, precision=md.precision, logdet_sigma=md.logdet_sigma, ht=md.ht)
+        base.update(kw)
+        with pytest.raises(RuntimeError):
+            binding.Evaluator(model.ModelDesc(**base))
+    expect_fail(ht=0.0)                                                   # exponential: rate <= 0
+    expect_fail(brace_off=[0, 2], brace_node=[2, 5], brace_sd=[0.0])      # braceSoftF: sd <= 0
+    expect_fail(con_young=[2], con_old=[16], con_p=[1.5])                 # probabilityMass
+    p = md.precision.copy()
+    p[0, 1] += 1.0
+    expect_fail(precision=p)                                              # not symmetric
+    expect_fail(parent=np.array([-1, 0, 1, 1, 1, 0, 0], np.int32), mean=np.zeros(5), precision=np.eye(5))  # multifurcating

@@ -1,0 +1,167 @@
+"""Host-side logic (no GPU): index maps bit-exact against the literal restatement, mask / vector
+packing, Newick + prepare + loaders, and that the C-ABI library loads and exports every symbol
+include/mcmcdate_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from mcmc_date_b200 import binding, model, prepare, sharding, synth, tree
+from oracle import oracle as O
+from util import FIXTURES, load_fixture
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model_for(parent):
+    n = len(parent)
+    return model.ModelDesc(parent=parent, mean=np.zeros(n - 2), precision=np.zeros(0), logdet_sigma=0.0,
+                           likelihood=model.LIK_NONE)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_branch_index_closed_form_is_bit_exact(seed):
+    """closed form of getBranches + sumFirstTwo == literal list construction"""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 60))
+    parent = tree.random_topology(n, rng)
+    md = _model_for(parent)
+    lit = O.Oracle(md).branch_index()
+    assert np.array_equal(tree.branch_index(parent), lit)
+    assert sorted(set(lit[1:])) == list(range(len(parent) - 2))   # onto 0..K-1
+    assert (lit[1:] == 0).sum() == 2                              # exactly the two root branches merge
+
+
+def test_branch_index_edge_cases():
+    # two leaves: K = 1
+    p = np.array([-1, 0, 0], np.int32)
+    assert tree.branch_index(p).tolist() == [-1, 0, 0]
+    # left root child is a leaf: range 2 <= i <= s_l is empty
+    p = np.array([-1, 0, 0, 2, 2], np.int32)
+    assert tree.branch_index(p).tolist() == [-1, 0, 0, 1, 2]
+    assert np.array_equal(O.Oracle(_model_for(p)).branch_index(), tree.branch_index(p))
+    with pytest.raises(ValueError):
+        tree.branch_index(np.array([-1, 0, 1, 1], np.int32))  # root not bifurcating
+
+
+def test_newick_roundtrip_and_preorder():
+    t = tree.parse_newick("((f:0.3,e:0.26):0.19,((d:0.5,c:0.01)x:0.54,(b:0.3,a:0.26):0.37):0)[c];")
+    parent, c0, c1, names, lens = tree.flatten_preorder(t)
+    assert parent.tolist() == [-1, 0, 1, 1, 0, 4, 5, 5, 4, 8, 8]
+    assert names[2] == "f" and names[5] == "x" and lens[4] == 0.0
+    assert c0.tolist()[:2] == [1, 2] and c1.tolist()[0] == 4
+    h = tree.node_heights_from_lengths(parent, np.array([0, 1, 1, 1, 1, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5]))
+    assert h[0] == 1.0
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_mask_and_vector_packing(name):
+    """getMask / toVector / fromVectorWith (app/Hamiltonian.hs:33-60): free = everything except root
+    height, leaf heights, rate stem, and H unless calibrations exist; theta is in REVERSED order."""
+    md, z = load_fixture(name)
+    orc = O.Oracle(md)
+    N = md.n_nodes
+    mask = orc.mask
+    assert np.array_equal(mask, z["mask"])
+    n = md.n_leaves
+    D = 2 + (1 if md.calibrations_available else 0) + (n - 2) + 2 + (N - 1)
+    assert mask.sum() == D
+    assert mask[3] == 0 and mask[5 + N] == 0 and mask[0] == mask[1] == mask[3 + N] == mask[4 + N] == 1
+    x = z["states"][1]
+    th = orc.to_vector(x)
+    assert np.array_equal(th, x[mask.astype(bool)][::-1])
+    th2 = th + 1.0
+    y = orc.from_vector(x, th2)
+    assert np.array_equal(y[mask.astype(bool)], x[mask.astype(bool)] + 1.0)
+    assert np.array_equal(y[~mask.astype(bool)], x[~mask.astype(bool)])
+
+
+def test_prepare_matches_numpy_and_is_invertible():
+    path = "/root/reference/tests/12-leaves-variable-rate/data/test.treelist"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present (GPU box)")
+    pr = prepare.prepare_from_treelist(open(path).read())
+    md, z = load_fixture("12-leaves-variable-rate")
+    assert np.array_equal(pr["parent"], md.parent)
+    assert np.allclose(pr["mean"], md.mean, rtol=0, atol=0)
+    assert np.allclose(pr["precision"] @ pr["cov"], np.eye(21), atol=1e-8)
+    assert np.allclose(pr["precision"], md.precision, rtol=1e-13, atol=0)
+
+
+def test_loaders_pin_survey_integer_fixtures():
+    """node indices derived in SURVEY.md 8c"""
+    _, z12 = load_fixture("12-leaves-variable-rate")
+    assert z12["parent"].tolist() == [-1, 0, 1, 2, 2, 1, 5, 5, 7, 8, 8, 7, 0, 12, 13, 14, 14, 16, 16, 13, 12, 20, 20]
+    assert z12["cal_node"].tolist() == [0, 14, 2] and z12["con_young"].tolist() == [2] and z12["con_old"].tolist() == [16]
+    assert float(z12["ht"]) == 1050.0
+    _, z24 = load_fixture("24-leaves-braces")
+    assert len(z24["parent"]) == 47 and np.nonzero(z24["parent"] == 0)[0].tolist() == [1, 24]
+    assert z24["cal_node"].tolist() == [0, 25, 12]
+    assert z24["con_young"].tolist() == [24, 26] and z24["con_old"].tolist() == [9, 19]
+    assert z24["brace_node"].tolist() == [6, 36] and float(z24["brace_sd"][0]) == 1e-4
+    _, z6 = load_fixture("06-leaves-constant-rate")
+    assert z6["parent"].tolist() == [-1, 0, 1, 1, 0, 4, 5, 5, 4, 8, 8] and z6["cal_node"].tolist() == [0]
+    _, z7 = load_fixture("mtcdnapri-7-leaves")
+    assert len(z7["parent"]) == 13 and float(z7["ht"]) == 50.0
+
+
+def test_initial_state_is_valid():
+    md, z = load_fixture("24-leaves-braces")
+    x0 = z["states"][0]
+    N = md.n_nodes
+    h = x0[3:3 + N]
+    assert h[0] == 1.0 and (h[md.child0 < 0] == 0).all()
+    assert (h[md.parent[1:]] - h[1:] > 0).all()
+    out, st = O.Oracle(md).eval(x0[None])
+    assert np.isfinite(out[0, 6]) and st[0] == model.ST_NEARCRIT  # initWith has lambda == mu == 1
+
+
+def test_synthetic_generators_are_seeded_and_valid():
+    md, h = synth.synthetic_model(50, seed=3, n_cal=4, n_con=3, n_brace=2)
+    md2, h2 = synth.synthetic_model(50, seed=3, n_cal=4, n_con=3, n_brace=2)
+    assert np.array_equal(md.parent, md2.parent) and np.array_equal(md.precision, md2.precision)
+    assert np.array_equal(md.precision, md.precision.T)
+    assert np.linalg.eigvalsh(md.precision).min() > 0
+    X = synth.synthetic_states(md, h, 32)
+    N = md.n_nodes
+    t = X[:, 3 + md.parent[1:]] - X[:, 3 + np.arange(1, N)]
+    assert (t > 0).all()
+    out, st = O.Oracle(md).eval(X)
+    assert np.isfinite(out).all() and (st == 0).all()
+
+
+def test_shard_ranges_partition_chains():
+    for B, W in [(8192, 8), (64, 8), (10, 4), (7, 3)]:
+        spans = [sharding.shard_range(B, W, r) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """no compute calls: dlopen + symbol lookup only"""
+    header = open(os.path.join(ROOT, "include", "mcmcdate_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mcd_[a-z_]+)\s*\(", header)))
+    assert "mcd_eval_grad" in declared and "mcd_create" in declared
+    assert os.path.exists(binding.LIB_PATH), "libmcmcdate_b200.so not built"
+    lib = ctypes.CDLL(binding.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(binding.EXPORTS) == declared
+    L = binding.load_library()
+    assert b"sm_100a" in L.mcd_version()
+
+
+def test_create_fails_loudly_without_gpu_or_with_bad_model():
+    """no CPU fallback: mcd_create reports an error instead of evaluating on the host"""
+    import torch
+    md, _ = load_fixture("06-leaves-constant-rate")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+            binding.Evaluator(md)
+    bad = model.ModelDesc(parent=np.array([-1, 0, 1, 1], np.int32), mean=np.zeros(2), precision=np.eye(2),
+                          logdet_sigma=0.0)
+    with pytest.raises(RuntimeError):
+        binding.Evaluator(bad)

@@ -1,0 +1,50 @@
+"""N > 1 path on CPU: world_size-2 gloo processes shard the chains, all-gather the MC3 swap statistics
+and reach identical swap decisions (the GPU evaluation itself needs no collective)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from mcmc_date_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B = 64
+    a, b = sharding.shard_range(B, world, rank)
+    rng = np.random.default_rng(0)
+    stats_all = rng.normal(size=(B, 2)) * 10.0          # stands in for (ln prior, ln lik) of every chain
+    local = torch.from_numpy(stats_all[a:b].copy())
+    gathered = sharding.allgather_swap_stats(local, world, dist).numpy()
+    betas = np.linspace(1.0, 0.3, B)
+    swaps = sharding.mc3_swap_decisions(gathered.copy(), betas, n_swaps=3, seed=42)
+    q.put((rank, a, b, gathered.tolist(), swaps))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allgather_and_swaps():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, a0, b0, g0, s0), (r1, a1, b1, g1, s1) = res
+    assert (a0, b0, a1, b1) == (0, 32, 32, 64)
+    rng = np.random.default_rng(0)
+    full = rng.normal(size=(64, 2)) * 10.0
+    assert np.array_equal(np.array(g0), full) and np.array_equal(np.array(g1), full)
+    assert s0 == s1
