@@ -46,7 +46,7 @@ struct mcd_handle {
   std::vector<uint8_t> mask;
   // device model
   DevModel dm{};
-  DevBuf d_parent, d_child1, d_mu, d_var, d_P;
+  DevBuf d_parent, d_child1, d_inner, d_mu, d_var, d_P;
   DevBuf d_cal_node, d_cal_lo, d_cal_hi, d_cal_slo, d_cal_shi, d_con_y, d_con_o, d_con_s, d_br_off, d_br_node, d_br_sd,
       d_inc_off, d_inc_ent;
   CUtensorMap tmP{}, tmX{};
@@ -358,6 +358,13 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   M.con_y = h->d_con_y.as<int>(); M.con_o = h->d_con_o.as<int>(); M.con_s = h->d_con_s.as<double>();
   M.br_off = h->d_br_off.as<int>(); M.br_node = h->d_br_node.as<int>(); M.br_sd = h->d_br_sd.as<double>();
   M.inc_off = h->d_inc_off.as<int>(); M.inc_ent = h->d_inc_ent.as<int2>();
+  {
+    std::vector<int4> inner;
+    for (int i = 1; i < N; ++i)
+      if (child0[i] >= 0) inner.push_back(make_int4(i, child1[i], inc_off[i], inc_off[i + 1] - inc_off[i]));
+    if (upload(h, h->d_inner, inner.data(), inner.size())) return bail("upload inner-node list");
+    M.inner = h->d_inner.as<int4>();
+  }
 
   for (int i = 0; i < N_STREAMS; ++i)
     if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");

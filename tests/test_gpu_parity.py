@@ -211,7 +211,7 @@ def test_error_behaviour():
     def expect_fail(**kw):
         base = dict(parent=md.parent, mean=md.mean, precision=md.precision, logdet_sigma=md.logdet_sigma, ht=md.ht)
         base.update(kw)
-        with pytest.raises(RuntimeError):
+        with pytest.raises((RuntimeError, ValueError)):
             binding.Evaluator(model.ModelDesc(**base))
     expect_fail(ht=0.0)                                                   # exponential: rate <= 0
     expect_fail(brace_off=[0, 2], brace_node=[2, 5], brace_sd=[0.0])      # braceSoftF: sd <= 0
@@ -220,3 +220,4 @@ def test_error_behaviour():
     p[0, 1] += 1.0
     expect_fail(precision=p)                                              # not symmetric
     expect_fail(parent=np.array([-1, 0, 1, 1, 1, 0, 0], np.int32), mean=np.zeros(5), precision=np.eye(5))  # multifurcating
+    expect_fail(parent=np.array([-1, 0, 1, 2, 2], np.int32), mean=np.zeros(3), precision=np.eye(3))       # unary root
