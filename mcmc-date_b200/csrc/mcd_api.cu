@@ -143,7 +143,7 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     CU_TRY(h, cudaEventRecord(ev[1], st));
   }
   if (h->timing) CU_TRY(h, cudaEventRecord(ev[2], st));
-  const size_t smem = POST_SMEM_FIXED + (GRAD ? (size_t)cpb * M.N * 16 : 0);
+  const size_t smem = POST_SMEM_FIXED + (size_t)cpb * M.N * 8 * (GRAD ? 4 : 3);
   double* o = d_out + (size_t)c0 * MCD_OUT_COLS;
   double* g = GRAD ? d_grad + (size_t)c0 * M.S : nullptr;
   int32_t* s = d_status + c0;
@@ -369,9 +369,10 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   for (int i = 0; i < N_STREAMS; ++i)
     if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
   // posterior kernels may need > 48 KiB dynamic smem on large trees
-  const int post_smem = POST_SMEM_FIXED + (N <= SMALL_TREE_MAX_NODES ? (POST_THREADS / 32) * N * 16 : N * 16);
-  if (post_smem > 200 * 1024) return bail("mcd_create: tree too large for the gradient kernel's shared memory (N > 12500)");
+  const int post_smem = POST_SMEM_FIXED + (N <= SMALL_TREE_MAX_NODES ? (POST_THREADS / 32) * N * 32 : N * 32);
+  if (post_smem > 200 * 1024) return bail("mcd_create: tree too large for the gradient kernel's shared memory (N > 6000)");
   cudaFuncSetAttribute(posterior_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(posterior_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (d->max_batch > 0 && ensure_capacity(h, d->max_batch, false, false)) return bail("allocating work buffers");
   if (cudaDeviceSynchronize() != cudaSuccess) return bail("device error during create");
   *out = h;
