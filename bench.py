@@ -222,11 +222,30 @@ def run_gpu(args):
     h_grad = torch.empty((B, S), dtype=torch.float64).pin_memory()
     h_status = torch.empty(B, dtype=torch.int32).pin_memory()
 
-    def e2e_step():
+    def e2e_state_step():
         ev.eval_grad_ptr(B, h_states.data_ptr(), h_out.data_ptr(), h_grad.data_ptr(), h_status.data_ptr())
 
+    # HMC form (what NUTS exchanges, app/Hamiltonian.hs:49-60): packed position vectors in, packed gradient out
+    D = ev.D
+    mask = ev.mask().astype(bool)
+    h_theta = torch.from_numpy(np.ascontiguousarray(X[:, mask][:, ::-1])).pin_memory()
+    h_base = torch.from_numpy(X[0].copy()).pin_memory()
+    h_gtheta = torch.empty((B, D), dtype=torch.float64).pin_memory()
+    h_out2 = torch.empty((B, model.OUT_COLS), dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        ev.eval_grad_theta_ptr(B, h_theta.data_ptr(), h_base.data_ptr(), h_out2.data_ptr(), h_gtheta.data_ptr(),
+                               h_status.data_ptr())
+
     for _ in range(2):
+        e2e_state_step()
         e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_state_step()
+    torch.cuda.synchronize()
+    e2e_state_s = time.perf_counter() - t0
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -236,12 +255,14 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     # parity guard: the timed outputs are the real thing (finite, and equal through both entry points)
     ok = bool(torch.isfinite(d_out[:, 6]).all().item()) and bool(
-        torch.allclose(d_out.cpu()[:, :7], h_out[:, :7], rtol=0, atol=0, equal_nan=True))
+        torch.allclose(d_out.cpu()[:, :7], h_out[:, :7], rtol=0, atol=0, equal_nan=True)) and bool(
+        torch.equal(h_out2, h_out)) and bool(torch.equal(h_gtheta, torch.from_numpy(
+            np.ascontiguousarray(h_grad.numpy()[:, mask][:, ::-1]))))
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, e2e_state_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, e2e_state_ms_max = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         total = B * world
         value = total * args.steps / (ms_max * 1e-3)
@@ -253,9 +274,14 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, B),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * 8,
-                    "d2h_bytes_per_step": B * (S + model.OUT_COLS) * 8 + B * 4,
-                    "note": "mcd_eval_grad on pinned host buffers; per rank bytes"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 8 + S * 8,
+                    "d2h_bytes_per_step": B * (D + model.OUT_COLS) * 8 + B * 4,
+                    "note": "mcd_eval_grad_theta on pinned host buffers (HMC position vectors in, packed gradient + "
+                            "ln-posterior parts out); bytes per rank",
+                    "full_state_api": {"value": total * args.steps / (e2e_state_ms_max * 1e-3), "unit": UNIT,
+                                       "h2d_bytes_per_step": B * S * 8,
+                                       "d2h_bytes_per_step": B * (S + model.OUT_COLS) * 8 + B * 4,
+                                       "note": "mcd_eval_grad (full canonical states in, full-layout gradient out)"}},
             "gpu_launches": int(launches),
             "roofline": {
                 "kernel": "gemm_f64_dmma_kernel", "bound": "tensor", "achieved": achieved, "peak": FP64_NOMINAL_TFLOPS,

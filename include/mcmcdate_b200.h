@@ -107,6 +107,14 @@ int mcd_eval_grad(mcd_handle* h, int32_t n_chains, const double* states /*[B][S]
                   double* out /*[B][MCD_OUT_COLS]*/, double* grad /*[B][S], masked entries 0*/,
                   int32_t* status /*[B]*/);
 
+/* HMC form: positions are the masked, reversed-order vectors of toVector (app/Hamiltonian.hs:49-53),
+ * theta[B][D]; fixed entries (root / leaf heights, rate stem, H without calibrations) come from one
+ * shared base_state[S] (fromVectorWith); the gradient comes back packed the same way.  Moves D instead
+ * of S doubles per chain over PCIe in each direction. */
+int mcd_eval_grad_theta(mcd_handle* h, int32_t n_chains, const double* theta /*[B][D]*/,
+                        const double* base_state /*[S]*/, double* out /*[B][MCD_OUT_COLS]*/,
+                        double* grad_theta /*[B][D]*/, int32_t* status /*[B]*/);
+
 /* evaluation with DEVICE buffers already resident in HBM (no copies); `stream` is a cudaStream_t
  * or NULL.  Asynchronous: returns after enqueueing. */
 int mcd_eval_device(mcd_handle* h, int32_t n_chains, const double* d_states, double* d_out,

@@ -19,7 +19,8 @@ _LIB = None
 
 EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
-    "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_device",
+    "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta",
+    "mcd_eval_device",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
     "mcd_kernel_times",
 ]
@@ -67,6 +68,7 @@ def load_library():
     L.mcd_from_vector.argtypes = [vp, dp, dp, dp]
     L.mcd_eval.argtypes = [vp, i32, dp, dp, ip]
     L.mcd_eval_grad.argtypes = [vp, i32, dp, dp, dp, ip]
+    L.mcd_eval_grad_theta.argtypes = [vp, i32, dp, dp, dp, dp, ip]
     L.mcd_eval_device.argtypes = [vp, i32, vp, vp, vp, vp]
     L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mcd_kernel_launches.argtypes = [vp]
@@ -172,6 +174,22 @@ class Evaluator:
         status = np.empty(B, np.int32) if status is None else status
         self._check(self._L.mcd_eval_grad(self.h, B, _dp(X), _dp(out), _dp(grad), _ip(status)))
         return out, grad, status
+
+    def eval_grad_theta(self, theta: np.ndarray, base_state: np.ndarray, out=None, grad_theta=None, status=None):
+        """HMC form: theta [B, D] (masked, reversed order) + one shared base state -> out, d/dtheta, status"""
+        T = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, self.D)
+        base = np.ascontiguousarray(base_state, dtype=np.float64)
+        B = T.shape[0]
+        out = np.empty((B, _m.OUT_COLS)) if out is None else out
+        grad_theta = np.empty((B, self.D)) if grad_theta is None else grad_theta
+        status = np.empty(B, np.int32) if status is None else status
+        self._check(self._L.mcd_eval_grad_theta(self.h, B, _dp(T), _dp(base), _dp(out), _dp(grad_theta), _ip(status)))
+        return out, grad_theta, status
+
+    def eval_grad_theta_ptr(self, B: int, theta_ptr: int, base_ptr: int, out_ptr: int, gtheta_ptr: int, status_ptr: int):
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        self._check(self._L.mcd_eval_grad_theta(self.h, B, C.cast(theta_ptr, dp), C.cast(base_ptr, dp), C.cast(out_ptr, dp),
+                                                C.cast(gtheta_ptr, dp), C.cast(status_ptr, ip)))
 
     # raw-pointer entry points (host or device addresses as ints) ---------------------------
     def eval_grad_ptr(self, B: int, states_ptr: int, out_ptr: int, grad_ptr: int, status_ptr: int):

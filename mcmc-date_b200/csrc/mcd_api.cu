@@ -13,6 +13,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -27,8 +28,11 @@ using namespace mcd;
 namespace {
 
 std::string g_create_error;
-constexpr int N_STREAMS = 3;
+constexpr int N_STREAMS = 4;
 constexpr int SMALL_TREE_MAX_NODES = 96;  // warp-per-chain kernels up to this many nodes
+#ifndef POST_MINB
+#define POST_MINB 4
+#endif
 
 struct DevBuf {
   void* p = nullptr;
@@ -54,10 +58,12 @@ struct mcd_handle {
   int cap = 0;
   DevBuf d_dx, d_y;               // internal: residuals and P.dx
   DevBuf d_states, d_out, d_grad, d_status;  // staging for the host-buffer API
-  cudaStream_t streams[N_STREAMS] = {nullptr, nullptr, nullptr};
+  DevBuf d_theta, d_gtheta, d_base, d_tidx, d_sidx;  // theta-packed API
+  cudaStream_t streams[N_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
   std::mutex mtx;
   std::string err;
   int64_t launches = 0;
+  int n_sms = 148;
   // optional per-kernel timing (CUDA events on the launching stream), see mcd_set_kernel_timing
   bool timing = false;
   std::vector<cudaEvent_t> tev;  // 4 events per timed call: before K1, after K1, after GEMM, after K3
@@ -89,7 +95,7 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
   int need = (n_chains + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
   if (need > h->cap) {
     CU_TRY(h, cudaDeviceSynchronize());
-    for (DevBuf* b : {&h->d_dx, &h->d_y, &h->d_states, &h->d_out, &h->d_grad, &h->d_status}) {
+    for (DevBuf* b : {&h->d_dx, &h->d_y, &h->d_states, &h->d_out, &h->d_grad, &h->d_status, &h->d_theta, &h->d_gtheta}) {
       if (b->p) cudaFree(b->p);
       b->p = nullptr;
     }
@@ -111,6 +117,20 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
     if (grad && !h->d_grad.p) CU_TRY(h, cudaMalloc(&h->d_grad.p, (size_t)h->cap * h->S * 8));
   }
   return 0;
+}
+
+// chains per pipelined chunk of the host-buffer APIs: >= 4 MiB of state per copy, multiple of 128;
+// small chunks keep the PCIe fill/drain bubbles short (MCD_CHUNK overrides, for experiments)
+int chunk_chains(int S) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("MCD_CHUNK");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) return (forced + 127) / 128 * 128;
+  int chunk = 512;
+  if ((size_t)chunk * S * 8 < (size_t)4 << 20) chunk = (int)(((size_t)4 << 20) / ((size_t)S * 8) / 128 + 1) * 128;
+  return chunk;
 }
 
 // enqueue the three kernels for chains [c0, c0 + n) of the given device buffers; c0 % 128 == 0
@@ -143,12 +163,23 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     CU_TRY(h, cudaEventRecord(ev[1], st));
   }
   if (h->timing) CU_TRY(h, cudaEventRecord(ev[2], st));
-  const size_t smem = POST_SMEM_FIXED + (size_t)cpb * M.N * 8 * (GRAD ? 4 : 3);
   double* o = d_out + (size_t)c0 * MCD_OUT_COLS;
   double* g = GRAD ? d_grad + (size_t)c0 * M.S : nullptr;
   int32_t* s = d_status + c0;
-  if (small) posterior_kernel<32, GRAD><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n);
-  else posterior_kernel<256, GRAD><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n);
+  // shared memory: reduction scratch + per chain group the staged state row [S] and contraction result [K]
+  const size_t smem = POST_SMEM_FIXED + (size_t)cpb * (M.S + M.K) * 8;
+#define MCD_LAUNCH_POST(GG, CC, MB) \
+  posterior_kernel<GG, CC, GRAD, MB><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n)
+#define MCD_LAUNCH_POST_G(GG, MB)                                              \
+  switch (M.clock) {                                                           \
+    case 0: MCD_LAUNCH_POST(GG, 0, MB); break;                                 \
+    case 1: MCD_LAUNCH_POST(GG, 1, MB); break;                                 \
+    case 2: MCD_LAUNCH_POST(GG, 2, MB); break;                                 \
+    default: MCD_LAUNCH_POST(GG, 3, MB); break;                                \
+  }
+  if (small) { MCD_LAUNCH_POST_G(32, 2) } else { MCD_LAUNCH_POST_G(256, POST_MINB) }
+#undef MCD_LAUNCH_POST_G
+#undef MCD_LAUNCH_POST
   h->launches += 1;
   if (h->timing) CU_TRY(h, cudaEventRecord(ev[3], st));
   CU_TRY(h, cudaGetLastError());
@@ -178,8 +209,7 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, true, GRAD)) return -1;
   const int S = h->S;
-  int chunk = 1024;  // chains per chunk (multiple of 128)
-  if ((size_t)chunk * S * 8 < (size_t)4 << 20) chunk = (int)(((size_t)4 << 20) / ((size_t)S * 8) / 128 + 1) * 128;
+  const int chunk = chunk_chains(S);
   int ci = 0;
   for (int c0 = 0; c0 < n; c0 += chunk, ++ci) {
     const int m = std::min(chunk, n - c0);
@@ -193,6 +223,44 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
     if (GRAD)
       CU_TRY(h, cudaMemcpyAsync(grad + (size_t)c0 * S, h->d_grad.as<double>() + (size_t)c0 * S, (size_t)m * S * 8,
                                 cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
+  return 0;
+}
+
+// theta-packed host API: only the D free parameters cross PCIe in either direction
+int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* base, double* out, double* gtheta,
+                    int32_t* status) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (n <= 0) return 0;
+  if (!theta || !base || !out || !gtheta || !status) return fail(h, "null host buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (ensure_capacity(h, n, true, true)) return -1;
+  const int S = h->S, D = h->D;
+  if (!h->d_theta.p) CU_TRY(h, cudaMalloc(&h->d_theta.p, (size_t)h->cap * D * 8));
+  if (!h->d_gtheta.p) CU_TRY(h, cudaMalloc(&h->d_gtheta.p, (size_t)h->cap * D * 8));
+  CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, h->streams[0]));
+  CU_TRY(h, cudaStreamSynchronize(h->streams[0]));
+  const int chunk = chunk_chains(S);
+  int ci = 0;
+  for (int c0 = 0; c0 < n; c0 += chunk, ++ci) {
+    const int m = std::min(chunk, n - c0);
+    cudaStream_t st = h->streams[ci % N_STREAMS];
+    double* d_th = h->d_theta.as<double>() + (size_t)c0 * D;
+    double* d_gt = h->d_gtheta.as<double>() + (size_t)c0 * D;
+    double* d_x = h->d_states.as<double>();
+    CU_TRY(h, cudaMemcpyAsync(d_th, theta + (size_t)c0 * D, (size_t)m * D * 8, cudaMemcpyHostToDevice, st));
+    unpack_theta_kernel<<<dim3((S + POST_THREADS - 1) / POST_THREADS, m), POST_THREADS, 0, st>>>(
+        d_th, h->d_base.as<double>(), h->d_tidx.as<int>(), d_x + (size_t)c0 * S, S, D, m);
+    if (enqueue<true>(h, c0, m, d_x, h->d_out.as<double>(), h->d_grad.as<double>(), h->d_status.as<int32_t>(), st)) return -1;
+    pack_theta_kernel<<<dim3((D + POST_THREADS - 1) / POST_THREADS, m), POST_THREADS, 0, st>>>(
+        h->d_grad.as<double>() + (size_t)c0 * S, h->d_sidx.as<int>(), d_gt, S, D, m);
+    h->launches += 2;
+    CU_TRY(h, cudaMemcpyAsync(out + (size_t)c0 * MCD_OUT_COLS, h->d_out.as<double>() + (size_t)c0 * MCD_OUT_COLS,
+                              (size_t)m * MCD_OUT_COLS * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(status + c0, h->d_status.as<int32_t>() + c0, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(gtheta + (size_t)c0 * D, d_gt, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st));
   }
   for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
   return 0;
@@ -261,6 +329,7 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, h->device);
   if (prop.major != 10) return bail("mcd_create: this build targets sm_100a (B200) only");
+  h->n_sms = prop.multiProcessorCount;
 
   const int K = N - 2;
   h->N = N; h->K = K; h->S = 5 + 2 * N;
@@ -291,10 +360,14 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   M.N = N; M.K = K; M.S = h->S; M.ldk = h->ldk; M.ldy = h->ldy;
   M.root_r = root_r; M.n_inner_nonroot = n_inner_nonroot;
   M.clock = d->clock_model; M.lik = d->likelihood; M.hmc_free_H = d->n_cal > 0;
-  M.ht = d->ht; M.logdet = d->logdet_sigma;
+  M.ht = d->ht; M.ln_ht = std::log(d->ht); M.logdet = d->logdet_sigma;
   M.lik_const = -(0.9189385332046727418 * (double)K);
-  if (upload(h, h->d_parent, h->parent.data(), N) || upload(h, h->d_child1, child1.data(), N)) return bail("upload topology");
-  M.parent = h->d_parent.as<int>(); M.child1 = h->d_child1.as<int>();
+  {
+    std::vector<int32_t> penc(N);
+    for (int i = 0; i < N; ++i) penc[i] = (i == 0 ? 0 : h->parent[i]) | (child0[i] < 0 ? LEAF_BIT : 0);
+    if (upload(h, h->d_parent, penc.data(), N)) return bail("upload topology");
+    M.parent = h->d_parent.as<int>();
+  }
   // likelihood data
   std::vector<double> mu(h->ldk, 0.0);
   if (d->likelihood != MCD_LIK_NONE) {
@@ -366,13 +439,28 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
     M.inner = h->d_inner.as<int4>();
   }
 
+  {  // theta <-> state index maps (toVector conses while folding left: reversed order)
+    std::vector<int> tidx(h->S, -1), sidx(std::max(h->D, 1), 0);
+    int t = h->D - 1;
+    for (int j = 0; j < h->S; ++j)
+      if (h->mask[j]) { tidx[j] = t; sidx[t] = j; --t; }
+    if (upload(h, h->d_tidx, tidx.data(), tidx.size()) || upload(h, h->d_sidx, sidx.data(), sidx.size()) ||
+        upload<double>(h, h->d_base, nullptr, h->S))
+      return bail("upload theta maps");
+  }
   for (int i = 0; i < N_STREAMS; ++i)
     if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
   // posterior kernels may need > 48 KiB dynamic smem on large trees
-  const int post_smem = POST_SMEM_FIXED + (N <= SMALL_TREE_MAX_NODES ? (POST_THREADS / 32) * N * 32 : N * 32);
-  if (post_smem > 200 * 1024) return bail("mcd_create: tree too large for the gradient kernel's shared memory (N > 6000)");
-  cudaFuncSetAttribute(posterior_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(posterior_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  {
+    const size_t post_smem = POST_SMEM_FIXED + (size_t)(N <= SMALL_TREE_MAX_NODES ? POST_THREADS / 32 : 1) * (h->S + K) * 8;
+    if (post_smem > 220 * 1024) return bail("mcd_create: tree too large for the posterior kernel's shared-memory staging (N > 9000)");
+    const int lim = 225 * 1024;
+#define MCD_SET_SMEM(CC)                                                                                               \
+  cudaFuncSetAttribute(posterior_kernel<256, CC, true, POST_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  cudaFuncSetAttribute(posterior_kernel<256, CC, false, POST_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    MCD_SET_SMEM(0) MCD_SET_SMEM(1) MCD_SET_SMEM(2) MCD_SET_SMEM(3)
+#undef MCD_SET_SMEM
+  }
   if (d->max_batch > 0 && ensure_capacity(h, d->max_batch, false, false)) return bail("allocating work buffers");
   if (cudaDeviceSynchronize() != cudaSuccess) return bail("device error during create");
   *out = h;
@@ -422,6 +510,10 @@ int mcd_eval(mcd_handle* h, int32_t n, const double* states, double* out, int32_
 }
 int mcd_eval_grad(mcd_handle* h, int32_t n, const double* states, double* out, double* grad, int32_t* status) {
   return eval_host<true>(h, n, states, out, grad, status);
+}
+int mcd_eval_grad_theta(mcd_handle* h, int32_t n, const double* theta, const double* base_state, double* out,
+                        double* grad_theta, int32_t* status) {
+  return eval_theta_host(h, n, theta, base_state, out, grad_theta, status);
 }
 int mcd_eval_device(mcd_handle* h, int32_t n, const double* d_states, double* d_out, int32_t* d_status, void* stream) {
   return eval_device<false>(h, n, d_states, d_out, nullptr, d_status, stream);
