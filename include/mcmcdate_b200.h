@@ -84,6 +84,9 @@ typedef struct mcd_model_desc {
   const double* brace_sd;    /* [n_brace], > 0 */
   int32_t device;            /* CUDA device ordinal */
   int32_t max_batch;         /* capacity hint; buffers grow on demand */
+  const double* precision_chol; /* optional (FULL): lower-triangular Cholesky factor L of Sigma^-1 = L L^T,
+                                   [K*K] row-major, used by the value-only path (half the flops); NULL: the
+                                   library factorises on the first mcd_eval call */
 } mcd_model_desc;
 
 /* lifecycle */

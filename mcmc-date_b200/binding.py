@@ -41,6 +41,7 @@ class ModelDescC(C.Structure):
         ("n_brace", C.c_int32), ("brace_off", C.POINTER(C.c_int32)), ("brace_node", C.POINTER(C.c_int32)),
         ("brace_sd", C.POINTER(C.c_double)),
         ("device", C.c_int32), ("max_batch", C.c_int32),
+        ("precision_chol", C.POINTER(C.c_double)),
     ]
 
 
@@ -90,7 +91,7 @@ def _ip(a):
 class Evaluator:
     """One model on one GPU (an `mcd_handle`)."""
 
-    def __init__(self, md: _m.ModelDesc, device: int = 0, max_batch: int = 0):
+    def __init__(self, md: _m.ModelDesc, device: int = 0, max_batch: int = 0, supply_cholesky: bool = True):
         L = load_library()
         self._L = L
         self.md = md
@@ -107,6 +108,14 @@ class Evaluator:
         d.n_con, d.con_young, d.con_old, d.con_p = md.n_con, _ip(md.con_young), _ip(md.con_old), _dp(md.con_p)
         d.n_brace, d.brace_off, d.brace_node, d.brace_sd = md.n_brace, _ip(md.brace_off), _ip(md.brace_node), _dp(md.brace_sd)
         d.device, d.max_batch = device, max_batch
+        d.precision_chol = None
+        if md.likelihood == _m.LIK_FULL and supply_cholesky:
+            try:  # numpy's LAPACK Cholesky is much faster than the library's fallback loop
+                chol = np.ascontiguousarray(np.linalg.cholesky(md.precision))
+                self._keep.append(chol)
+                d.precision_chol = _dp(chol)
+            except np.linalg.LinAlgError:
+                pass
         h = C.c_void_p()
         rc = L.mcd_create(C.byref(d), C.byref(h))
         if rc != 0:

@@ -77,7 +77,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
 // per thread.  Thread 0 doubles as the TMA producer.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f64_dmma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmX,
-                     double* __restrict__ Y, int nk, int ldy, int bt_base) {
+                     double* __restrict__ Y, int nk, int ldy, int bt_base, int upper_tri) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)GEMM_STAGES * GEMM_STAGE_BYTES);
@@ -90,6 +90,10 @@ gemm_f64_dmma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
   const int wpr = (warp >> 1) * 32;
   const int pr0 = blockIdx.x * GEMM_PR;
   const int bt0 = bt_base + blockIdx.y * GEMM_BT;
+  // upper-triangular operand (U = L^T of the Cholesky factor, value-only path): row m only has entries at
+  // k >= m, so this tile's reduction starts at its own diagonal block
+  const int kt0 = upper_tri ? pr0 / GEMM_BK : 0;
+  nk -= kt0;
 
   if (tid == 0) {
 #pragma unroll
@@ -106,8 +110,8 @@ gemm_f64_dmma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
     if (t >= GEMM_STAGES) mbar_wait(&empty[s], ((t / GEMM_STAGES) - 1) & 1);
     unsigned char* dst = smem + (size_t)s * GEMM_STAGE_BYTES;
     mbar_arrive_expect_tx(&full[s], GEMM_STAGE_BYTES);
-    tma_load_2d(dst, &tmX, t * GEMM_BK, bt0, &full[s]);
-    tma_load_2d(dst + GEMM_BT * GEMM_BK * 8, &tmP, t * GEMM_BK, pr0, &full[s]);
+    tma_load_2d(dst, &tmX, (kt0 + t) * GEMM_BK, bt0, &full[s]);
+    tma_load_2d(dst + GEMM_BT * GEMM_BK * 8, &tmP, (kt0 + t) * GEMM_BK, pr0, &full[s]);
   };
   if (tid == 0) {
     for (int t = 0; t < GEMM_PREFETCH && t < nk; ++t) issue(t);
@@ -208,9 +212,9 @@ inline cudaError_t gemm_f64_dmma_configure() {
 
 // Mp = P rows (mult of 128), ldk = padded K (mult of 16); chains [bt_base, bt_base + Bp), both mult of 128
 inline cudaError_t gemm_f64_dmma_launch(const CUtensorMap& tmP, const CUtensorMap& tmX, double* Y, int Mp, int Bp,
-                                        int ldk, int ldy, cudaStream_t st, int bt_base = 0) {
+                                        int ldk, int ldy, cudaStream_t st, int bt_base = 0, int upper_tri = 0) {
   dim3 grid(Mp / GEMM_PR, Bp / GEMM_BT);
-  gemm_f64_dmma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmP, tmX, Y, ldk / GEMM_BK, ldy, bt_base);
+  gemm_f64_dmma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmP, tmX, Y, ldk / GEMM_BK, ldy, bt_base, upper_tri);
   return cudaGetLastError();
 }
 

@@ -50,10 +50,12 @@ struct mcd_handle {
   std::vector<uint8_t> mask;
   // device model
   DevModel dm{};
-  DevBuf d_parent, d_child1, d_inner, d_mu, d_var, d_P;
+  DevBuf d_parent, d_child1, d_inner, d_mu, d_var, d_P, d_U;
+  std::vector<double> hostP;      // K x K copy kept for the lazy Cholesky factorisation
+  int chol_state = 0;             // 0 = not tried, 1 = U = L^T uploaded, -1 = not positive definite
   DevBuf d_cal_node, d_cal_lo, d_cal_hi, d_cal_slo, d_cal_shi, d_con_y, d_con_o, d_con_s, d_br_off, d_br_node, d_br_sd,
       d_inc_off, d_inc_ent;
-  CUtensorMap tmP{}, tmX{};
+  CUtensorMap tmP{}, tmX{}, tmU{};
   // work buffers (capacity `cap` chains, multiple of 128)
   int cap = 0;
   DevBuf d_dx, d_y;               // internal: residuals and P.dx
@@ -119,6 +121,50 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
   return 0;
 }
 
+// Value-only path (MH proposals): quad = |L^T dx|^2 with P = L L^T needs only the triangular half of the
+// contraction's flops.  L is taken from the model description when supplied, else factorised here once
+// (row-oriented Cholesky, ~K^3/3 flops on the host).  Not positive definite -> keep the symmetric product.
+int ensure_cholesky(mcd_handle* h, const double* L_in) {
+  if (h->chol_state != 0) return 0;
+  const int K = h->K;
+  std::vector<double> L;
+  if (L_in) {
+    L.assign(L_in, L_in + (size_t)K * K);
+  } else {
+    L.assign((size_t)K * K, 0.0);
+    const double* P = h->hostP.data();
+    for (int i = 0; i < K && h->chol_state == 0; ++i) {
+      double* Li = &L[(size_t)i * K];
+      for (int j = 0; j <= i; ++j) {
+        const double* Lj = &L[(size_t)j * K];
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        int k = 0;
+        for (; k + 4 <= j; k += 4) {
+          s0 += Li[k] * Lj[k]; s1 += Li[k + 1] * Lj[k + 1]; s2 += Li[k + 2] * Lj[k + 2]; s3 += Li[k + 3] * Lj[k + 3];
+        }
+        for (; k < j; ++k) s0 += Li[k] * Lj[k];
+        const double s = P[(size_t)i * K + j] - ((s0 + s1) + (s2 + s3));
+        if (i == j) {
+          if (!(s > 0.0)) { h->chol_state = -1; break; }
+          Li[i] = std::sqrt(s);
+        } else {
+          Li[j] = s / Lj[j];
+        }
+      }
+    }
+    if (h->chol_state == -1) return 0;
+  }
+  std::vector<double> U((size_t)h->Mp * h->ldk, 0.0);  // U[m][k] = L[k][m], k >= m
+  for (int k = 0; k < K; ++k)
+    for (int m = 0; m <= k; ++m) U[(size_t)m * h->ldk + k] = L[(size_t)k * K + m];
+  if (upload(h, h->d_U, U.data(), U.size())) return -1;
+  if (make_tile_map(&h->tmU, h->d_U.as<double>(), h->Mp, h->ldk) != 0) return fail(h, "cuTensorMapEncodeTiled failed for the Cholesky factor");
+  h->chol_state = 1;
+  h->hostP.clear();
+  h->hostP.shrink_to_fit();
+  return 0;
+}
+
 // chains per pipelined chunk of the host-buffer APIs: >= 4 MiB of state per copy, multiple of 128;
 // small chunks keep the PCIe fill/drain bubbles short (MCD_CHUNK overrides, for experiments)
 int chunk_chains(int S) {
@@ -137,7 +183,9 @@ int chunk_chains(int S) {
 template <bool GRAD>
 int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
             cudaStream_t st) {
-  const DevModel& M = h->dm;
+  DevModel M = h->dm;
+  const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1;
+  M.quad_from_z = tri ? 1 : 0;
   const bool small = M.N <= SMALL_TREE_MAX_NODES;
   const int cpb = small ? POST_THREADS / 32 : 1;
   const int grid = (n + cpb - 1) / cpb;
@@ -157,7 +205,8 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     else residual_kernel<256><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
     if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
     const int np = (n + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
-    CU_TRY(h, gemm_f64_dmma_launch(h->tmP, h->tmX, h->d_y.as<double>(), h->Mp, np, M.ldk, M.ldy, st, c0));
+    CU_TRY(h, gemm_f64_dmma_launch(tri ? h->tmU : h->tmP, h->tmX, h->d_y.as<double>(), h->Mp, np, M.ldk, M.ldy, st, c0,
+                                   tri ? 1 : 0));
     h->launches += 2;
   } else if (h->timing) {
     CU_TRY(h, cudaEventRecord(ev[1], st));
@@ -195,6 +244,7 @@ int eval_device(mcd_handle* h, int n, const double* d_states, double* d_out, dou
   if (!d_states || !d_out || !d_status || (GRAD && !d_grad)) return fail(h, "null device buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, false, GRAD)) return -1;
+  if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && ensure_cholesky(h, nullptr)) return -1;
   return enqueue<GRAD>(h, 0, n, d_states, d_out, d_grad, d_status, static_cast<cudaStream_t>(stream));
 }
 
@@ -208,6 +258,7 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
   if (!states || !out || !status || (GRAD && !grad)) return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, true, GRAD)) return -1;
+  if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && ensure_cholesky(h, nullptr)) return -1;
   const int S = h->S;
   const int chunk = chunk_chains(S);
   int ci = 0;
@@ -359,7 +410,7 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   DevModel& M = h->dm;
   M.N = N; M.K = K; M.S = h->S; M.ldk = h->ldk; M.ldy = h->ldy;
   M.root_r = root_r; M.n_inner_nonroot = n_inner_nonroot;
-  M.clock = d->clock_model; M.lik = d->likelihood; M.hmc_free_H = d->n_cal > 0;
+  M.clock = d->clock_model; M.lik = d->likelihood; M.hmc_free_H = d->n_cal > 0; M.quad_from_z = 0;
   M.ht = d->ht; M.ln_ht = std::log(d->ht); M.logdet = d->logdet_sigma;
   M.lik_const = -(0.9189385332046727418 * (double)K);
   {
@@ -392,6 +443,11 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
       }
     }
     if (upload(h, h->d_P, P.data(), P.size())) return bail("upload precision");
+    if (d->precision_chol) {
+      if (ensure_cholesky(h, d->precision_chol)) return bail("upload Cholesky factor");
+    } else {
+      h->hostP.assign(d->precision, d->precision + (size_t)K * K);
+    }
     if (make_tile_map(&h->tmP, h->d_P.as<double>(), h->Mp, h->ldk) != 0) return bail("cuTensorMapEncodeTiled failed for the precision matrix");
     if (gemm_f64_dmma_configure() != cudaSuccess) return bail("cudaFuncSetAttribute(gemm smem) failed");
   }

@@ -45,7 +45,9 @@ def test_fixture_parity_value_gradient_status(name, clock):
     # value-only entry point returns the same numbers
     out2, st2 = ev.eval(X)
     # (separate template instantiations: FMA contraction may differ in the last bits)
-    assert relerr(out2[:, :7], out[:, :7]).max() < 1e-13 and np.array_equal(st2, st)
+    # and the value-only path evaluates the quadratic form through the Cholesky factor, |L^T dx|^2)
+    assert relerr(out2[:, :7], out[:, :7]).max() < TOL and np.array_equal(st2, st)
+    assert relerr(out2[:, :7], z[f"out_{clock}"]).max() < TOL
     ev.close()
 
 
@@ -133,8 +135,8 @@ def test_full_size_deterministic_and_chunk_invariant(full_size):
     perm = np.random.default_rng(0).permutation(len(X))[:2048]
     o4, g4, _ = ev.eval_grad(X[perm])
     assert np.array_equal(o4, out[perm]) and np.array_equal(g4, grad[perm])
-    o5, s5 = ev.eval(X)
-    assert relerr(o5[:, :7], out[:, :7]).max() < 1e-13
+    o5, s5 = ev.eval(X)            # value-only: triangular (Cholesky) contraction
+    assert relerr(o5[:, :7], out[:, :7]).max() < 1e-11
 
 
 def test_full_size_spot_check_against_oracle(full_size):
@@ -221,6 +223,30 @@ def test_theta_packed_entry_point(full_size):
         gd = orc.grad_dual(Xs[b])
         assert grad_relerr(g2[b], orc.to_vector(gd)).max() < TOL
     ev2.close()
+
+
+def test_value_only_cholesky_path():
+    """mcd_eval uses quad = |L^T dx|^2 (triangular contraction, half the flops): with the factor supplied
+    by the caller, factorised by the library, and -- for an indefinite matrix -- the symmetric fallback"""
+    md, h = synth.synthetic_model(300, seed=77, n_cal=4, n_con=2, n_brace=1)
+    X = synth.synthetic_states(md, h, 200)
+    oo, ost = O.Oracle(md).eval(X, nthreads=4)
+    for supply in (True, False):
+        ev = binding.Evaluator(md, supply_cholesky=supply)
+        out, st = ev.eval(X)
+        assert relerr(out[:, :7], oo).max() < TOL and np.array_equal(st, ost)
+        ev.close()
+    # indefinite "precision": Cholesky fails -> symmetric product; the density formula is still evaluated
+    P = md.precision.copy()
+    P[5, 5] = -abs(P[5, 5])
+    md2 = model.ModelDesc(parent=md.parent, mean=md.mean, precision=P, logdet_sigma=md.logdet_sigma, ht=md.ht,
+                          cal_node=md.cal_node, cal_lo=md.cal_lo, cal_lo_p=md.cal_lo_p, cal_hi=md.cal_hi,
+                          cal_hi_p=md.cal_hi_p)
+    ev = binding.Evaluator(md2)
+    out, st = ev.eval(X[:50])
+    o2, s2 = O.Oracle(md2).eval(X[:50])
+    assert relerr(out[:, :7], o2).max() < TOL
+    ev.close()
 
 
 def test_error_behaviour():
