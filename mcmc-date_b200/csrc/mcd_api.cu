@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -179,6 +180,14 @@ int chunk_chains(int S) {
   return chunk;
 }
 
+// chunk schedule of the host-buffer pipeline: equal chunks (tapering the ends was measured: no gain)
+std::vector<std::pair<int, int>> chunk_schedule(int n, int S) {
+  const int chunk = chunk_chains(S);
+  std::vector<std::pair<int, int>> out;
+  for (int c0 = 0; c0 < n; c0 += chunk) out.push_back({c0, std::min(chunk, n - c0)});
+  return out;
+}
+
 // enqueue the three kernels for chains [c0, c0 + n) of the given device buffers; c0 % 128 == 0
 template <bool GRAD>
 int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
@@ -260,11 +269,10 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
   if (ensure_capacity(h, n, true, GRAD)) return -1;
   if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && ensure_cholesky(h, nullptr)) return -1;
   const int S = h->S;
-  const int chunk = chunk_chains(S);
   int ci = 0;
-  for (int c0 = 0; c0 < n; c0 += chunk, ++ci) {
-    const int m = std::min(chunk, n - c0);
-    cudaStream_t st = h->streams[ci % N_STREAMS];
+  for (const auto& cm : chunk_schedule(n, S)) {
+    const int c0 = cm.first, m = cm.second;
+    cudaStream_t st = h->streams[ci++ % N_STREAMS];
     double* d_x = h->d_states.as<double>();
     CU_TRY(h, cudaMemcpyAsync(d_x + (size_t)c0 * S, states + (size_t)c0 * S, (size_t)m * S * 8, cudaMemcpyHostToDevice, st));
     if (enqueue<GRAD>(h, c0, m, d_x, h->d_out.as<double>(), h->d_grad.as<double>(), h->d_status.as<int32_t>(), st)) return -1;
@@ -293,11 +301,10 @@ int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* bas
   if (!h->d_gtheta.p) CU_TRY(h, cudaMalloc(&h->d_gtheta.p, (size_t)h->cap * D * 8));
   CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, h->streams[0]));
   CU_TRY(h, cudaStreamSynchronize(h->streams[0]));
-  const int chunk = chunk_chains(S);
   int ci = 0;
-  for (int c0 = 0; c0 < n; c0 += chunk, ++ci) {
-    const int m = std::min(chunk, n - c0);
-    cudaStream_t st = h->streams[ci % N_STREAMS];
+  for (const auto& cm : chunk_schedule(n, S)) {
+    const int c0 = cm.first, m = cm.second;
+    cudaStream_t st = h->streams[ci++ % N_STREAMS];
     double* d_th = h->d_theta.as<double>() + (size_t)c0 * D;
     double* d_gt = h->d_gtheta.as<double>() + (size_t)c0 * D;
     double* d_x = h->d_states.as<double>();
