@@ -209,9 +209,33 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     }
     CU_TRY(h, cudaEventRecord(ev[0], st));
   }
+  if (small) {
+    // one fused launch: tables and P in shared memory, one warp per chain
+    const size_t fsmem = POST_SMEM_FIXED + ((size_t)M.K * M.K + (size_t)(POST_THREADS / 32) * (M.S + 2 * M.K)) * 8;
+    const int fgrid = std::min(grid, 2 * h->n_sms);
+    double* fo = d_out + (size_t)c0 * MCD_OUT_COLS;
+    double* fg = GRAD ? d_grad + (size_t)c0 * M.S : nullptr;
+    M.quad_from_z = 0;
+#define MCD_LAUNCH_SMALL(CC) \
+  small_tree_fused_kernel<CC, GRAD><<<fgrid, POST_THREADS, fsmem, st>>>(M, h->d_P.as<double>(), xs, fo, fg, d_status + c0, n)
+    switch (M.clock) {
+      case 0: MCD_LAUNCH_SMALL(0); break;
+      case 1: MCD_LAUNCH_SMALL(1); break;
+      case 2: MCD_LAUNCH_SMALL(2); break;
+      default: MCD_LAUNCH_SMALL(3); break;
+    }
+#undef MCD_LAUNCH_SMALL
+    h->launches += 1;
+    if (h->timing) {
+      CU_TRY(h, cudaEventRecord(ev[1], st));
+      CU_TRY(h, cudaEventRecord(ev[2], st));
+      CU_TRY(h, cudaEventRecord(ev[3], st));
+    }
+    CU_TRY(h, cudaGetLastError());
+    return 0;
+  }
   if (M.lik == MCD_LIK_FULL) {
-    if (small) residual_kernel<32><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
-    else residual_kernel<256><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
+    residual_kernel<256><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
     if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
     const int np = (n + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
     CU_TRY(h, gemm_f64_dmma_launch(tri ? h->tmU : h->tmP, h->tmX, h->d_y.as<double>(), h->Mp, np, M.ldk, M.ldy, st, c0,
@@ -235,7 +259,7 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     case 2: MCD_LAUNCH_POST(GG, 2, MB); break;                                 \
     default: MCD_LAUNCH_POST(GG, 3, MB); break;                                \
   }
-  if (small) { MCD_LAUNCH_POST_G(32, 2) } else { MCD_LAUNCH_POST_G(256, POST_MINB) }
+  MCD_LAUNCH_POST_G(256, POST_MINB)
 #undef MCD_LAUNCH_POST_G
 #undef MCD_LAUNCH_POST
   h->launches += 1;
@@ -521,6 +545,11 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
 #define MCD_SET_SMEM(CC)                                                                                               \
   cudaFuncSetAttribute(posterior_kernel<256, CC, true, POST_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
   cudaFuncSetAttribute(posterior_kernel<256, CC, false, POST_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    MCD_SET_SMEM(0) MCD_SET_SMEM(1) MCD_SET_SMEM(2) MCD_SET_SMEM(3)
+#undef MCD_SET_SMEM
+#define MCD_SET_SMEM(CC)                                                                                          \
+  cudaFuncSetAttribute(small_tree_fused_kernel<CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);     \
+  cudaFuncSetAttribute(small_tree_fused_kernel<CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     MCD_SET_SMEM(0) MCD_SET_SMEM(1) MCD_SET_SMEM(2) MCD_SET_SMEM(3)
 #undef MCD_SET_SMEM
   }
