@@ -42,8 +42,8 @@ typedef struct mcd_handle mcd_handle;
 /* RelaxedMolecularClockModel, app/Probability.hs:88-93 */
 enum { MCD_CLOCK_UNCORRELATED_GAMMA = 0, MCD_CLOCK_UNCORRELATED_LOGNORMAL = 1,
        MCD_CLOCK_UNCORRELATED_WHITENOISE = 2, MCD_CLOCK_AUTOCORRELATED_LOGNORMAL = 3 };
-/* LikelihoodData, app/Probability.hs:210-235 (Sparse: not built yet) */
-enum { MCD_LIK_FULL = 0, MCD_LIK_UNIVARIATE = 1, MCD_LIK_NONE = 2 };
+/* LikelihoodData, app/Probability.hs:210-235 */
+enum { MCD_LIK_FULL = 0, MCD_LIK_UNIVARIATE = 1, MCD_LIK_NONE = 2, MCD_LIK_SPARSE = 3 };
 /* per-chain status bits */
 enum { MCD_ST_REF_ERROR = 1,    /* the reference would have called `error` (abort); value -inf */
        MCD_ST_ZERO = 2,         /* ln posterior = -inf (probability zero) */
@@ -87,6 +87,10 @@ typedef struct mcd_model_desc {
   const double* precision_chol; /* optional (FULL): lower-triangular Cholesky factor L of Sigma^-1 = L L^T,
                                    [K*K] row-major, used by the value-only path (half the flops); NULL: the
                                    library factorises on the first mcd_eval call */
+  int32_t n_sparse;          /* SPARSE: the association list ((i, j), v) of the sparse Sigma^-1 exactly as the */
+  const int32_t* sparse_row; /*   reference stores it (SparseS, app/Main.hs:75-81; mkSparse :95-97);        */
+  const int32_t* sparse_col; /*   duplicates add up; `precision` is ignored, logdet_sigma = ln det of the   */
+  const double* sparse_val;  /*   sparse covariance                                                         */
 } mcd_model_desc;
 
 /* lifecycle */

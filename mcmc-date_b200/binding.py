@@ -42,6 +42,8 @@ class ModelDescC(C.Structure):
         ("brace_sd", C.POINTER(C.c_double)),
         ("device", C.c_int32), ("max_batch", C.c_int32),
         ("precision_chol", C.POINTER(C.c_double)),
+        ("n_sparse", C.c_int32), ("sparse_row", C.POINTER(C.c_int32)), ("sparse_col", C.POINTER(C.c_int32)),
+        ("sparse_val", C.POINTER(C.c_double)),
     ]
 
 
@@ -109,6 +111,8 @@ class Evaluator:
         d.n_brace, d.brace_off, d.brace_node, d.brace_sd = md.n_brace, _ip(md.brace_off), _ip(md.brace_node), _dp(md.brace_sd)
         d.device, d.max_batch = device, max_batch
         d.precision_chol = None
+        d.n_sparse = len(md.sparse_val)
+        d.sparse_row, d.sparse_col, d.sparse_val = _ip(md.sparse_row), _ip(md.sparse_col), _dp(md.sparse_val)
         if md.likelihood == _m.LIK_FULL and supply_cholesky:
             try:  # numpy's LAPACK Cholesky is much faster than the library's fallback loop
                 chol = np.ascontiguousarray(np.linalg.cholesky(md.precision))

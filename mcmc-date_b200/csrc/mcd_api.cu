@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -53,6 +54,8 @@ struct mcd_handle {
   DevModel dm{};
   DevBuf d_parent, d_child1, d_inner, d_mu, d_var, d_P, d_U;
   std::vector<double> hostP;      // K x K copy kept for the lazy Cholesky factorisation
+  bool sparse = false;            // MCD_LIK_SPARSE on a large tree: CSR contraction instead of the dense one
+  DevBuf d_sp_ptr, d_sp_col, d_sp_val;
   int chol_state = 0;             // 0 = not tried, 1 = U = L^T uploaded, -1 = not positive definite
   DevBuf d_cal_node, d_cal_lo, d_cal_hi, d_cal_slo, d_cal_shi, d_con_y, d_con_o, d_con_s, d_br_off, d_br_node, d_br_sd,
       d_inc_off, d_inc_ent;
@@ -127,6 +130,7 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
 // (row-oriented Cholesky, ~K^3/3 flops on the host).  Not positive definite -> keep the symmetric product.
 int ensure_cholesky(mcd_handle* h, const double* L_in) {
   if (h->chol_state != 0) return 0;
+  if (!L_in && h->hostP.empty()) { h->chol_state = -1; return 0; }  // sparse models: no dense factor
   const int K = h->K;
   std::vector<double> L;
   if (L_in) {
@@ -193,7 +197,7 @@ template <bool GRAD>
 int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
             cudaStream_t st) {
   DevModel M = h->dm;
-  const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1;
+  const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1 && !h->sparse;
   M.quad_from_z = tri ? 1 : 0;
   const bool small = M.N <= SMALL_TREE_MAX_NODES;
   const int cpb = small ? POST_THREADS / 32 : 1;
@@ -234,7 +238,11 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     CU_TRY(h, cudaGetLastError());
     return 0;
   }
-  if (M.lik == MCD_LIK_FULL) {
+  if (h->sparse) {
+    sparse_contraction_kernel<<<n, POST_THREADS, (size_t)(M.S + M.K) * 8, st>>>(M, xs, h->d_y.as<double>() + (size_t)c0 * M.ldy, n);
+    h->launches += 1;
+    if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
+  } else if (M.lik == MCD_LIK_FULL) {
     residual_kernel<256><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
     if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
     const int np = (n + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
@@ -362,7 +370,14 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   const int N = d->n_nodes;
   if (N < 3 || N % 2 == 0 || !d->parent) return fail(nullptr, "mcd_create: need a bifurcating tree with >= 2 leaves");
   if (d->clock_model < 0 || d->clock_model > 3) return fail(nullptr, "mcd_create: unknown clock model");
-  if (d->likelihood < 0 || d->likelihood > 2) return fail(nullptr, "mcd_create: unknown likelihood kind");
+  if (d->likelihood < 0 || d->likelihood > 3) return fail(nullptr, "mcd_create: unknown likelihood kind");
+  if (d->likelihood == MCD_LIK_SPARSE) {
+    if (d->n_sparse < 0 || (d->n_sparse > 0 && (!d->sparse_row || !d->sparse_col || !d->sparse_val)))
+      return fail(nullptr, "mcd_create: sparse precision missing");
+    for (int e = 0; e < d->n_sparse; ++e)
+      if (d->sparse_row[e] < 0 || d->sparse_row[e] >= N - 2 || d->sparse_col[e] < 0 || d->sparse_col[e] >= N - 2)
+        return fail(nullptr, "mcd_create: sparse precision index out of range");
+  }
   if (!(d->ht > 0.0)) return fail(nullptr, "exponential: Rate is zero or negative.");  // exponential ht (Probability.hs:106)
   // topology checks: pre-order (parent < child), strictly bifurcating
   std::vector<int32_t> child0(N, -1), child1(N, -1);
@@ -453,7 +468,7 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   // likelihood data
   std::vector<double> mu(h->ldk, 0.0);
   if (d->likelihood != MCD_LIK_NONE) {
-    if (!d->mean || !d->precision) return bail("mcd_create: mean / precision missing");
+    if (!d->mean || (!d->precision && d->likelihood != MCD_LIK_SPARSE)) return bail("mcd_create: mean / precision missing");
     std::memcpy(mu.data(), d->mean, K * 8);
   }
   if (upload(h, h->d_mu, mu.data(), h->ldk)) return bail("upload mean");
@@ -462,6 +477,39 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   if (d->likelihood == MCD_LIK_UNIVARIATE) {
     if (upload(h, h->d_var, d->precision, K)) return bail("upload variances");
     M.var = h->d_var.as<double>();
+  } else if (d->likelihood == MCD_LIK_SPARSE) {
+    // symmetrise: S_sym = (S + S^T)/2 has the same quadratic form, and -S_sym dx is the gradient
+    std::vector<std::vector<std::pair<int, double>>> rows(K);
+    for (int e = 0; e < d->n_sparse; ++e) {
+      rows[d->sparse_row[e]].push_back({d->sparse_col[e], 0.5 * d->sparse_val[e]});
+      rows[d->sparse_col[e]].push_back({d->sparse_row[e], 0.5 * d->sparse_val[e]});
+    }
+    std::vector<int> ptr(K + 1, 0), col;
+    std::vector<double> val;
+    for (int i = 0; i < K; ++i) {
+      std::sort(rows[i].begin(), rows[i].end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+      for (size_t e = 0; e < rows[i].size(); ++e) {
+        if (!col.empty() && (int)col.size() > ptr[i] && col.back() == rows[i][e].first) val.back() += rows[i][e].second;
+        else { col.push_back(rows[i][e].first); val.push_back(rows[i][e].second); }
+      }
+      ptr[i + 1] = (int)col.size();
+    }
+    if (N <= SMALL_TREE_MAX_NODES) {
+      // small trees: densify, the fused single-launch kernel keeps the matrix in shared memory
+      std::vector<double> P((size_t)h->Mp * h->ldk, 0.0);
+      for (int i = 0; i < K; ++i)
+        for (int e = ptr[i]; e < ptr[i + 1]; ++e) P[(size_t)i * h->ldk + col[e]] = val[e];
+      if (upload(h, h->d_P, P.data(), P.size())) return bail("upload precision");
+    } else {
+      if (upload(h, h->d_sp_ptr, ptr.data(), ptr.size()) || upload(h, h->d_sp_col, col.data(), col.size()) ||
+          upload(h, h->d_sp_val, val.data(), val.size()))
+        return bail("upload sparse precision");
+      M.sp_ptr = h->d_sp_ptr.as<int>(); M.sp_col = h->d_sp_col.as<int>(); M.sp_val = h->d_sp_val.as<double>();
+      h->sparse = true;
+      if (h->S + K > 27000) return bail("mcd_create: tree too large for the sparse contraction's shared memory");
+      cudaFuncSetAttribute(sparse_contraction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    }
+    M.lik = MCD_LIK_FULL;  // downstream kernels see y = S dx exactly like the dense case
   } else if (d->likelihood == MCD_LIK_FULL) {
     // P padded to [Mp][ldk]; symmetry is assumed by the reference (L.Herm, app/Probability.hs:166) and
     // relied on here (gradient = -P dx), so it is checked

@@ -16,8 +16,8 @@ from . import tree as _tree
 # RelaxedMolecularClockModel (app/Probability.hs:88-93)
 UNCORRELATED_GAMMA, UNCORRELATED_LOGNORMAL, UNCORRELATED_WHITENOISE, AUTOCORRELATED_LOGNORMAL = 0, 1, 2, 3
 CLOCK_NAMES = {"ug": 0, "ul": 1, "uw": 2, "al": 3}
-# LikelihoodData constructors (app/Probability.hs:210-235); Sparse is not built yet
-LIK_FULL, LIK_UNIVARIATE, LIK_NONE = 0, 1, 2
+# LikelihoodData constructors (app/Probability.hs:210-235)
+LIK_FULL, LIK_UNIVARIATE, LIK_NONE, LIK_SPARSE = 0, 1, 2, 3
 
 # per-chain status bits returned by the evaluator (include/mcmcdate_b200.h)
 ST_REF_ERROR, ST_ZERO, ST_NAN, ST_NEARCRIT, ST_LEAF_HEIGHT = 1, 2, 4, 8, 16
@@ -55,14 +55,18 @@ class ModelDesc:
     brace_off: np.ndarray = field(default_factory=lambda: np.zeros(1, np.int32))
     brace_node: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
     brace_sd: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    # LIK_SPARSE: association list ((i, j), v) of the sparse precision (SparseS, app/Main.hs:75-81)
+    sparse_row: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    sparse_col: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    sparse_val: np.ndarray = field(default_factory=lambda: np.zeros(0))
 
     def __post_init__(self):
         self.parent = _i32(self.parent)
         self.mean = _f64(self.mean)
         self.precision = _f64(self.precision)
-        for k in ("cal_node", "con_young", "con_old", "brace_off", "brace_node"):
+        for k in ("cal_node", "con_young", "con_old", "brace_off", "brace_node", "sparse_row", "sparse_col"):
             setattr(self, k, _i32(getattr(self, k)))
-        for k in ("cal_lo", "cal_lo_p", "cal_hi", "cal_hi_p", "con_p", "brace_sd"):
+        for k in ("cal_lo", "cal_lo_p", "cal_hi", "cal_hi_p", "con_p", "brace_sd", "sparse_val"):
             setattr(self, k, _f64(getattr(self, k)))
         self.child0, self.child1 = _tree.children_from_parent(self.parent)
 

@@ -54,6 +54,12 @@ def synthetic_model(n_leaves: int, seed: int = BASE_SEED, clock_model: int = _m.
     elif likelihood == _m.LIK_UNIVARIATE:
         prec = (0.1 * mu + 1e-3) ** 2
         logdet = float(np.sum(np.log(prec)))
+    elif likelihood == _m.LIK_SPARSE:
+        # banded Cholesky factor without fill -> an exactly banded (sparse), positive definite precision
+        dense, logdet = synthetic_precision(mu, rng, band=6, fill=0.0)
+        si, sj = np.nonzero(dense)
+        sparse = (si.astype(np.int32), sj.astype(np.int32), dense[si, sj])
+        prec = np.zeros(0)
     else:
         prec, logdet = np.zeros(0), 0.0
 
@@ -103,6 +109,8 @@ def synthetic_model(n_leaves: int, seed: int = BASE_SEED, clock_model: int = _m.
         cal_hi_p=[0.025] * len(cal_node),
         con_young=con_y, con_old=con_o, con_p=[0.025] * len(con_y),
         brace_off=br_off, brace_node=br_node, brace_sd=br_sd)
+    if likelihood == _m.LIK_SPARSE:
+        md.sparse_row, md.sparse_col, md.sparse_val = sparse
     return md, h
 
 

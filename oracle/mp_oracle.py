@@ -117,6 +117,12 @@ def ln_posterior_parts(md, x):
         for i in range(K):
             quad += dx[i] * sum(mp.mpf(float(P[i, j])) * dx[j] for j in range(K))
         lnL = -K * mp.log(mp.sqrt(2 * mp.pi)) - (mp.mpf(float(md.logdet_sigma)) + quad) / 2
+    elif md.likelihood == 3:
+        dx = [dvec[k] - mp.mpf(float(md.mean[k])) for k in range(K)]
+        quad = mp.mpf(0)
+        for i, j, val in zip(md.sparse_row, md.sparse_col, md.sparse_val):
+            quad += dx[int(i)] * mp.mpf(float(val)) * dx[int(j)]
+        lnL = -K * mp.log(mp.sqrt(2 * mp.pi)) - (mp.mpf(float(md.logdet_sigma)) + quad) / 2
     elif md.likelihood == 1:
         es = sum((dvec[k] - mp.mpf(float(md.mean[k]))) ** 2 / mp.mpf(float(md.precision[k])) for k in range(K))
         lnL = -K * mp.log(mp.sqrt(2 * mp.pi)) - (mp.mpf(float(md.logdet_sigma)) + es) / 2

@@ -35,7 +35,7 @@ namespace orc {
 // model description (flattened; pre-order node numbering, root = 0)
 // ----------------------------------------------------------------------------------------------
 enum ClockModel { UGAMMA = 0, ULOGNORMAL = 1, UWHITENOISE = 2, ALOGNORMAL = 3 };  // app/Probability.hs:88-93
-enum LikKind { LIK_FULL = 0, LIK_UNIVARIATE = 1, LIK_NONE = 2 };                   // app/Probability.hs:210-235
+enum LikKind { LIK_FULL = 0, LIK_UNIVARIATE = 1, LIK_NONE = 2, LIK_SPARSE = 3 };   // app/Probability.hs:210-235
 enum Status {
   ST_REF_ERROR = 1,   // the reference would have called Haskell `error` (process abort)
   ST_ZERO = 2,        // probability zero (ln = -inf) somewhere in prior*likelihood*jacobian
@@ -51,6 +51,8 @@ struct Model {
   int K = 0;                              // N-2
   std::vector<double> mu;                 // [K]
   std::vector<double> prec;               // [K*K] row-major Sigma^-1 (LIK_FULL) or [K] variances
+  std::vector<int> sp_row, sp_col;        // LIK_SPARSE: association list ((i, j), v) as stored by the
+  std::vector<double> sp_val;             //   reference (SparseS, app/Main.hs:75-81,95-97)
   double logdet = 0;                      // ln det Sigma   (or sum ln var)
   int clock = ULOGNORMAL, lik = LIK_FULL;
   double ht = 1.0;                        // mean root height (app/Main.hs:394)
@@ -240,6 +242,19 @@ T mvn_full_generic(const Model& M, const std::vector<T>& d) {
     for (int j = 0; j < K; ++j) acc = acc + dx[i] * T(M.prec[(size_t)i * K + j]) * dx[j];
   T c = T(-(LN_SQRT_2PI * (double)K));
   return c + T(-0.5) * (T(M.logdet) + acc);
+}
+// logDensitySparseMultivariateNormal (app/Probability.hs:178-184): dxs <.> (sigmaInvS !#> dxs)
+template <class T>
+T mvn_sparse(const Model& M, const std::vector<T>& d, std::vector<T>* y_out = nullptr) {
+  const int K = M.K;
+  std::vector<T> dx(K), y(K, T(0.0));
+  for (int k = 0; k < K; ++k) dx[k] = d[k] - T(M.mu[k]);
+  for (size_t e = 0; e < M.sp_val.size(); ++e) y[M.sp_row[e]] = y[M.sp_row[e]] + T(M.sp_val[e]) * dx[M.sp_col[e]];
+  T quad(0.0);
+  for (int k = 0; k < K; ++k) quad = quad + dx[k] * y[k];
+  if (y_out) *y_out = y;
+  T c = T(-(LN_SQRT_2PI * (double)K));
+  return c + T(-0.5) * (T(M.logdet) + quad);
 }
 // logDensityUnivariateNormal (app/Probability.hs:186-193)
 template <class T>
@@ -544,6 +559,7 @@ Result<T> eval_state(const Model& M, const T* x, bool generic_lik) {
   } else {
     std::vector<T> d = distances(M, s, t);
     if (M.lik == LIK_UNIVARIATE) R.lnLik = mvn_univariate(M, d);
+    else if (M.lik == LIK_SPARSE) R.lnLik = mvn_sparse(M, d);
     else R.lnLik = mvn_full_generic(M, d);
     (void)generic_lik;
   }
@@ -566,7 +582,9 @@ inline Result<double> eval_state_double(const Model& M, const double* x, std::ve
     R.lnLik = 0.0;
   } else {
     std::vector<double> d = distances(M, s, t);
-    R.lnLik = M.lik == LIK_UNIVARIATE ? mvn_univariate(M, d) : mvn_full_double(M, d, y_out);
+    R.lnLik = M.lik == LIK_UNIVARIATE ? mvn_univariate(M, d)
+              : M.lik == LIK_SPARSE   ? mvn_sparse(M, d)
+                                      : mvn_full_double(M, d, y_out);
   }
   R.lnJac = ln_jacobian(M, s, t);
   R.lnPost = R.lnPrior + R.lnLik + R.lnJac;

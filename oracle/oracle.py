@@ -64,17 +64,23 @@ class Oracle:
         mu, prec = _f64(md.mean), _f64(md.precision).reshape(-1)
         if md.likelihood == 2:
             mu, prec = np.zeros(1), np.zeros(1)
+        sp_row = _i32(getattr(md, "sparse_row", np.zeros(0, np.int32)))
+        sp_col = _i32(getattr(md, "sparse_col", np.zeros(0, np.int32)))
+        sp_val = _f64(getattr(md, "sparse_val", np.zeros(0)))
+        if md.likelihood == 3:
+            prec = np.zeros(1)
         arrs = [_i32(md.cal_node), _f64(md.cal_lo), _f64(md.cal_lo_p), _f64(md.cal_hi), _f64(md.cal_hi_p),
                 _i32(md.con_young), _i32(md.con_old), _f64(md.con_p),
                 _i32(md.brace_off), _i32(md.brace_node), _f64(md.brace_sd)]
-        self._keep = [parent, c0, c1, mu, prec] + arrs
+        self._keep = [parent, c0, c1, mu, prec, sp_row, sp_col, sp_val] + arrs
         D, I = C.c_double, C.c_int
         self.h = C.c_void_p(L.orc_model_create(
             I(self.N), _p(parent, I), _p(c0, I), _p(c1, I), I(self.K), _p(mu, D), _p(prec, D),
             D(md.logdet_sigma), I(md.clock_model), I(md.likelihood), D(md.ht),
             I(len(md.cal_node)), _p(arrs[0], I), _p(arrs[1], D), _p(arrs[2], D), _p(arrs[3], D), _p(arrs[4], D),
             I(len(md.con_young)), _p(arrs[5], I), _p(arrs[6], I), _p(arrs[7], D),
-            I(len(md.brace_sd)), _p(arrs[8], I), _p(arrs[9], I), _p(arrs[10], D)))
+            I(len(md.brace_sd)), _p(arrs[8], I), _p(arrs[9], I), _p(arrs[10], D),
+            I(len(sp_val)), _p(sp_row, I), _p(sp_col, I), _p(sp_val, D)))
         if not self.h:
             raise ValueError("oracle: model rejected (root not bifurcating?)")
         self.mask = self.get_mask(self.calibrations_available)

@@ -33,7 +33,8 @@ void* orc_model_create(int N, const int* parent, const int* child0, const int* c
                        const double* prec_or_var, double logdet, int clock, int lik, double ht, int ncal,
                        const int* cal_idx, const double* cal_lo, const double* cal_plo, const double* cal_hi,
                        const double* cal_phi, int ncon, const int* con_y, const int* con_o, const double* con_p,
-                       int nbrace, const int* br_off, const int* br_idx, const double* br_sd) {
+                       int nbrace, const int* br_off, const int* br_idx, const double* br_sd, int nnz,
+                       const int* sp_row, const int* sp_col, const double* sp_val) {
   Model* M = new Model();
   M->N = N;
   M->parent.assign(parent, parent + N);
@@ -44,10 +45,15 @@ void* orc_model_create(int N, const int* parent, const int* child0, const int* c
   M->lik = lik;
   M->ht = ht;
   M->logdet = logdet;
-  if (lik != LIK_NONE) {
-    M->mu.assign(mu, mu + K);
+  if (lik != LIK_NONE) M->mu.assign(mu, mu + K);
+  if (lik == LIK_FULL || lik == LIK_UNIVARIATE) {
     size_t np = lik == LIK_FULL ? (size_t)K * K : (size_t)K;
     M->prec.assign(prec_or_var, prec_or_var + np);
+  }
+  if (lik == LIK_SPARSE) {
+    M->sp_row.assign(sp_row, sp_row + nnz);
+    M->sp_col.assign(sp_col, sp_col + nnz);
+    M->sp_val.assign(sp_val, sp_val + nnz);
   }
   for (int c = 0; c < ncal; ++c) {
     M->cal_idx.push_back(cal_idx[c]);

@@ -65,6 +65,13 @@ inline Result<double> eval_grad_double(const Model& M, const double* x, const ui
     } else if (M.lik == LIK_UNIVARIATE) {
       std::vector<double> d = distances(M, s, t);
       for (int k = 0; k < M.K; ++k) w[k] = -(d[k] - M.mu[k]) / M.prec[k];
+    } else if (M.lik == LIK_SPARSE) {  // d/d dx of -1/2 dx^T S dx = -1/2 (S + S^T) dx
+      std::vector<double> d = distances(M, s, t);
+      for (size_t e = 0; e < M.sp_val.size(); ++e) {
+        const int i = M.sp_row[e], j = M.sp_col[e];
+        w[i] -= 0.5 * M.sp_val[e] * (d[j] - M.mu[j]);
+        w[j] -= 0.5 * M.sp_val[e] * (d[i] - M.mu[i]);
+      }
     }
     double d0 = sc * (t[l] * s.r(l) + t[r] * s.r(r));
     w[0] -= 1.0 / d0;

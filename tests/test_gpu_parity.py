@@ -225,6 +225,32 @@ def test_theta_packed_entry_point(full_size):
     ev2.close()
 
 
+@pytest.mark.parametrize("n_leaves,B", [(12, 100), (40, 64), (300, 257), (1000, 130)])
+def test_sparse_precision_likelihood(n_leaves, B):
+    """LikelihoodData `Sparse` (app/Probability.hs:178-184): association-list precision as the reference
+    stores it; small trees run densified in the fused kernel, large ones through the CSR contraction"""
+    md, h = synth.synthetic_model(n_leaves, seed=500 + n_leaves, likelihood=model.LIK_SPARSE, n_cal=3, n_con=2,
+                                  n_brace=1, clock_model=1 + (n_leaves % 3))
+    assert len(md.sparse_val) < 20 * md.dim + 400
+    X = synth.synthetic_states(md, h, B)
+    ev = binding.Evaluator(md)
+    out, grad, st = ev.eval_grad(X)
+    oo, og, ost = O.Oracle(md).eval_grad(X, nthreads=4)
+    assert np.array_equal(st, ost)
+    assert relerr(out[:, :7], oo).max() < TOL and grad_relerr(grad, og).max() < TOL
+    o2, s2 = ev.eval(X)
+    assert relerr(o2[:, :7], oo).max() < TOL
+    ev.close()
+    # an asymmetric association list (only the upper triangle listed twice as heavy) is the same quadratic form
+    up = md.sparse_row <= md.sparse_col
+    md.sparse_val = np.where(md.sparse_row == md.sparse_col, md.sparse_val, 2.0 * md.sparse_val)[up]
+    md.sparse_row, md.sparse_col = md.sparse_row[up], md.sparse_col[up]
+    ev = binding.Evaluator(md)
+    o3, g3, s3 = ev.eval_grad(X)
+    assert relerr(o3[:, :7], oo).max() < TOL and grad_relerr(g3, og).max() < TOL
+    ev.close()
+
+
 def test_value_only_cholesky_path():
     """mcd_eval uses quad = |L^T dx|^2 (triangular contraction, half the flops): with the factor supplied
     by the caller, factorised by the library, and -- for an indefinite matrix -- the symmetric fallback"""

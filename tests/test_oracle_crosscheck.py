@@ -74,6 +74,24 @@ def test_gradient_matches_high_precision_finite_differences():
         assert abs(fd - gd[j]) <= 1e-9 * max(1.0, abs(fd)), (j, fd, gd[j])
 
 
+def test_sparse_likelihood_oracle():
+    """Sparse likelihood: oracle vs mpmath, port gradient vs duals, and sparse == full on the same matrix"""
+    md, h = synth.synthetic_model(12, seed=3, likelihood=model.LIK_SPARSE, n_cal=2, clock_model=2)
+    X = synth.synthetic_states(md, h, 3)
+    orc = O.Oracle(md)
+    out, grad, st = orc.eval_grad(X)
+    p = MP.ln_posterior_parts(md, X[0])
+    assert abs((mp.mpf(out[0, 4]) - p["lik"]) / max(1, abs(p["lik"]))) < 1e-12
+    assert grad_relerr(grad[0], orc.grad_dual(X[0])).max() < TOL
+    dense = np.zeros((md.dim, md.dim))
+    np.add.at(dense, (md.sparse_row, md.sparse_col), md.sparse_val)
+    md_full = model.ModelDesc(parent=md.parent, mean=md.mean, precision=dense, logdet_sigma=md.logdet_sigma,
+                              clock_model=2, ht=md.ht, cal_node=md.cal_node, cal_lo=md.cal_lo, cal_lo_p=md.cal_lo_p,
+                              cal_hi=md.cal_hi, cal_hi_p=md.cal_hi_p)
+    of, gf, _ = O.Oracle(md_full).eval_grad(X)
+    assert relerr(out, of).max() < 1e-13 and grad_relerr(grad, gf).max() < 1e-12
+
+
 def test_generic_and_double_likelihood_agree():
     """reduceVMV (generic HMC target) and the BLAS-like Double path are the same number"""
     md, z = load_fixture("24-leaves-braces", 1)
