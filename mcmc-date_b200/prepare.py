@@ -162,6 +162,92 @@ def initial_state(parent, mean_lengths):
     return x
 
 
+# ----------------------------------------------------------------------------- on-disk formats
+def write_data_file(path, kind, mean=None, precision=None, logdet_sigma=None, variances=None, sparse=None):
+    """`<name>.data` as `prepare` writes it (app/Main.hs:75-81,286): aeson `deriveJSON defaultOptions` of
+    LikelihoodDataStore, i.e. {"tag": "FullS", "contents": [mu, rows, logdet]} etc."""
+    if kind == "FullS":
+        obj = {"tag": kind, "contents": [list(map(float, mean)), [list(map(float, r)) for r in precision], float(logdet_sigma)]}
+    elif kind == "SparseS":
+        r, c, v = sparse
+        obj = {"tag": kind, "contents": [list(map(float, mean)), [[[int(i), int(j)], float(x)] for i, j, x in zip(r, c, v)],
+                                         float(logdet_sigma)]}
+    elif kind == "UnivariateS":
+        obj = {"tag": kind, "contents": [list(map(float, mean)), list(map(float, variances))]}
+    elif kind == "NoLikelihoodS":
+        obj = {"tag": kind}
+    else:
+        raise ValueError("unknown LikelihoodDataStore constructor " + kind)
+    with open(path, "w") as f:
+        json.dump(obj, f)
+
+
+def read_data_file(path):
+    """getData (app/Main.hs:85-99) -> dict(likelihood, mean, precision | variances | sparse, logdet_sigma)"""
+    with open(path) as f:
+        obj = json.load(f)
+    tag, c = obj["tag"], obj.get("contents")
+    if tag == "FullS":
+        return {"likelihood": _m.LIK_FULL, "mean": np.array(c[0]), "precision": np.array(c[1]), "logdet_sigma": float(c[2])}
+    if tag == "SparseS":
+        r = np.array([e[0][0] for e in c[1]], np.int32)
+        col = np.array([e[0][1] for e in c[1]], np.int32)
+        v = np.array([e[1] for e in c[1]], float)
+        return {"likelihood": _m.LIK_SPARSE, "mean": np.array(c[0]), "sparse": (r, col, v), "logdet_sigma": float(c[2])}
+    if tag == "UnivariateS":
+        var = np.array(c[1])
+        return {"likelihood": _m.LIK_UNIVARIATE, "mean": np.array(c[0]), "variances": var,
+                "logdet_sigma": float(np.sum(np.log(var)))}   # logSigmaSquaredProduct (app/Probability.hs:274)
+    if tag == "NoLikelihoodS":
+        return {"likelihood": _m.LIK_NONE}
+    raise ValueError("getData: Could not decode data file: " + path)
+
+
+def mean_tree_newick(parent, names, mean_lengths) -> str:
+    """`<name>.meantree` (app/Main.hs:289-307): the first tree's topology with mean branch lengths; unnamed
+    (inner) nodes get their running pre-order index as label (assignIndices, app/Tools.hs:73-81)."""
+    c0, c1 = _tree.children_from_parent(np.asarray(parent))
+
+    def label(i):
+        nm = names[i]
+        return nm if nm and not nm.isdigit() else str(i)
+
+    def rec(i):
+        s = label(i) + ":" + repr(float(mean_lengths[i]))
+        if c0[i] < 0:
+            return s
+        return "(" + rec(int(c0[i])) + "," + rec(int(c1[i])) + ")" + s
+
+    return rec(0) + ";"
+
+
+def model_from_data_file(data_path, meantree_text, calibrations_text=None, constraints_text=None, braces_text=None,
+                         clock_model=_m.UNCORRELATED_LOGNORMAL):
+    """run / continue mode inputs (app/Main.hs:370-417): `<name>.data` + `<name>.meantree` (+ auxiliary
+    files) -> (ModelDesc, initial state)."""
+    dat = read_data_file(data_path)
+    parent, c0, c1, names, lengths = _tree.flatten_preorder(_tree.parse_newick(meantree_text))
+    cal = load_calibrations(calibrations_text, parent, names) if calibrations_text else None
+    con = load_constraints(constraints_text, parent, names) if constraints_text else None
+    br = load_braces(braces_text, parent, names) if braces_text else None
+    kw = {}
+    if cal:
+        kw.update(cal_node=cal["node"], cal_lo=cal["lo"], cal_lo_p=cal["lo_p"], cal_hi=cal["hi"], cal_hi_p=cal["hi_p"])
+    if con:
+        kw.update(con_young=con["young"], con_old=con["old"], con_p=con["p"])
+    if br:
+        kw.update(brace_off=br["off"], brace_node=br["node"], brace_sd=br["sd"])
+    lik = dat["likelihood"]
+    K = len(parent) - 2
+    md = _m.ModelDesc(parent=parent, mean=dat.get("mean", np.zeros(K)),
+                      precision=dat.get("precision", dat.get("variances", np.zeros(0))),
+                      logdet_sigma=dat.get("logdet_sigma", 0.0), clock_model=clock_model, likelihood=lik,
+                      ht=mean_root_height(cal) if cal else 1.0, **kw)
+    if lik == _m.LIK_SPARSE:
+        md.sparse_row, md.sparse_col, md.sparse_val = dat["sparse"]
+    return md, initial_state(parent, lengths)
+
+
 def model_from_files(treelist_text, calibrations_text=None, constraints_text=None, braces_text=None,
                      clock_model=_m.UNCORRELATED_LOGNORMAL, likelihood=_m.LIK_FULL):
     """Everything `getMcmcProps` assembles (app/Main.hs:370-457) -> (ModelDesc, prepared dict)."""

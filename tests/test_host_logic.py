@@ -90,6 +90,34 @@ def test_prepare_matches_numpy_and_is_invertible():
     assert np.allclose(pr["precision"], md.precision, rtol=1e-13, atol=0)
 
 
+def test_data_and_meantree_formats_roundtrip(tmp_path):
+    """<name>.data (aeson LikelihoodDataStore JSON) and <name>.meantree as `prepare` writes them
+    (app/Main.hs:75-99,286-307) feed the same model the tree list gave"""
+    md, z = load_fixture("12-leaves-variable-rate")
+    names = [str(x) for x in z["leaf_names"]]
+    lengths = np.abs(np.random.default_rng(0).normal(0.2, 0.05, md.n_nodes))
+    lengths[0] = 0.0
+    f = tmp_path / "a.data"
+    prepare.write_data_file(str(f), "FullS", mean=md.mean, precision=md.precision, logdet_sigma=md.logdet_sigma)
+    obj = __import__("json").load(open(f))
+    assert obj["tag"] == "FullS" and len(obj["contents"]) == 3 and len(obj["contents"][1]) == md.dim
+    mt = prepare.mean_tree_newick(md.parent, names, lengths)
+    md2, x0 = prepare.model_from_data_file(str(f), mt)
+    assert np.array_equal(md2.parent, md.parent) and np.array_equal(md2.precision, md.precision)
+    assert md2.logdet_sigma == md.logdet_sigma and np.array_equal(md2.mean, md.mean)
+    assert x0[3] == 1.0 and len(x0) == md.state_len
+    # inner nodes carry their pre-order index as label (assignIndices)
+    p2, _, _, nm2, ln2 = tree.flatten_preorder(tree.parse_newick(mt))
+    assert nm2[0] == "0" and nm2[1] == "1" and np.allclose(ln2, lengths)
+    for kind, kw in (("UnivariateS", dict(mean=md.mean, variances=1.0 / np.diag(md.precision))),
+                     ("NoLikelihoodS", {}),
+                     ("SparseS", dict(mean=md.mean, sparse=([0, 1, 1], [0, 1, 0], [2.0, 3.0, 0.5]), logdet_sigma=1.5))):
+        prepare.write_data_file(str(f), kind, **kw)
+        d = prepare.read_data_file(str(f))
+        assert d["likelihood"] == {"UnivariateS": 1, "NoLikelihoodS": 2, "SparseS": 3}[kind]
+    assert d["sparse"][2].tolist() == [2.0, 3.0, 0.5]
+
+
 def test_loaders_pin_survey_integer_fixtures():
     """node indices derived in SURVEY.md 8c"""
     _, z12 = load_fixture("12-leaves-variable-rate")
