@@ -215,7 +215,7 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   }
   if (small) {
     // one fused launch: tables and P in shared memory, one warp per chain
-    const size_t fsmem = POST_SMEM_FIXED + ((size_t)M.K * M.K + (size_t)(POST_THREADS / 32) * (M.S + 2 * M.K)) * 8;
+    const size_t fsmem = POST_SMEM_FIXED + ((size_t)M.K * M.K + (size_t)(POST_THREADS / 32) * (M.S + M.N + M.K)) * 8;
     const int fgrid = std::min(grid, 2 * h->n_sms);
     double* fo = d_out + (size_t)c0 * MCD_OUT_COLS;
     double* fg = GRAD ? d_grad + (size_t)c0 * M.S : nullptr;
@@ -257,7 +257,7 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   double* g = GRAD ? d_grad + (size_t)c0 * M.S : nullptr;
   int32_t* s = d_status + c0;
   // shared memory: reduction scratch + per chain group the staged state row [S] and contraction result [K]
-  const size_t smem = POST_SMEM_FIXED + (size_t)cpb * (M.S + M.K) * 8;
+  const size_t smem = POST_SMEM_FIXED + (size_t)cpb * (M.S + M.N) * 8;
 #define MCD_LAUNCH_POST(GG, CC, MB) \
   posterior_kernel<GG, CC, GRAD, MB><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n)
 #define MCD_LAUNCH_POST_G(GG, MB)                                              \
@@ -587,7 +587,7 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
     if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
   // posterior kernels may need > 48 KiB dynamic smem on large trees
   {
-    const size_t post_smem = POST_SMEM_FIXED + (size_t)(N <= SMALL_TREE_MAX_NODES ? POST_THREADS / 32 : 1) * (h->S + K) * 8;
+    const size_t post_smem = POST_SMEM_FIXED + (size_t)(N <= SMALL_TREE_MAX_NODES ? POST_THREADS / 32 : 1) * (h->S + N) * 8;
     if (post_smem > 220 * 1024) return bail("mcd_create: tree too large for the posterior kernel's shared-memory staging (N > 9000)");
     const int lim = 225 * 1024;
 #define MCD_SET_SMEM(CC)                                                                                               \

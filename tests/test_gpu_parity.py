@@ -94,6 +94,26 @@ def test_synthetic_trees_ragged_batches(n_leaves, B, clock):
     ev.close()
 
 
+@pytest.mark.parametrize("n_leaves,clock", [(150, 1), (150, 2), (40, 3), (1000, 1)])
+def test_near_critical_birth_death_on_all_kernel_paths(n_leaves, clock):
+    """|lambda - mu| < 1e-6: the literal near-critical D/E recursion (value and reverse-mode gradient) in the
+    large-tree kernel (CTA per chain) and in the fused small-tree kernel"""
+    md, h = synth.synthetic_model(n_leaves, seed=9 + n_leaves, clock_model=clock, n_cal=3, n_con=2, n_brace=1)
+    X = synth.synthetic_states(md, h, 40)
+    X[1, 1] = X[1, 0] + 2e-7
+    X[2, 1] = X[2, 0]
+    X[3, 1] = X[3, 0] - 9.9e-7
+    X[4, 1] = X[4, 0] + 1.01e-6          # just outside: closed form
+    ev = binding.Evaluator(md)
+    out, grad, st = ev.eval_grad(X)
+    oo, og, ost = O.Oracle(md).eval_grad(X, nthreads=4)
+    assert np.array_equal(st, ost) and (st[1:4] == model.ST_NEARCRIT).all() and st[4] == 0
+    assert relerr(out[:, :7], oo).max() < TOL and grad_relerr(grad, og).max() < TOL
+    o2, s2 = ev.eval(X)
+    assert relerr(o2[:, :7], oo).max() < TOL
+    ev.close()
+
+
 def test_thousand_leaf_tree_against_oracle():
     """configs[4] shape at a batch the oracle finishes in seconds"""
     md, h = synth.synthetic_model(1000, seed=synth.BASE_SEED + 4, n_cal=16, n_con=8, n_brace=4)
