@@ -38,6 +38,9 @@ CHAINS_PER_GPU = 8192
 METRIC = "log-posterior+gradient evals/sec (batched chains)"
 UNIT = "evals/s"
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 FP64 FMA/clk/SM x 1965 MHz = 37.2
+# dram__bytes_read.sum + dram__bytes_write.sum of gemm_f64_dmma_kernel at this shape, one `ncu --set full`
+# capture (profiles/r01_ncu_summary.md, r01_kernels_final): 237.9 MB + 113.7 MB; algorithmic: 297 MB
+NCU_GEMM_DRAM_BYTES = 351.5e6
 
 
 def workload_config(n_gpus, chains):
@@ -113,10 +116,12 @@ def cpu_port_rate(md, X, threads, target_seconds=12.0):
     orc.eval_grad(X[:probe], nthreads=threads)
     dt = time.perf_counter() - t0
     n = int(max(probe, min(len(X), probe * target_seconds / max(dt, 1e-6))))
+    reps = max(1, int(round(1.5 * probe / max(dt, 1e-6) / n)))   # ~1.5 s wall on all threads (20-30 core-seconds)
     t0 = time.perf_counter()
-    orc.eval_grad(X[:n], nthreads=threads)
+    for _ in range(reps):
+        orc.eval_grad(X[:n], nthreads=threads)
     dt = time.perf_counter() - t0
-    return n / dt, n, dt
+    return n * reps / dt, n * reps, dt
 
 
 def run_reference(args):
@@ -285,7 +290,8 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "roofline": {
                 "kernel": "gemm_f64_dmma_kernel", "bound": "tensor", "achieved": achieved, "peak": FP64_NOMINAL_TFLOPS,
-                "unit": "TFLOP/s", "frac": achieved / FP64_NOMINAL_TFLOPS, "traffic": args.traffic,
+                "unit": "TFLOP/s", "frac": achieved / FP64_NOMINAL_TFLOPS,
+                "traffic": args.traffic if B == CHAINS_PER_GPU else None,
                 "peak_source": "nominal FP64 (148 SMs x 64 FMA/clk x 1965 MHz); MEASURED_PEAKS.json has no FP64 entry; "
                                "cublasDgemm on this shape measured 35.6 TFLOP/s executed (profiles/)",
                 "kernel_ms": gemm_ms, "algorithmic_flops_per_launch": flops_alg,
@@ -317,7 +323,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from ncu (profiles/), if known")
+    ap.add_argument("--traffic", type=float, default=NCU_GEMM_DRAM_BYTES,
+                    help="dram bytes per launch of the contraction kernel from ncu (profiles/r01_ncu_summary.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
