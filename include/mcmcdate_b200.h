@@ -122,6 +122,18 @@ int mcd_eval_grad_theta(mcd_handle* h, int32_t n_chains, const double* theta /*[
                         const double* base_state /*[S]*/, double* out /*[B][MCD_OUT_COLS]*/,
                         double* grad_theta /*[B][D]*/, int32_t* status /*[B]*/);
 
+/* Device-resident leapfrog trajectory (first half of SURVEY 8f rank 1): n_steps leapfrog steps of the
+ * Hamiltonian H = -ln post(theta) + 1/2 p^T M^-1 p (M diagonal) for every chain, positions / momenta /
+ * gradients never leaving HBM between the two ends.  The integrator is the one behind the reference's
+ * Hamiltonian proposal (app/Hamiltonian.hs:95-104 -> `mcmc`): half kick, drift, ..., half kick.
+ * energy[b] = (H at the start, H at the end); out = ln-posterior parts at the end point;
+ * status[b] = OR of the status words of every gradient evaluation of the trajectory. */
+int mcd_leapfrog(mcd_handle* h, int32_t n_chains, int32_t n_steps, const double* theta0 /*[B][D]*/,
+                 const double* momentum0 /*[B][D]*/, const double* base_state /*[S]*/,
+                 const double* inv_mass /*[D]*/, const double* step_size /*[B]*/, double* theta_out /*[B][D]*/,
+                 double* momentum_out /*[B][D]*/, double* out /*[B][MCD_OUT_COLS]*/, double* energy /*[B][2]*/,
+                 int32_t* status /*[B]*/);
+
 /* evaluation with DEVICE buffers already resident in HBM (no copies); `stream` is a cudaStream_t
  * or NULL.  Asynchronous: returns after enqueueing. */
 int mcd_eval_device(mcd_handle* h, int32_t n_chains, const double* d_states, double* d_out,

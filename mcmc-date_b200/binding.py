@@ -19,7 +19,7 @@ _LIB = None
 
 EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
-    "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta",
+    "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_leapfrog",
     "mcd_eval_device",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
     "mcd_kernel_times",
@@ -72,6 +72,7 @@ def load_library():
     L.mcd_eval.argtypes = [vp, i32, dp, dp, ip]
     L.mcd_eval_grad.argtypes = [vp, i32, dp, dp, dp, ip]
     L.mcd_eval_grad_theta.argtypes = [vp, i32, dp, dp, dp, dp, ip]
+    L.mcd_leapfrog.argtypes = [vp, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip]
     L.mcd_eval_device.argtypes = [vp, i32, vp, vp, vp, vp]
     L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mcd_kernel_launches.argtypes = [vp]
@@ -198,6 +199,20 @@ class Evaluator:
         status = np.empty(B, np.int32) if status is None else status
         self._check(self._L.mcd_eval_grad_theta(self.h, B, _dp(T), _dp(base), _dp(out), _dp(grad_theta), _ip(status)))
         return out, grad_theta, status
+
+    def leapfrog(self, theta0, momentum0, base_state, inv_mass, step_size, n_steps: int):
+        """n_steps leapfrog steps, resident on the device -> (theta, momentum, out, energy[B,2], status)"""
+        T = np.ascontiguousarray(theta0, dtype=np.float64).reshape(-1, self.D)
+        P = np.ascontiguousarray(momentum0, dtype=np.float64).reshape(-1, self.D)
+        B = T.shape[0]
+        base = np.ascontiguousarray(base_state, dtype=np.float64)
+        im = np.ascontiguousarray(inv_mass, dtype=np.float64)
+        eps = np.ascontiguousarray(np.broadcast_to(np.asarray(step_size, dtype=np.float64), (B,)))
+        th, pm = np.empty_like(T), np.empty_like(P)
+        out, en, st = np.empty((B, _m.OUT_COLS)), np.empty((B, 2)), np.empty(B, np.int32)
+        self._check(self._L.mcd_leapfrog(self.h, B, int(n_steps), _dp(T), _dp(P), _dp(base), _dp(im), _dp(eps), _dp(th),
+                                         _dp(pm), _dp(out), _dp(en), _ip(st)))
+        return th, pm, out, en, st
 
     def eval_grad_theta_ptr(self, B: int, theta_ptr: int, base_ptr: int, out_ptr: int, gtheta_ptr: int, status_ptr: int):
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)

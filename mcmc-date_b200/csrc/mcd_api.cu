@@ -23,6 +23,7 @@
 
 #include "../../include/mcmcdate_b200.h"
 #include "gemm_f64.cuh"
+#include "hmc_kernels.cuh"
 #include "posterior_kernels.cuh"
 
 using namespace mcd;
@@ -65,6 +66,7 @@ struct mcd_handle {
   DevBuf d_dx, d_y;               // internal: residuals and P.dx
   DevBuf d_states, d_out, d_grad, d_status;  // staging for the host-buffer API
   DevBuf d_theta, d_gtheta, d_base, d_tidx, d_sidx;  // theta-packed API
+  DevBuf d_mom, d_eps, d_invmass, d_energy, d_status_acc;  // device-resident leapfrog trajectories
   cudaStream_t streams[N_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
   std::mutex mtx;
   std::string err;
@@ -101,7 +103,8 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
   int need = (n_chains + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
   if (need > h->cap) {
     CU_TRY(h, cudaDeviceSynchronize());
-    for (DevBuf* b : {&h->d_dx, &h->d_y, &h->d_states, &h->d_out, &h->d_grad, &h->d_status, &h->d_theta, &h->d_gtheta}) {
+    for (DevBuf* b : {&h->d_dx, &h->d_y, &h->d_states, &h->d_out, &h->d_grad, &h->d_status, &h->d_theta, &h->d_gtheta,
+                      &h->d_mom, &h->d_eps, &h->d_energy, &h->d_status_acc}) {
       if (b->p) cudaFree(b->p);
       b->p = nullptr;
     }
@@ -353,6 +356,76 @@ int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* bas
     CU_TRY(h, cudaMemcpyAsync(gtheta + (size_t)c0 * D, d_gt, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st));
   }
   for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
+  return 0;
+}
+
+// L leapfrog steps for n chains, everything resident on the device between the two ends
+int leapfrog_host(mcd_handle* h, int n, int L, const double* theta0, const double* mom0, const double* base,
+                  const double* inv_mass, const double* eps, double* theta_out, double* mom_out, double* out,
+                  double* energy, int32_t* status) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (n <= 0) return 0;
+  if (L < 1) return fail(h, "mcd_leapfrog: n_steps must be >= 1");
+  if (!theta0 || !mom0 || !base || !inv_mass || !eps || !theta_out || !mom_out || !out || !energy || !status)
+    return fail(h, "null host buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (ensure_capacity(h, n, true, true)) return -1;
+  const int S = h->S, D = h->D;
+  const size_t nd = (size_t)h->cap * D * 8;
+  if (!h->d_theta.p) CU_TRY(h, cudaMalloc(&h->d_theta.p, nd));
+  if (!h->d_gtheta.p) CU_TRY(h, cudaMalloc(&h->d_gtheta.p, nd));
+  if (!h->d_mom.p) CU_TRY(h, cudaMalloc(&h->d_mom.p, nd));
+  if (!h->d_eps.p) CU_TRY(h, cudaMalloc(&h->d_eps.p, (size_t)h->cap * 8));
+  if (!h->d_energy.p) CU_TRY(h, cudaMalloc(&h->d_energy.p, (size_t)h->cap * 16));
+  if (!h->d_status_acc.p) CU_TRY(h, cudaMalloc(&h->d_status_acc.p, (size_t)h->cap * 4));
+  if (!h->d_invmass.p) CU_TRY(h, cudaMalloc(&h->d_invmass.p, (size_t)std::max(D, 1) * 8));
+  cudaStream_t st = h->streams[0];
+  double* th = h->d_theta.as<double>();
+  double* gt = h->d_gtheta.as<double>();
+  double* pm = h->d_mom.as<double>();
+  double* xs = h->d_states.as<double>();
+  double* o = h->d_out.as<double>();
+  double* en = h->d_energy.as<double>();
+  int32_t* stp = h->d_status.as<int32_t>();
+  int32_t* sacc = h->d_status_acc.as<int32_t>();
+  const size_t nb = (size_t)n * D * 8;
+  CU_TRY(h, cudaMemcpyAsync(th, theta0, nb, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(pm, mom0, nb, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(h->d_eps.p, eps, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(h->d_invmass.p, inv_mass, (size_t)D * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemsetAsync(sacc, 0, (size_t)n * 4, st));
+  const dim3 gS((S + POST_THREADS - 1) / POST_THREADS, n), gD((D + HMC_THREADS - 1) / HMC_THREADS, n);
+  auto gradient = [&]() -> int {  // theta -> states -> (ln post, grad) -> packed gradient
+    unpack_theta_kernel<<<gS, POST_THREADS, 0, st>>>(th, h->d_base.as<double>(), h->d_tidx.as<int>(), xs, S, D, n);
+    if (enqueue<true>(h, 0, n, xs, o, h->d_grad.as<double>(), stp, st)) return -1;
+    pack_theta_kernel<<<gD, POST_THREADS, 0, st>>>(h->d_grad.as<double>(), h->d_sidx.as<int>(), gt, S, D, n);
+    h->launches += 2;
+    return 0;
+  };
+  const double* im = h->d_invmass.as<double>();
+  const double* ep = h->d_eps.as<double>();
+  const int gE = (n + HMC_THREADS / 32 - 1) / (HMC_THREADS / 32);
+  if (gradient()) return -1;
+  hamiltonian_kernel<<<gE, HMC_THREADS, 0, st>>>(pm, im, o, en, 0, D, n);
+  leapfrog_update_kernel<<<gD, HMC_THREADS, 0, st>>>(th, pm, gt, im, ep, 0.5, 1, stp, sacc, D, n);
+  h->launches += 2;
+  for (int l = 1; l <= L; ++l) {
+    if (gradient()) return -1;
+    if (l < L) leapfrog_update_kernel<<<gD, HMC_THREADS, 0, st>>>(th, pm, gt, im, ep, 1.0, 1, stp, sacc, D, n);
+    else leapfrog_update_kernel<<<gD, HMC_THREADS, 0, st>>>(th, pm, gt, im, ep, 0.5, 0, stp, sacc, D, n);
+    h->launches += 1;
+  }
+  hamiltonian_kernel<<<gE, HMC_THREADS, 0, st>>>(pm, im, o, en, 1, D, n);
+  h->launches += 1;
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaMemcpyAsync(theta_out, th, nb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(mom_out, pm, nb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(out, o, (size_t)n * MCD_OUT_COLS * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(energy, en, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(status, sacc, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -654,6 +727,12 @@ int mcd_eval_grad(mcd_handle* h, int32_t n, const double* states, double* out, d
 int mcd_eval_grad_theta(mcd_handle* h, int32_t n, const double* theta, const double* base_state, double* out,
                         double* grad_theta, int32_t* status) {
   return eval_theta_host(h, n, theta, base_state, out, grad_theta, status);
+}
+int mcd_leapfrog(mcd_handle* h, int32_t n, int32_t n_steps, const double* theta0, const double* momentum0,
+                 const double* base_state, const double* inv_mass, const double* step_size, double* theta_out,
+                 double* momentum_out, double* out, double* energy, int32_t* status) {
+  return leapfrog_host(h, n, n_steps, theta0, momentum0, base_state, inv_mass, step_size, theta_out, momentum_out, out,
+                       energy, status);
 }
 int mcd_eval_device(mcd_handle* h, int32_t n, const double* d_states, double* d_out, int32_t* d_status, void* stream) {
   return eval_device<false>(h, n, d_states, d_out, nullptr, d_status, stream);

@@ -295,6 +295,57 @@ def test_value_only_cholesky_path():
     ev.close()
 
 
+def _oracle_leapfrog(orc, x0, theta, mom, inv_mass, eps, L):
+    """half kick, drift, ..., half kick with the ORACLE's gradient (host loop, float64)"""
+    theta, mom = theta.copy(), mom.copy()
+
+    def grad(th):
+        X = np.array([orc.from_vector(x0, t) for t in th])
+        out, g, st = orc.eval_grad(X)
+        return out, np.array([orc.to_vector(gi) for gi in g]), st
+
+    out, g, st = grad(theta)
+    h0 = -out[:, 6] + 0.5 * (mom * mom * inv_mass).sum(axis=1)
+    stat = st.copy()
+    for l in range(L):
+        mom = mom + 0.5 * eps[:, None] * g
+        theta = theta + eps[:, None] * inv_mass * mom
+        out, g, st = grad(theta)
+        stat |= st
+        mom = mom + 0.5 * eps[:, None] * g
+    h1 = -out[:, 6] + 0.5 * (mom * mom * inv_mass).sum(axis=1)
+    return theta, mom, out, np.stack([h0, h1], axis=1), stat
+
+
+@pytest.mark.parametrize("n_leaves,B,L", [(24, 33, 6), (300, 20, 4)])
+def test_device_resident_leapfrog(n_leaves, B, L):
+    """mcd_leapfrog == the same integrator driven step by step from the host with the oracle's gradient"""
+    md, h = synth.synthetic_model(n_leaves, seed=31 + n_leaves, n_cal=3, n_con=2, n_brace=0)
+    X = synth.synthetic_states(md, h, B)
+    ev = binding.Evaluator(md)
+    orc = O.Oracle(md)
+    theta = np.array([orc.to_vector(x) for x in X])
+    rng = np.random.default_rng(4)
+    _, g0, _ = orc.eval_grad(X)
+    gth = np.array([orc.to_vector(gi) for gi in g0])
+    inv_mass = 1.0 / np.maximum(1.0, np.abs(gth).max(axis=0)) ** 2       # crude per-parameter scale
+    mom = rng.normal(size=theta.shape) / np.sqrt(inv_mass)
+    eps = np.full(B, 0.02) * rng.uniform(0.5, 1.0, B)
+    th, pm, out, en, st = ev.leapfrog(theta, mom, X[0], inv_mass, eps, L)
+    rt, rp, ro, re, rs = _oracle_leapfrog(orc, X[0], theta, mom, inv_mass, eps, L)
+    assert np.array_equal(st, rs)
+    ok = rs == 0
+    assert ok.sum() >= B // 2
+    assert (np.abs(th - rt)[ok] <= 1e-9 * np.maximum(1.0, np.abs(rt[ok]))).all()
+    assert (np.abs(pm - rp)[ok] <= 1e-9 * np.maximum(1.0, np.abs(rp[ok]).max(axis=1, keepdims=True))).all()
+    assert relerr(out[ok, :7], ro[ok]).max() < 1e-9 and relerr(en[ok], re[ok]).max() < 1e-9
+    # the integrator is symplectic and time-reversible: flip the momentum, integrate back, land on the start
+    th2, pm2, _, en2, _ = ev.leapfrog(th[ok], -pm[ok], X[0], inv_mass, eps[ok], L)
+    assert (np.abs(th2 - theta[ok]) <= 1e-8 * np.maximum(1.0, np.abs(theta[ok]))).all()
+    assert relerr(en2[:, 1], en[ok, 0]).max() < 1e-9
+    ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
