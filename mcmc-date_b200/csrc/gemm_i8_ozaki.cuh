@@ -1,0 +1,331 @@
+// gemm_i8_ozaki.cuh -- the FP64 contraction  Y = DX . P  on the INT8 tensor pipe (tcgen05 + TMEM).
+//
+//   Y[b][m] = sum_k P[m][k] * DX[b][k]          b = chain, m/k = branch (MVN dimension)
+//
+// Same product as gemm_f64.cuh (the batched  dxs <# sigmaInv  of app/Probability.hs:169), evaluated with
+// the error-free integer splitting of Ozaki et al.: every row of an operand is written as
+//
+//   x[k] = scale * sum_{s=0}^{S-1} q_s[k] * 2^(-7 (s+1)),      q_0 in [-127, 127], q_s in [-64, 64]  (int8 "digit planes")
+//
+// (scale = a power of two per row, so the split is exact up to the dropped tail 2^(-7S-1) * scale).  The
+// product of two rows is then sum_{s,t} 2^(-7(s+t+2)) * <q_s, p_t>; the integer dot products are EXACT on
+// the INT8 tensor cores (int32 accumulation: |q p| <= 2^14, K <= 2^13, at most S pairs per accumulator),
+// pairs with s + t >= S are below the dropped tail and skipped, and all pairs with the same s + t share
+// one TMEM accumulator.  S = 8: 36 int8 products, error ~ the rounding error of an FP64 GEMM;
+// S = 7: 28 products, ~2^-45 relative to |P|.|dx|.  Integer accumulation makes the result
+// bit-reproducible and independent of tiling / summation order.
+//
+// Kernel: one CTA = 128 chains (UMMA M, TMEM lanes) x 64 P rows (UMMA N), S accumulators of 64 TMEM
+// columns (S*64 <= 512).  Warp-specialised: warp 0 = TMA producer (all digit planes of both operands for
+// one 64-byte k-block per stage, SWIZZLE_64B), warp 1 = TMEM allocator + single-thread tcgen05.mma
+// issuer (kind::i8, M128 N64 K32), warps 2-5 = epilogue (tcgen05.ld, Horner in FP64, row/column scales).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_f64.cuh"  // mbarrier / TMA wrappers, get_encode_tiled
+
+namespace mcd {
+
+constexpr int OZ_M = 128;        // chains per CTA tile
+constexpr int OZ_N = 64;         // P rows per CTA tile
+constexpr int OZ_KB = 64;        // reduction elements (bytes) per pipeline stage = one swizzle row
+constexpr int OZ_UK = 32;        // reduction depth of one tcgen05.mma kind::i8
+constexpr int OZ_STAGES = 2;
+constexpr int OZ_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int OZ_TMEM_COLS = 512;
+constexpr int OZ_MAX_SLICES = 8;
+
+template <int S>
+__host__ __device__ constexpr int oz_stage_bytes() { return S * (OZ_M + OZ_N) * OZ_KB; }
+template <int S>
+__host__ __device__ constexpr size_t oz_smem_bytes() { return (size_t)OZ_STAGES * oz_stage_bytes<S>() + 1024 /*align*/ + 256 /*barriers*/; }
+
+// ------------------------------------------------------------------------------ tcgen05 wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(slot_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, int8 x int8 -> int32, issued by ONE thread.  COLLECT selects what happens
+// to the A operand in the tensor core's collector buffer: consecutive MMAs that share A read it from shared
+// memory once (SASS: UTCIMMA ... .A_KEEP / .A_REUSE).
+enum { OZ_A_DISCARD = 0, OZ_A_FILL = 1, OZ_A_USE = 2, OZ_A_LASTUSE = 3 };
+template <int COLLECT>
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+#define MCD_UMMA_I8(SUFFIX)                                                                       \
+  asm volatile(                                                                                   \
+      "{\n"                                                                                       \
+      ".reg .pred p;\n"                                                                           \
+      "setp.ne.b32 p, %4, 0;\n"                                                                   \
+      "tcgen05.mma.cta_group::1.kind::i8" SUFFIX " [%0], %1, %2, %3, p;\n"                        \
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)                  \
+      : "memory")
+  if (COLLECT == OZ_A_FILL) MCD_UMMA_I8(".collector::a::fill");
+  else if (COLLECT == OZ_A_USE) MCD_UMMA_I8(".collector::a::use");
+  else if (COLLECT == OZ_A_LASTUSE) MCD_UMMA_I8(".collector::a::lastuse");
+  else MCD_UMMA_I8("");
+#undef MCD_UMMA_I8
+}
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns: thread t of the warp gets lane (base lane + t)
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+// one lane of a converged warp (the compiler then predicates the single-thread tcgen05 / TMA instructions
+// instead of wrapping each of them in an elect-and-retry loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(tm) : "memory");
+}
+
+// shared-memory matrix descriptor, K-major operand tile of 64-byte rows, SWIZZLE_64B:
+//   start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 8 rows * 64 B = 512 B | version 1 | layout 4
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+// instruction descriptor: D = S32 (2 @4), A = B = signed int8 (1 @7, 1 @10), both K-major, N>>3 @17, M>>4 @24
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
+
+// ------------------------------------------------------------------------------ the contraction
+// tmA: digit planes of the residuals, [S][Bp][ld8] int8 seen as a 2-D [S*Bp][ld8] tensor, box 128 x 64
+// tmB: digit planes of P,             [S][Mp][ld8]                        [S*Mp][ld8],       box  64 x 64
+// scaleA[b] = row scale of chain b (NaN marks a chain with non-finite residuals), scaleB[m] = row scale of
+// P row m times 2^-14.  Grid: x = P-row tile (fastest: co-resident CTAs share the chains' planes), y = chain tile.
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ Y,
+                     int nkb, int ldy, int Bp, int Mp, int bt_base) {
+  static_assert(S >= 2 && S <= OZ_MAX_SLICES && S * OZ_N <= OZ_TMEM_COLS, "digit planes must fit TMEM");
+  constexpr int STAGE = oz_stage_bytes<S>();
+  constexpr int A_PLANE = OZ_M * OZ_KB, B_PLANE = OZ_N * OZ_KB;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)OZ_STAGES * STAGE);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* acc_full = empty + OZ_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
+  const int lane = threadIdx.x & 31;
+  const int pr0 = blockIdx.x * OZ_N;
+  const int bt0 = bt_base + blockIdx.y * OZ_M;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, OZ_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    const bool leader = elect_one();
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb % OZ_STAGES;
+      if (kb >= OZ_STAGES) mbar_wait(&empty[st], ((kb / OZ_STAGES) - 1) & 1);
+      if (leader) {
+        unsigned char* dst = smem + (size_t)st * STAGE;
+        mbar_arrive_expect_tx(&full[st], STAGE);
+#pragma unroll
+        for (int s = 0; s < S; ++s) tma_load_2d(dst + s * A_PLANE, &tmA, kb * OZ_KB, s * Bp + bt0, &full[st]);
+#pragma unroll
+        for (int s = 0; s < S; ++s) tma_load_2d(dst + S * A_PLANE + s * B_PLANE, &tmB, kb * OZ_KB, s * Mp + pr0, &full[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane)
+    const bool leader = elect_one();
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb % OZ_STAGES;
+      mbar_wait(&full[st], (kb / OZ_STAGES) & 1);
+      tc_fence_after();
+      if (leader) {
+        // descriptor of the stage base; planes / k-steps are 16-byte-granular offsets added to the address field
+        const uint64_t dbase = oz_smem_desc(smem_u32(smem + (size_t)st * STAGE));
+#pragma unroll
+        for (int ks = 0; ks < OZ_KB / OZ_UK; ++ks) {
+#pragma unroll
+          for (int a = 0; a < S; ++a) {
+            const uint64_t da = dbase + (uint64_t)((a * A_PLANE + ks * OZ_UK) >> 4);
+#pragma unroll
+            for (int b = 0; b + a < S; ++b) {
+              const uint64_t db = dbase + (uint64_t)((S * A_PLANE + b * B_PLANE + ks * OZ_UK) >> 4);
+              // the first product into accumulator d = a + b is (a = 0, b = d) of the first k-step
+              const uint32_t acc = (kb | ks | a) != 0 ? 1u : 0u;
+              const uint32_t td = tmem_base + (uint32_t)((a + b) * OZ_N);
+              // plane a of the chains is shared by the S - a products of this inner loop: keep it in the collector
+              if (S - a == 1) umma_i8<OZ_A_DISCARD>(td, da, db, OZ_IDESC, acc);
+              else if (b == 0) umma_i8<OZ_A_FILL>(td, da, db, OZ_IDESC, acc);
+              else if (b + a == S - 1) umma_i8<OZ_A_LASTUSE>(td, da, db, OZ_IDESC, acc);
+              else umma_i8<OZ_A_USE>(td, da, db, OZ_IDESC, acc);
+            }
+          }
+        }
+        umma_commit(&empty[st]);  // frees the stage once these MMAs have read it
+        if (kb == nkb - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: 4 warps x 32 TMEM lanes
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes 32 (warp % 4) .. +31
+    const int row = quarter * 32 + lane;
+    const int b = bt0 + row;
+    const double sa = scaleA[b];
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    double* yrow = Y + (size_t)b * ldy + pr0;
+#pragma unroll 1
+    for (int c = 0; c < OZ_N / 16; ++c) {
+      uint32_t v[S][16];
+#pragma unroll
+      for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        double r0 = (double)(int)v[S - 1][j], r1 = (double)(int)v[S - 1][j + 1];
+#pragma unroll
+        for (int d = S - 2; d >= 0; --d) {
+          r0 = fma(r0, 0.0078125, (double)(int)v[d][j]);
+          r1 = fma(r1, 0.0078125, (double)(int)v[d][j + 1]);
+        }
+        const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
+        *reinterpret_cast<double2*>(yrow + c * 16 + j) = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, OZ_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------ digit planes
+// One warp per row: x[k] (k < K) -> planes[s][row][k], s < S, and scale[row].  Rows are ld8 bytes apart,
+// planes plane_stride bytes apart; bytes k >= K of a row are left untouched (zero-initialised by the caller).
+// scale = 2^e with 2^(e-1) <= max|x| < 2^e (2^(e+1) if max|x| > 0.996 * 2^e), so |x / scale| <= 0.996: the leading
+// digit lies in [-127, 127], every later digit in [-64, 64].
+// A row holding a non-finite value gets scale = NaN (and zero digits): the whole output row becomes NaN.
+__device__ __forceinline__ double oz_row_scale(double amax, bool finite) {
+  if (!finite) return __longlong_as_double(0x7ff8000000000000LL);
+  if (amax == 0.0) return 0.0;
+  int e;
+  const double f = frexp(amax, &e);  // amax = f * 2^e, f in [0.5, 1)
+  return ldexp(1.0, f > 0.996 ? e + 1 : e);
+}
+template <int S>
+__device__ __forceinline__ void oz_digits(double x, double inv_scale, signed char (&q)[S]) {
+  double r = x * inv_scale;  // exact (power of two), |r| <= 0.996
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const double v = r * 128.0;
+    const double d = rint(v);
+    q[s] = (signed char)(int)d;
+    r = v - d;  // exact
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256)
+oz_split_rows_kernel(const double* __restrict__ X, int ldx, int rows, int K, signed char* __restrict__ planes, int ld8,
+                     size_t plane_stride, double* __restrict__ scale, double post_scale) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const double* x = X + (size_t)row * ldx;
+  double amax = 0.0;
+  bool finite = true;
+  for (int k = lane; k < K; k += 32) {
+    const double a = fabs(x[k]);
+    finite = finite && (a <= 1.7976931348623157e308);
+    amax = fmax(amax, a);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    finite = __shfl_xor_sync(0xffffffffu, (int)finite, off) && finite;
+  }
+  const double sc = oz_row_scale(amax, finite);
+  const double inv = (finite && amax > 0.0) ? 1.0 / sc : 0.0;
+  if (lane == 0) scale[row] = sc * post_scale;
+  signed char* out = planes + (size_t)row * ld8;
+  for (int k = lane; k < K; k += 32) {
+    signed char q[S];
+    oz_digits<S>(finite ? x[k] : 0.0, inv, q);
+#pragma unroll
+    for (int s = 0; s < S; ++s) out[(size_t)s * plane_stride + k] = q[s];
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+// tensor map over digit planes stacked along rows: [total_rows][ld8] int8, box = box_rows x 64 bytes, 64B swizzle
+inline int oz_make_plane_map(CUtensorMap* tm, const signed char* base, size_t total_rows, int ld8, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)ld8, (cuuint64_t)total_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld8};
+  cuuint32_t box[2] = {OZ_KB, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+template <int S>
+inline cudaError_t gemm_i8_ozaki_configure() {
+  return cudaFuncSetAttribute(gemm_i8_ozaki_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes<S>());
+}
+
+// Bp chains (multiple of 128) starting at bt_base, Mp P rows (multiple of 64), ld8 = padded K (multiple of 64)
+template <int S>
+inline cudaError_t gemm_i8_ozaki_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const double* scaleA,
+                                        const double* scaleB, double* Y, int Mp, int n_chains_padded, int ld8, int ldy,
+                                        int Bp_total, cudaStream_t st, int bt_base = 0) {
+  dim3 grid(Mp / OZ_N, n_chains_padded / OZ_M);
+  gemm_i8_ozaki_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), st>>>(tmA, tmB, scaleA, scaleB, Y, ld8 / OZ_KB, ldy,
+                                                                         Bp_total, Mp, bt_base);
+  return cudaGetLastError();
+}
+
+}  // namespace mcd
