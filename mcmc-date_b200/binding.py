@@ -20,7 +20,7 @@ _LIB = None
 EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
     "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_leapfrog",
-    "mcd_eval_device",
+    "mcd_eval_device", "mcd_set_contraction", "mcd_get_contraction",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
     "mcd_kernel_times",
 ]
@@ -75,6 +75,8 @@ def load_library():
     L.mcd_leapfrog.argtypes = [vp, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip]
     L.mcd_eval_device.argtypes = [vp, i32, vp, vp, vp, vp]
     L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.mcd_set_contraction.argtypes = [vp, i32]
+    L.mcd_get_contraction.argtypes = [vp]
     L.mcd_kernel_launches.argtypes = [vp]
     L.mcd_kernel_launches.restype = C.c_int64
     L.mcd_set_kernel_timing.argtypes = [vp, C.c_int]
@@ -237,6 +239,14 @@ class Evaluator:
 
     def kernel_launches(self) -> int:
         return int(self._L.mcd_kernel_launches(self.h))
+
+    def set_contraction(self, mode):
+        """'dmma' (FP64 tensor instructions) or 'i8s6' / 'i8s7' / 'i8s8' (INT8 tensor cores, n digit planes)"""
+        modes = {"dmma": 0, "i8s6": 6, "i8s7": 7, "i8s8": 8}
+        self._check(self._L.mcd_set_contraction(self.h, modes[mode] if isinstance(mode, str) else int(mode)))
+
+    def get_contraction(self) -> int:
+        return int(self._L.mcd_get_contraction(self.h))
 
     def set_kernel_timing(self, on: bool):
         self._check(self._L.mcd_set_kernel_timing(self.h, int(on)))

@@ -30,9 +30,15 @@ namespace mcd {
 
 constexpr int OZ_M = 128;        // chains per CTA tile
 constexpr int OZ_N = 64;         // P rows per CTA tile
-constexpr int OZ_KB = 64;        // reduction elements (bytes) per pipeline stage = one swizzle row
+#ifndef MCD_OZ_KB
+#define MCD_OZ_KB 32
+#endif
+constexpr int OZ_KB = MCD_OZ_KB; // reduction elements (bytes) per pipeline stage = one swizzle row (32 or 64)
 constexpr int OZ_UK = 32;        // reduction depth of one tcgen05.mma kind::i8
-constexpr int OZ_STAGES = 2;
+#ifndef MCD_OZ_STAGES
+#define MCD_OZ_STAGES (MCD_OZ_KB == 32 ? 4 : 2)
+#endif
+constexpr int OZ_STAGES = MCD_OZ_STAGES;
 constexpr int OZ_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int OZ_TMEM_COLS = 512;
 constexpr int OZ_MAX_SLICES = 8;
@@ -105,11 +111,16 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(tm) : "memory");
 }
 
-// shared-memory matrix descriptor, K-major operand tile of 64-byte rows, SWIZZLE_64B:
-//   start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 8 rows * 64 B = 512 B | version 1 | layout 4
+// shared-memory matrix descriptor, K-major operand tile of OZ_KB-byte rows, swizzled over the row length:
+//   start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 8 rows * OZ_KB bytes | version 1 |
+//   layout 4 (SWIZZLE_64B) or 6 (SWIZZLE_32B)
 __device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)4 << 61);
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((8 * OZ_KB) >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)(OZ_KB == 64 ? 4 : 6) << 61);
+}
+// exact int32 -> double without the conversion pipe: 2^52 + 2^31 + v as a bit pattern, minus the bias
+__device__ __forceinline__ double oz_i2d(uint32_t v) {
+  return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
 }
 // instruction descriptor: D = S32 (2 @4), A = B = signed int8 (1 @7, 1 @10), both K-major, N>>3 @17, M>>4 @24
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
@@ -139,16 +150,31 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int pr0 = blockIdx.x * OZ_N;
   const int bt0 = bt_base + blockIdx.y * OZ_M;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+  // producer: fills stage kb % STAGES with all digit planes of k-block kb
+  auto load_kblock = [&](int kb) {
+    const int st = kb % OZ_STAGES;
+    unsigned char* dst = smem + (size_t)st * STAGE;
+    mbar_arrive_expect_tx(&full[st], STAGE);
 #pragma unroll
-    for (int s = 0; s < OZ_STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < S; ++s) tma_load_2d(dst + s * A_PLANE, &tmA, kb * OZ_KB, s * Bp + bt0, &full[st]);
+#pragma unroll
+    for (int s = 0; s < S; ++s) tma_load_2d(dst + S * A_PLANE + s * B_PLANE, &tmB, kb * OZ_KB, s * Mp + pr0, &full[st]);
+  };
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+#pragma unroll
+      for (int s = 0; s < OZ_STAGES; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(acc_full, 1);
+      mbar_fence_init();
+      // the first loads start before the TMEM allocation and the CTA-wide barrier below
+      for (int kb = 0; kb < OZ_STAGES && kb < nkb; ++kb) load_kblock(kb);
     }
-    mbar_init(acc_full, 1);
-    mbar_fence_init();
+    __syncwarp();
   }
   if (warp == 1) tmem_alloc(tmem_slot, OZ_TMEM_COLS);
   tc_fence_before();
@@ -159,17 +185,13 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     const bool leader = elect_one();
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int st = kb % OZ_STAGES;
-      if (kb >= OZ_STAGES) mbar_wait(&empty[st], ((kb / OZ_STAGES) - 1) & 1);
-      if (leader) {
-        unsigned char* dst = smem + (size_t)st * STAGE;
-        mbar_arrive_expect_tx(&full[st], STAGE);
-#pragma unroll
-        for (int s = 0; s < S; ++s) tma_load_2d(dst + s * A_PLANE, &tmA, kb * OZ_KB, s * Bp + bt0, &full[st]);
-#pragma unroll
-        for (int s = 0; s < S; ++s) tma_load_2d(dst + S * A_PLANE + s * B_PLANE, &tmB, kb * OZ_KB, s * Mp + pr0, &full[st]);
-      }
+#ifdef MCD_OZ_NO_REFILL
+    for (int kb = nkb; kb < nkb; ++kb) {
+#else
+    for (int kb = OZ_STAGES; kb < nkb; ++kb) {
+#endif
+      mbar_wait(&empty[kb % OZ_STAGES], ((kb / OZ_STAGES) - 1) & 1);
+      if (leader) load_kblock(kb);
       __syncwarp();
     }
   } else if (warp == 1) {
@@ -177,6 +199,9 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool leader = elect_one();
     for (int kb = 0; kb < nkb; ++kb) {
       const int st = kb % OZ_STAGES;
+#ifdef MCD_OZ_NO_REFILL
+      if (kb < OZ_STAGES)
+#endif
       mbar_wait(&full[st], (kb / OZ_STAGES) & 1);
       tc_fence_after();
       if (leader) {
@@ -216,19 +241,23 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tc_fence_after();
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     double* yrow = Y + (size_t)b * ldy + pr0;
+#ifdef MCD_OZ_NO_EPI
+    for (int c = 0; c < (int)(sa == 12345.678); ++c) {
+#else
 #pragma unroll 1
     for (int c = 0; c < OZ_N / 16; ++c) {
+#endif
       uint32_t v[S][16];
 #pragma unroll
       for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
-        double r0 = (double)(int)v[S - 1][j], r1 = (double)(int)v[S - 1][j + 1];
+        double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
 #pragma unroll
         for (int d = S - 2; d >= 0; --d) {
-          r0 = fma(r0, 0.0078125, (double)(int)v[d][j]);
-          r1 = fma(r1, 0.0078125, (double)(int)v[d][j + 1]);
+          r0 = fma(r0, 0.0078125, oz_i2d(v[d][j]));
+          r1 = fma(r1, 0.0078125, oz_i2d(v[d][j + 1]));
         }
         const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
         *reinterpret_cast<double2*>(yrow + c * 16 + j) = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
@@ -297,8 +326,71 @@ oz_split_rows_kernel(const double* __restrict__ X, int ldx, int rows, int K, sig
   }
 }
 
+// ------------------------------------------------------------------------------ K1 fused with the split
+// One CTA per chain: residuals (residual_kernel's arithmetic: heightTreeToLengthTree, getBranches + sumFirstTwo,
+// scaling, minus the mean) into shared memory, block-wide max, digit planes into shared memory, then 16-byte
+// coalesced stores of every plane row.  Reads 8S bytes per chain, writes S_planes * ld8 bytes (<= the 8K of the
+// FP64 residual row it replaces).  Dynamic shared memory: 8 ld8 + S ld8 bytes.
+template <int S>
+__global__ void __launch_bounds__(256)
+residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ parent, const double* __restrict__ mu,
+                      const double* __restrict__ states, signed char* __restrict__ planes, int ld8, size_t plane_stride,
+                      double* __restrict__ scale, int B) {
+  extern __shared__ __align__(16) unsigned char smem_rs[];
+  double* sdx = reinterpret_cast<double*>(smem_rs);                       // [ld8]
+  signed char* sq = reinterpret_cast<signed char*>(smem_rs + (size_t)ld8 * 8);  // [S][ld8]
+  __shared__ double s_amax[8];
+  __shared__ int s_bad[8];
+  const int chain = blockIdx.x;
+  if (chain >= B) return;
+  const int tid = threadIdx.x;
+  const double* x = states + (size_t)chain * SL;
+  const double* h = x + 3;
+  const double* r = x + 5 + N;
+  const double sc = x[2] * x[3 + N];  // tH * rMu
+  double amax = 0.0;
+  int bad = 0;
+  for (int i = 1 + tid; i < N; i += 256) {
+    if (i == root_r) continue;  // merged into k = 0 by node 1 (sumFirstTwo)
+    double e = (h[parent[i] & 0x7fffffff] - h[i]) * r[i];
+    if (i == 1) e = e + (h[0] - h[root_r]) * r[root_r];
+    const int k = i < root_r ? i - 1 : i - 2;
+    const double d = e * sc - mu[k];
+    sdx[k] = d;
+    const double a = fabs(d);
+    bad |= !(a <= 1.7976931348623157e308);
+    amax = fmax(amax, a);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+  }
+  if ((tid & 31) == 0) { s_amax[tid >> 5] = amax; s_bad[tid >> 5] = bad; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { amax = fmax(amax, s_amax[w]); bad |= s_bad[w]; }
+  const bool finite = bad == 0;
+  const double scl = oz_row_scale(amax, finite);
+  const double inv = (finite && amax > 0.0) ? 1.0 / scl : 0.0;
+  if (tid == 0) scale[chain] = scl;
+  for (int k = tid; k < ld8; k += 256) {
+    signed char q[S];
+    oz_digits<S>((finite && k < K) ? sdx[k] : 0.0, inv, q);
+#pragma unroll
+    for (int s = 0; s < S; ++s) sq[s * ld8 + k] = q[s];
+  }
+  __syncthreads();
+  const int vec_per_row = ld8 / 16;
+  for (int v = tid; v < S * vec_per_row; v += 256) {
+    const int s = v / vec_per_row, c = v - s * vec_per_row;
+    *reinterpret_cast<int4*>(planes + (size_t)s * plane_stride + (size_t)chain * ld8 + (size_t)c * 16) =
+        *reinterpret_cast<const int4*>(sq + s * ld8 + c * 16);
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
-// tensor map over digit planes stacked along rows: [total_rows][ld8] int8, box = box_rows x 64 bytes, 64B swizzle
+// tensor map over digit planes stacked along rows: [total_rows][ld8] int8, box = box_rows x OZ_KB bytes, swizzled over OZ_KB
 inline int oz_make_plane_map(CUtensorMap* tm, const signed char* base, size_t total_rows, int ld8, int box_rows) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return -1;
@@ -307,7 +399,8 @@ inline int oz_make_plane_map(CUtensorMap* tm, const signed char* base, size_t to
   cuuint32_t box[2] = {OZ_KB, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, OZ_KB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -2;
 }

@@ -7,7 +7,8 @@
 // (app/Hamiltonian.hs:33-60); mcd_branch_index = getBranches + sumFirstTwo (app/Tools.hs:36-48).
 //
 // There is no CPU fallback: every evaluation runs the three CUDA kernels
-//   residual_kernel -> gemm_f64_dmma_kernel -> posterior_kernel.
+//   residual_kernel -> gemm_f64_dmma_kernel -> posterior_kernel                 (MCD_CONTRACT_DMMA)
+//   residual_split_kernel -> gemm_i8_ozaki_kernel -> posterior_kernel           (MCD_CONTRACT_I8_*, default)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -23,6 +24,7 @@
 
 #include "../../include/mcmcdate_b200.h"
 #include "gemm_f64.cuh"
+#include "gemm_i8_ozaki.cuh"
 #include "hmc_kernels.cuh"
 #include "posterior_kernels.cuh"
 
@@ -67,6 +69,13 @@ struct mcd_handle {
   DevBuf d_states, d_out, d_grad, d_status;  // staging for the host-buffer API
   DevBuf d_theta, d_gtheta, d_base, d_tidx, d_sidx;  // theta-packed API
   DevBuf d_mom, d_eps, d_invmass, d_energy, d_status_acc;  // device-resident leapfrog trajectories
+  // INT8 tensor-core contraction (gemm_i8_ozaki.cuh): digit planes of P (built once per plane count) and of
+  // the chains' residuals (rebuilt by residual_split_kernel on every evaluation)
+  int oz_S = 0;                   // 0: FP64 DMMA contraction; 6..8: int8 digit planes
+  int oz_P_S = 0, oz_X_S = 0;     // plane counts the buffers below were built for
+  int ld8 = 0, Mp8 = 0;
+  DevBuf d_pP, d_sP, d_pX, d_sX;
+  CUtensorMap tmA8{}, tmB8{};
   cudaStream_t streams[N_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
   std::mutex mtx;
   std::string err;
@@ -99,15 +108,18 @@ int upload(mcd_handle* h, DevBuf& b, const T* src, size_t n) {
   return 0;
 }
 
+int ensure_i8(mcd_handle* h);
+
 int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
   int need = (n_chains + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
   if (need > h->cap) {
     CU_TRY(h, cudaDeviceSynchronize());
     for (DevBuf* b : {&h->d_dx, &h->d_y, &h->d_states, &h->d_out, &h->d_grad, &h->d_status, &h->d_theta, &h->d_gtheta,
-                      &h->d_mom, &h->d_eps, &h->d_energy, &h->d_status_acc}) {
+                      &h->d_mom, &h->d_eps, &h->d_energy, &h->d_status_acc, &h->d_pX, &h->d_sX}) {
       if (b->p) cudaFree(b->p);
       b->p = nullptr;
     }
+    h->oz_X_S = 0;
     h->cap = need;
     if (h->dm.lik == MCD_LIK_FULL) {
       size_t ndx = (size_t)need * h->ldk, ny = (size_t)need * h->ldy;
@@ -125,7 +137,7 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
     if (!h->d_status.p) CU_TRY(h, cudaMalloc(&h->d_status.p, (size_t)h->cap * 4));
     if (grad && !h->d_grad.p) CU_TRY(h, cudaMalloc(&h->d_grad.p, (size_t)h->cap * h->S * 8));
   }
-  return 0;
+  return ensure_i8(h);
 }
 
 // Value-only path (MH proposals): quad = |L^T dx|^2 with P = L L^T needs only the triangular half of the
@@ -173,6 +185,67 @@ int ensure_cholesky(mcd_handle* h, const double* L_in) {
   return 0;
 }
 
+// INT8 contraction: digit planes of P are built once per plane count; the chains' plane buffers follow the
+// work-buffer capacity.  Called with the handle locked, after ensure_capacity.
+template <int S>
+int ensure_i8_planes(mcd_handle* h) {
+  const int K = h->K;
+  if (h->oz_P_S != S) {
+    if (h->d_pP.p) { CU_TRY(h, cudaDeviceSynchronize()); cudaFree(h->d_pP.p); h->d_pP.p = nullptr; }
+    if (h->d_sP.p) { cudaFree(h->d_sP.p); h->d_sP.p = nullptr; }
+    const size_t stride = (size_t)h->Mp8 * h->ld8;
+    CU_TRY(h, cudaMalloc(&h->d_pP.p, stride * S));
+    CU_TRY(h, cudaMemset(h->d_pP.p, 0, stride * S));
+    CU_TRY(h, cudaMalloc(&h->d_sP.p, (size_t)h->Mp8 * 8));
+    CU_TRY(h, cudaMemset(h->d_sP.p, 0, (size_t)h->Mp8 * 8));
+    oz_split_rows_kernel<S><<<(K + 7) / 8, 256>>>(h->d_P.as<double>(), h->ldk, K, K, h->d_pP.as<signed char>(), h->ld8,
+                                                   stride, h->d_sP.as<double>(), 6.103515625e-05 /* 2^-14 */);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaDeviceSynchronize());
+    if (oz_make_plane_map(&h->tmB8, h->d_pP.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ_N) != 0)
+      return fail(h, "cuTensorMapEncodeTiled failed for the precision digit planes");
+    CU_TRY(h, gemm_i8_ozaki_configure<S>());
+    CU_TRY(h, cudaFuncSetAttribute(residual_split_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((size_t)h->ld8 * (8 + S))));
+    h->oz_P_S = S;
+  }
+  if (h->oz_X_S != S) {
+    if (h->d_pX.p) { CU_TRY(h, cudaDeviceSynchronize()); cudaFree(h->d_pX.p); h->d_pX.p = nullptr; }
+    if (h->d_sX.p) { cudaFree(h->d_sX.p); h->d_sX.p = nullptr; }
+    const size_t stride = (size_t)h->cap * h->ld8;
+    CU_TRY(h, cudaMalloc(&h->d_pX.p, stride * S));
+    CU_TRY(h, cudaMemset(h->d_pX.p, 0, stride * S));
+    CU_TRY(h, cudaMalloc(&h->d_sX.p, (size_t)h->cap * 8));
+    CU_TRY(h, cudaMemset(h->d_sX.p, 0, (size_t)h->cap * 8));
+    if (oz_make_plane_map(&h->tmA8, h->d_pX.as<signed char>(), (size_t)S * h->cap, h->ld8, OZ_M) != 0)
+      return fail(h, "cuTensorMapEncodeTiled failed for the residual digit planes");
+    h->oz_X_S = S;
+  }
+  return 0;
+}
+int ensure_i8(mcd_handle* h) {
+  if (h->oz_S == 0 || h->dm.lik != MCD_LIK_FULL || h->sparse || h->N <= SMALL_TREE_MAX_NODES) return 0;
+  switch (h->oz_S) {
+    case 6: return ensure_i8_planes<6>(h);
+    case 7: return ensure_i8_planes<7>(h);
+    default: return ensure_i8_planes<8>(h);
+  }
+}
+// K1 + contraction on the INT8 tensor pipe for chains [c0, c0 + n)
+template <int S>
+int enqueue_i8(mcd_handle* h, int c0, int n, const double* xs, cudaStream_t st, cudaEvent_t ev_mid) {
+  const DevModel& M = h->dm;
+  const size_t stride = (size_t)h->cap * h->ld8;
+  residual_split_kernel<S><<<n, 256, (size_t)h->ld8 * (8 + S), st>>>(
+      M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs, h->d_pX.as<signed char>() + (size_t)c0 * h->ld8, h->ld8, stride,
+      h->d_sX.as<double>() + c0, n);
+  if (ev_mid) CU_TRY(h, cudaEventRecord(ev_mid, st));
+  const int np = (n + OZ_M - 1) / OZ_M * OZ_M;
+  CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, h->tmB8, h->d_sX.as<double>(), h->d_sP.as<double>(), h->d_y.as<double>(),
+                                    h->Mp8, np, h->ld8, M.ldy, h->cap, st, c0));
+  return 0;
+}
+
 // chains per pipelined chunk of the host-buffer APIs: >= 4 MiB of state per copy, multiple of 128;
 // small chunks keep the PCIe fill/drain bubbles short (MCD_CHUNK overrides, for experiments)
 int chunk_chains(int S) {
@@ -200,7 +273,7 @@ template <bool GRAD>
 int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
             cudaStream_t st) {
   DevModel M = h->dm;
-  const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1 && !h->sparse;
+  const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1 && !h->sparse && h->oz_S == 0;
   M.quad_from_z = tri ? 1 : 0;
   const bool small = M.N <= SMALL_TREE_MAX_NODES;
   const int cpb = small ? POST_THREADS / 32 : 1;
@@ -245,6 +318,15 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     sparse_contraction_kernel<<<n, POST_THREADS, (size_t)(M.S + M.K) * 8, st>>>(M, xs, h->d_y.as<double>() + (size_t)c0 * M.ldy, n);
     h->launches += 1;
     if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
+  } else if (M.lik == MCD_LIK_FULL && h->oz_S != 0) {
+    int rc;
+    switch (h->oz_S) {
+      case 6: rc = enqueue_i8<6>(h, c0, n, xs, st, ev[1]); break;
+      case 7: rc = enqueue_i8<7>(h, c0, n, xs, st, ev[1]); break;
+      default: rc = enqueue_i8<8>(h, c0, n, xs, st, ev[1]); break;
+    }
+    if (rc) return rc;
+    h->launches += 2;
   } else if (M.lik == MCD_LIK_FULL) {
     residual_kernel<256><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
     if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
@@ -288,7 +370,7 @@ int eval_device(mcd_handle* h, int n, const double* d_states, double* d_out, dou
   if (!d_states || !d_out || !d_status || (GRAD && !d_grad)) return fail(h, "null device buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, false, GRAD)) return -1;
-  if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && ensure_cholesky(h, nullptr)) return -1;
+  if (!GRAD && h->dm.lik == MCD_LIK_FULL && h->oz_S == 0 && !getenv("MCD_NO_CHOLESKY") && ensure_cholesky(h, nullptr)) return -1;
   return enqueue<GRAD>(h, 0, n, d_states, d_out, d_grad, d_status, static_cast<cudaStream_t>(stream));
 }
 
@@ -302,7 +384,7 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
   if (!states || !out || !status || (GRAD && !grad)) return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, true, GRAD)) return -1;
-  if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && ensure_cholesky(h, nullptr)) return -1;
+  if (!GRAD && h->dm.lik == MCD_LIK_FULL && h->oz_S == 0 && !getenv("MCD_NO_CHOLESKY") && ensure_cholesky(h, nullptr)) return -1;
   const int S = h->S;
   int ci = 0;
   for (const auto& cm : chunk_schedule(n, S)) {
@@ -506,6 +588,17 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   h->ldk = (K + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
   h->Mp = (K + GEMM_PR - 1) / GEMM_PR * GEMM_PR;
   h->ldy = h->Mp;
+  h->ld8 = (K + OZ_KB - 1) / OZ_KB * OZ_KB;
+  h->Mp8 = (K + OZ_N - 1) / OZ_N * OZ_N;
+  {  // contraction pipe: INT8 tensor cores with 8 digit planes unless MCD_CONTRACTION says otherwise
+    const char* e = getenv("MCD_CONTRACTION");
+    h->oz_S = 8;
+    if (e && !strcmp(e, "dmma")) h->oz_S = 0;
+    else if (e && !strcmp(e, "i8s6")) h->oz_S = 6;
+    else if (e && !strcmp(e, "i8s7")) h->oz_S = 7;
+    else if (e && !strcmp(e, "i8s8")) h->oz_S = 8;
+    else if (e && *e) return bail("mcd_create: MCD_CONTRACTION must be one of dmma, i8s6, i8s7, i8s8");
+  }
   h->parent.assign(d->parent, d->parent + N);
   h->child1 = child1;
   const int root_r = child1[0];
@@ -741,6 +834,17 @@ int mcd_eval_grad_device(mcd_handle* h, int32_t n, const double* d_states, doubl
                          int32_t* d_status, void* stream) {
   return eval_device<true>(h, n, d_states, d_out, d_grad, d_status, stream);
 }
+int mcd_set_contraction(mcd_handle* h, int32_t mode) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (mode != MCD_CONTRACT_DMMA && mode != MCD_CONTRACT_I8_S6 && mode != MCD_CONTRACT_I8_S7 && mode != MCD_CONTRACT_I8_S8)
+    return fail(h, "mcd_set_contraction: unknown mode");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaDeviceSynchronize());
+  h->oz_S = mode;
+  return h->cap > 0 ? ensure_i8(h) : 0;
+}
+int mcd_get_contraction(const mcd_handle* h) { return h ? h->oz_S : -1; }
 int64_t mcd_kernel_launches(const mcd_handle* h) { return h ? h->launches : -1; }
 int mcd_set_kernel_timing(mcd_handle* h, int on) {
   if (!h) return -1;

@@ -279,6 +279,7 @@ def test_value_only_cholesky_path():
     oo, ost = O.Oracle(md).eval(X, nthreads=4)
     for supply in (True, False):
         ev = binding.Evaluator(md, supply_cholesky=supply)
+        ev.set_contraction("dmma")       # the triangular path belongs to the FP64 DMMA contraction
         out, st = ev.eval(X)
         assert relerr(out[:, :7], oo).max() < TOL and np.array_equal(st, ost)
         ev.close()
@@ -289,9 +290,72 @@ def test_value_only_cholesky_path():
                           cal_node=md.cal_node, cal_lo=md.cal_lo, cal_lo_p=md.cal_lo_p, cal_hi=md.cal_hi,
                           cal_hi_p=md.cal_hi_p)
     ev = binding.Evaluator(md2)
+    ev.set_contraction("dmma")
     out, st = ev.eval(X[:50])
     o2, s2 = O.Oracle(md2).eval(X[:50])
     assert relerr(out[:, :7], o2).max() < TOL
+    ev.set_contraction("i8s8")
+    out, st = ev.eval(X[:50])
+    assert relerr(out[:, :7], o2).max() < TOL
+    ev.close()
+
+
+@pytest.mark.parametrize("n_leaves,B", [(60, 70), (300, 257), (1000, 200)])
+def test_contraction_pipes_agree_with_oracle(n_leaves, B):
+    """the FP64 DMMA contraction and the INT8 tensor-core (Ozaki-split) contraction with 8 and 7 digit planes all
+    meet the 1e-10 bar; 6 planes is the documented coarse mode.  The default of a new handle is i8s8."""
+    md, h = synth.synthetic_model(n_leaves, seed=1234 + n_leaves, n_cal=4, n_con=2, n_brace=1)
+    X = synth.synthetic_states(md, h, B)
+    oo, og, ost = O.Oracle(md).eval_grad(X, nthreads=8)
+    ev = binding.Evaluator(md)
+    assert ev.get_contraction() == 8
+    errs = {}
+    for mode, tol in (("i8s8", TOL), ("dmma", TOL), ("i8s7", TOL), ("i8s6", 1e-7)):
+        ev.set_contraction(mode)
+        out, grad, st = ev.eval_grad(X)
+        assert np.array_equal(st, ost)
+        errs[mode] = (relerr(out[:, :7], oo).max(), grad_relerr(grad, og).max())
+        assert errs[mode][0] < tol and errs[mode][1] < tol, (mode, errs[mode])
+        o2, s2 = ev.eval(X)              # value-only entry point on the same pipe
+        assert relerr(o2[:, :7], oo).max() < tol
+    # eight planes are of FP64-GEMM quality: within a small factor of the DMMA path's own rounding error
+    assert errs["i8s8"][0] < max(50 * errs["dmma"][0], 1e-13)
+    ev.close()
+
+
+def test_int8_contraction_is_bit_reproducible_and_tiling_invariant():
+    """integer accumulation: any batch split and any chain position gives bit-identical results"""
+    md, h = synth.synthetic_model(300, seed=4321, n_cal=4, n_con=2, n_brace=1)
+    X = synth.synthetic_states(md, h, 300)
+    ev = binding.Evaluator(md)
+    out, grad, st = ev.eval_grad(X)
+    out2, grad2, _ = ev.eval_grad(X)
+    assert np.array_equal(out, out2) and np.array_equal(grad, grad2)
+    perm = np.random.default_rng(0).permutation(300)
+    o3, g3, _ = ev.eval_grad(X[perm][:77])
+    assert np.array_equal(o3, out[perm][:77]) and np.array_equal(g3, grad[perm][:77])
+    ev.close()
+
+
+def test_int8_contraction_non_finite_states():
+    """NaN / inf in a state poison that chain only (NaN propagates like in the FP64 product), on both pipes"""
+    md, h = synth.synthetic_model(300, seed=99, n_cal=4, n_con=2, n_brace=1)
+    X = synth.synthetic_states(md, h, 140)
+    X[3, 3 + 7] = np.nan                 # a height
+    X[5, 5 + md.n_nodes + 9] = np.inf    # a rate
+    X[130, 2] = np.nan                   # H
+    orc = O.Oracle(md)
+    oo, og, ost = orc.eval_grad(X, nthreads=4)
+    ev = binding.Evaluator(md)
+    for mode in ("i8s8", "dmma"):
+        ev.set_contraction(mode)
+        out, grad, st = ev.eval_grad(X)
+        bad = np.array([3, 5, 130])
+        good = np.setdiff1d(np.arange(140), bad)
+        assert np.array_equal(st[good], ost[good]) and relerr(out[good, :7], oo[good]).max() < TOL
+        assert grad_relerr(grad[good], og[good]).max() < TOL
+        assert not np.isfinite(out[bad, 6]).any() and np.array_equal(np.isnan(out[bad, 6]), np.isnan(oo[bad, 6]))
+        assert np.array_equal(st[bad], ost[bad])
     ev.close()
 
 
