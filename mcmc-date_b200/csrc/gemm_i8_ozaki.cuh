@@ -15,10 +15,11 @@
 // S = 7: 28 products, ~2^-45 relative to |P|.|dx|.  Integer accumulation makes the result
 // bit-reproducible and independent of tiling / summation order.
 //
-// Kernel: one CTA = 128 chains (UMMA M, TMEM lanes) x 64 P rows (UMMA N), S accumulators of 64 TMEM
-// columns (S*64 <= 512).  Warp-specialised: warp 0 = TMA producer (all digit planes of both operands for
-// one 64-byte k-block per stage, SWIZZLE_64B), warp 1 = TMEM allocator + single-thread tcgen05.mma
-// issuer (kind::i8, M128 N64 K32), warps 2-5 = epilogue (tcgen05.ld, Horner in FP64, row/column scales).
+// Kernel: persistent CTAs, one tile = 128 chains (UMMA M, TMEM lanes) x 64 P rows (UMMA N), S accumulators of
+// 64 TMEM columns (S*64 <= 512).  Warp-specialised: warp 0 = TMA producer (all digit planes of both operands
+// for one 64-byte k-block per stage, SWIZZLE_64B), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer
+// (kind::i8, M128 N64 K32, A operand kept in the collector across the products that share it), warps 2-9 =
+// epilogue (tcgen05.ld, Horner in FP64, row/column scales).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -31,7 +32,7 @@ namespace mcd {
 constexpr int OZ_M = 128;        // chains per CTA tile
 constexpr int OZ_N = 64;         // P rows per CTA tile
 #ifndef MCD_OZ_KB
-#define MCD_OZ_KB 32
+#define MCD_OZ_KB 64
 #endif
 constexpr int OZ_KB = MCD_OZ_KB; // reduction elements (bytes) per pipeline stage = one swizzle row (32 or 64)
 constexpr int OZ_UK = 32;        // reduction depth of one tcgen05.mma kind::i8
@@ -39,7 +40,8 @@ constexpr int OZ_UK = 32;        // reduction depth of one tcgen05.mma kind::i8
 #define MCD_OZ_STAGES (MCD_OZ_KB == 32 ? 4 : 2)
 #endif
 constexpr int OZ_STAGES = MCD_OZ_STAGES;
-constexpr int OZ_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int OZ_TMEM_COLS = 512;
 constexpr int OZ_MAX_SLICES = 8;
 
@@ -126,15 +128,19 @@ __device__ __forceinline__ double oz_i2d(uint32_t v) {
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
 
 // ------------------------------------------------------------------------------ the contraction
-// tmA: digit planes of the residuals, [S][Bp][ld8] int8 seen as a 2-D [S*Bp][ld8] tensor, box 128 x 64
-// tmB: digit planes of P,             [S][Mp][ld8]                        [S*Mp][ld8],       box  64 x 64
+// tmA: digit planes of the residuals, [S][Bp][ld8] int8 seen as a 2-D [S*Bp][ld8] tensor, box 128 x OZ_KB
+// tmB: digit planes of P,             [S][Mp][ld8]                        [S*Mp][ld8],       box  64 x OZ_KB
 // scaleA[b] = row scale of chain b (NaN marks a chain with non-finite residuals), scaleB[m] = row scale of
-// P row m times 2^-14.  Grid: x = P-row tile (fastest: co-resident CTAs share the chains' planes), y = chain tile.
+// P row m times 2^-14.
+// Persistent: gridDim.x CTAs (one per SM) walk the tiles t = blockIdx.x, + gridDim.x, ...; tile t = (chain tile
+// t / n_pr, P-row tile t % n_pr), so CTAs that run together share the chains' planes and sweep P, which stays
+// L2-resident.  The shared-memory ring and its parities run on across tiles: the producer prefetches the next
+// tile's first k-blocks while the epilogue warps drain TMEM.
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ Y,
-                     int nkb, int ldy, int Bp, int Mp, int bt_base) {
+                     int nkb, int ldy, int Bp, int Mp, int bt_base, int n_pr, int n_tiles) {
   static_assert(S >= 2 && S <= OZ_MAX_SLICES && S * OZ_N <= OZ_TMEM_COLS, "digit planes must fit TMEM");
   constexpr int STAGE = oz_stage_bytes<S>();
   constexpr int A_PLANE = OZ_M * OZ_KB, B_PLANE = OZ_N * OZ_KB;
@@ -142,17 +148,16 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)OZ_STAGES * STAGE);
   uint64_t* empty = full + OZ_STAGES;
-  uint64_t* acc_full = empty + OZ_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = empty + OZ_STAGES;   // MMA warp -> epilogue: all accumulators of the tile are complete
+  uint64_t* acc_empty = acc_full + 1;       // epilogue warps -> MMA warp: TMEM has been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
-  const int pr0 = blockIdx.x * OZ_N;
-  const int bt0 = bt_base + blockIdx.y * OZ_M;
 
-  // producer: fills stage kb % STAGES with all digit planes of k-block kb
-  auto load_kblock = [&](int kb) {
-    const int st = kb % OZ_STAGES;
+  // producer: fills stage g % STAGES with all digit planes of k-block kb of tile (bt0, pr0); g = running k-block count
+  auto load_kblock = [&](int g, int kb, int bt0, int pr0) {
+    const int st = g % OZ_STAGES;
     unsigned char* dst = smem + (size_t)st * STAGE;
     mbar_arrive_expect_tx(&full[st], STAGE);
 #pragma unroll
@@ -170,9 +175,8 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_init(&empty[s], 1);
       }
       mbar_init(acc_full, 1);
+      mbar_init(acc_empty, OZ_EPI_WARPS);
       mbar_fence_init();
-      // the first loads start before the TMEM allocation and the CTA-wide barrier below
-      for (int kb = 0; kb < OZ_STAGES && kb < nkb; ++kb) load_kblock(kb);
     }
     __syncwarp();
   }
@@ -185,83 +189,100 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     const bool leader = elect_one();
-#ifdef MCD_OZ_NO_REFILL
-    for (int kb = nkb; kb < nkb; ++kb) {
-#else
-    for (int kb = OZ_STAGES; kb < nkb; ++kb) {
-#endif
-      mbar_wait(&empty[kb % OZ_STAGES], ((kb / OZ_STAGES) - 1) & 1);
-      if (leader) load_kblock(kb);
-      __syncwarp();
+    int g = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int pr0 = (t % n_pr) * OZ_N, bt0 = bt_base + (t / n_pr) * OZ_M;
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        if (g >= OZ_STAGES) mbar_wait(&empty[g % OZ_STAGES], ((g / OZ_STAGES) - 1) & 1);
+        if (leader) load_kblock(g, kb, bt0, pr0);
+        __syncwarp();
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one elected lane)
     const bool leader = elect_one();
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int st = kb % OZ_STAGES;
+    int g = 0, it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      if (it > 0) {  // the epilogue warps must have read the previous tile out of TMEM
+        mbar_wait(acc_empty, (it - 1) & 1);
+        tc_fence_after();
+      }
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const int st = g % OZ_STAGES;
 #ifdef MCD_OZ_NO_REFILL
-      if (kb < OZ_STAGES)
+        if (g < OZ_STAGES)
 #endif
-      mbar_wait(&full[st], (kb / OZ_STAGES) & 1);
-      tc_fence_after();
-      if (leader) {
-        // descriptor of the stage base; planes / k-steps are 16-byte-granular offsets added to the address field
-        const uint64_t dbase = oz_smem_desc(smem_u32(smem + (size_t)st * STAGE));
+        mbar_wait(&full[st], (g / OZ_STAGES) & 1);
+        tc_fence_after();
+        if (leader) {
+          // descriptor of the stage base; planes / k-steps are 16-byte-granular offsets added to the address field
+          const uint64_t dbase = oz_smem_desc(smem_u32(smem + (size_t)st * STAGE));
 #pragma unroll
-        for (int ks = 0; ks < OZ_KB / OZ_UK; ++ks) {
+          for (int ks = 0; ks < OZ_KB / OZ_UK; ++ks) {
 #pragma unroll
-          for (int a = 0; a < S; ++a) {
-            const uint64_t da = dbase + (uint64_t)((a * A_PLANE + ks * OZ_UK) >> 4);
+            for (int a = 0; a < S; ++a) {
+              const uint64_t da = dbase + (uint64_t)((a * A_PLANE + ks * OZ_UK) >> 4);
 #pragma unroll
-            for (int b = 0; b + a < S; ++b) {
-              const uint64_t db = dbase + (uint64_t)((S * A_PLANE + b * B_PLANE + ks * OZ_UK) >> 4);
-              // the first product into accumulator d = a + b is (a = 0, b = d) of the first k-step
-              const uint32_t acc = (kb | ks | a) != 0 ? 1u : 0u;
-              const uint32_t td = tmem_base + (uint32_t)((a + b) * OZ_N);
-              // plane a of the chains is shared by the S - a products of this inner loop: keep it in the collector
-              if (S - a == 1) umma_i8<OZ_A_DISCARD>(td, da, db, OZ_IDESC, acc);
-              else if (b == 0) umma_i8<OZ_A_FILL>(td, da, db, OZ_IDESC, acc);
-              else if (b + a == S - 1) umma_i8<OZ_A_LASTUSE>(td, da, db, OZ_IDESC, acc);
-              else umma_i8<OZ_A_USE>(td, da, db, OZ_IDESC, acc);
+              for (int b = 0; b + a < S; ++b) {
+                const uint64_t db = dbase + (uint64_t)((S * A_PLANE + b * B_PLANE + ks * OZ_UK) >> 4);
+                // the first product into accumulator d = a + b is (a = 0, b = d) of the tile's first k-step
+                const uint32_t acc = (kb | ks | a) != 0 ? 1u : 0u;
+                const uint32_t td = tmem_base + (uint32_t)((a + b) * OZ_N);
+                // plane a of the chains is shared by the S - a products of this inner loop: keep it in the collector
+                if (S - a == 1) umma_i8<OZ_A_DISCARD>(td, da, db, OZ_IDESC, acc);
+                else if (b == 0) umma_i8<OZ_A_FILL>(td, da, db, OZ_IDESC, acc);
+                else if (b + a == S - 1) umma_i8<OZ_A_LASTUSE>(td, da, db, OZ_IDESC, acc);
+                else umma_i8<OZ_A_USE>(td, da, db, OZ_IDESC, acc);
+              }
             }
           }
+          umma_commit(&empty[st]);  // frees the stage once these MMAs have read it
+          if (kb == nkb - 1) umma_commit(acc_full);
         }
-        umma_commit(&empty[st]);  // frees the stage once these MMAs have read it
-        if (kb == nkb - 1) umma_commit(acc_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: 4 warps x 32 TMEM lanes
+    // ------------------------------------------------------------------ epilogue: 8 warps = 4 lane quarters x 2 column halves
+    const int ew = warp - 2;
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes 32 (warp % 4) .. +31
+    const int chalf = ew >> 2;     // columns [32 chalf, 32 chalf + 32) of every accumulator
     const int row = quarter * 32 + lane;
-    const int b = bt0 + row;
-    const double sa = scaleA[b];
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    double* yrow = Y + (size_t)b * ldy + pr0;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int pr0 = (t % n_pr) * OZ_N, bt0 = bt_base + (t / n_pr) * OZ_M;
+      const int b = bt0 + row;
+      const double sa = scaleA[b];
+      double* yrow = Y + (size_t)b * ldy + pr0;
+      mbar_wait(acc_full, it & 1);
+      tc_fence_after();
 #ifdef MCD_OZ_NO_EPI
-    for (int c = 0; c < (int)(sa == 12345.678); ++c) {
+      for (int c = 0; c < (int)(sa == 12345.678); ++c) {
 #else
 #pragma unroll 1
-    for (int c = 0; c < OZ_N / 16; ++c) {
+      for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
 #endif
-      uint32_t v[S][16];
+        uint32_t v[S][16];
 #pragma unroll
-      for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
-      tmem_ld_wait();
+        for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
+        for (int j = 0; j < 16; j += 2) {
+          double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
 #pragma unroll
-        for (int d = S - 2; d >= 0; --d) {
-          r0 = fma(r0, 0.0078125, oz_i2d(v[d][j]));
-          r1 = fma(r1, 0.0078125, oz_i2d(v[d][j + 1]));
+          for (int d = S - 2; d >= 0; --d) {
+            r0 = fma(r0, 0.0078125, oz_i2d(v[d][j]));
+            r1 = fma(r1, 0.0078125, oz_i2d(v[d][j + 1]));
+          }
+          const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
+          *reinterpret_cast<double2*>(yrow + c * 16 + j) = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
         }
-        const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
-        *reinterpret_cast<double2*>(yrow + c * 16 + j) = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
       }
+      // this warp's TMEM reads are complete (tcgen05.wait::ld above): hand the accumulators back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
     }
   }
   tc_fence_before();
@@ -328,17 +349,18 @@ oz_split_rows_kernel(const double* __restrict__ X, int ldx, int rows, int K, sig
 
 // ------------------------------------------------------------------------------ K1 fused with the split
 // One CTA per chain: residuals (residual_kernel's arithmetic: heightTreeToLengthTree, getBranches + sumFirstTwo,
-// scaling, minus the mean) into shared memory, block-wide max, digit planes into shared memory, then 16-byte
-// coalesced stores of every plane row.  Reads 8S bytes per chain, writes S_planes * ld8 bytes (<= the 8K of the
-// FP64 residual row it replaces).  Dynamic shared memory: 8 ld8 + S ld8 bytes.
+// scaling, minus the mean) into shared memory, block-wide max, then every thread turns 4 consecutive residuals
+// into one 32-bit word per digit plane and stores it (a warp writes 128 contiguous bytes per plane).  Digits
+// come from magic-number rounding (v + 1.5 * 2^52): two FP64 adds, the int8 digit is the low byte of the sum's
+// bit pattern -- no conversion instructions.  Reads 8S bytes per chain, writes S_planes * ld8 bytes (<= the 8K
+// bytes of the FP64 residual row it replaces).  Dynamic shared memory: 8 ld8 bytes.
 template <int S>
 __global__ void __launch_bounds__(256)
 residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ parent, const double* __restrict__ mu,
                       const double* __restrict__ states, signed char* __restrict__ planes, int ld8, size_t plane_stride,
                       double* __restrict__ scale, int B) {
   extern __shared__ __align__(16) unsigned char smem_rs[];
-  double* sdx = reinterpret_cast<double*>(smem_rs);                       // [ld8]
-  signed char* sq = reinterpret_cast<signed char*>(smem_rs + (size_t)ld8 * 8);  // [S][ld8]
+  double* sdx = reinterpret_cast<double*>(smem_rs);  // [ld8]
   __shared__ double s_amax[8];
   __shared__ int s_bad[8];
   const int chain = blockIdx.x;
@@ -350,6 +372,7 @@ residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ 
   const double sc = x[2] * x[3 + N];  // tH * rMu
   double amax = 0.0;
   int bad = 0;
+  if (tid < ld8 - K) sdx[K + tid] = 0.0;  // k-padding (< 64 entries)
   for (int i = 1 + tid; i < N; i += 256) {
     if (i == root_r) continue;  // merged into k = 0 by node 1 (sumFirstTwo)
     double e = (h[parent[i] & 0x7fffffff] - h[i]) * r[i];
@@ -372,20 +395,29 @@ residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ 
   for (int w = 0; w < 8; ++w) { amax = fmax(amax, s_amax[w]); bad |= s_bad[w]; }
   const bool finite = bad == 0;
   const double scl = oz_row_scale(amax, finite);
-  const double inv = (finite && amax > 0.0) ? 1.0 / scl : 0.0;
+  const double inv = (finite && amax > 0.0) ? 1.0 / scl : 0.0;  // non-finite rows: zero digits, NaN scale
   if (tid == 0) scale[chain] = scl;
-  for (int k = tid; k < ld8; k += 256) {
-    signed char q[S];
-    oz_digits<S>((finite && k < K) ? sdx[k] : 0.0, inv, q);
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC = rint(v), low word = (int) rint(v)
+  signed char* prow = planes + (size_t)chain * ld8;
+  for (int q4 = tid; q4 < ld8 / 4; q4 += 256) {
+    const double2 x01 = *reinterpret_cast<const double2*>(sdx + 4 * q4);
+    const double2 x23 = *reinterpret_cast<const double2*>(sdx + 4 * q4 + 2);
+    double rr[4] = {x01.x * inv, x01.y * inv, x23.x * inv, x23.y * inv};
+    if (!finite) rr[0] = rr[1] = rr[2] = rr[3] = 0.0;
+    uint32_t w[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) sq[s * ld8 + k] = q[s];
-  }
-  __syncthreads();
-  const int vec_per_row = ld8 / 16;
-  for (int v = tid; v < S * vec_per_row; v += 256) {
-    const int s = v / vec_per_row, c = v - s * vec_per_row;
-    *reinterpret_cast<int4*>(planes + (size_t)s * plane_stride + (size_t)chain * ld8 + (size_t)c * 16) =
-        *reinterpret_cast<const int4*>(sq + s * ld8 + c * 16);
+    for (int s = 0; s < S; ++s) {
+      w[s] = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double v = rr[j] * 128.0;
+        const double t = v + MAGIC;
+        w[s] |= ((uint32_t)__double2loint(t) & 0xffu) << (8 * j);
+        rr[j] = v - (t - MAGIC);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t*>(prow + (size_t)s * plane_stride + 4 * q4) = w[s];
   }
 }
 
@@ -410,14 +442,16 @@ inline cudaError_t gemm_i8_ozaki_configure() {
   return cudaFuncSetAttribute(gemm_i8_ozaki_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes<S>());
 }
 
-// Bp chains (multiple of 128) starting at bt_base, Mp P rows (multiple of 64), ld8 = padded K (multiple of 64)
+// n_chains_padded chains (multiple of 128) starting at bt_base, Mp P rows (multiple of 64), ld8 = padded K
+// (multiple of OZ_KB); one persistent CTA per SM
 template <int S>
 inline cudaError_t gemm_i8_ozaki_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const double* scaleA,
                                         const double* scaleB, double* Y, int Mp, int n_chains_padded, int ld8, int ldy,
-                                        int Bp_total, cudaStream_t st, int bt_base = 0) {
-  dim3 grid(Mp / OZ_N, n_chains_padded / OZ_M);
+                                        int Bp_total, cudaStream_t st, int bt_base = 0, int n_sms = 148) {
+  const int n_pr = Mp / OZ_N, n_tiles = n_pr * (n_chains_padded / OZ_M);
+  const int grid = n_tiles < n_sms ? n_tiles : n_sms;
   gemm_i8_ozaki_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), st>>>(tmA, tmB, scaleA, scaleB, Y, ld8 / OZ_KB, ldy,
-                                                                         Bp_total, Mp, bt_base);
+                                                                         Bp_total, Mp, bt_base, n_pr, n_tiles);
   return cudaGetLastError();
 }
 

@@ -206,7 +206,7 @@ int ensure_i8_planes(mcd_handle* h) {
       return fail(h, "cuTensorMapEncodeTiled failed for the precision digit planes");
     CU_TRY(h, gemm_i8_ozaki_configure<S>());
     CU_TRY(h, cudaFuncSetAttribute(residual_split_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)((size_t)h->ld8 * (8 + S))));
+                                   (int)((size_t)h->ld8 * 8)));
     h->oz_P_S = S;
   }
   if (h->oz_X_S != S) {
@@ -236,13 +236,13 @@ template <int S>
 int enqueue_i8(mcd_handle* h, int c0, int n, const double* xs, cudaStream_t st, cudaEvent_t ev_mid) {
   const DevModel& M = h->dm;
   const size_t stride = (size_t)h->cap * h->ld8;
-  residual_split_kernel<S><<<n, 256, (size_t)h->ld8 * (8 + S), st>>>(
+  residual_split_kernel<S><<<n, 256, (size_t)h->ld8 * 8, st>>>(
       M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs, h->d_pX.as<signed char>() + (size_t)c0 * h->ld8, h->ld8, stride,
       h->d_sX.as<double>() + c0, n);
   if (ev_mid) CU_TRY(h, cudaEventRecord(ev_mid, st));
   const int np = (n + OZ_M - 1) / OZ_M * OZ_M;
   CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, h->tmB8, h->d_sX.as<double>(), h->d_sP.as<double>(), h->d_y.as<double>(),
-                                    h->Mp8, np, h->ld8, M.ldy, h->cap, st, c0));
+                                    h->Mp8, np, h->ld8, M.ldy, h->cap, st, c0, h->n_sms));
   return 0;
 }
 
