@@ -12,7 +12,8 @@ ln prior (three parts), ln likelihood, ln Jacobian and the full HMC gradient for
   value : chains/s with states resident in HBM (mcd_eval_grad_device), CUDA events, max over ranks
   e2e   : chains/s through the host-buffer C-ABI call mcd_eval_grad (pinned host states in, ln-posterior
           parts + gradient out; H2D and D2H copies inside the timed region)
-  roofline     : the FP64 contraction kernel (DMMA), algorithmic 2 K^2 flops per chain
+  roofline     : the contraction kernel (INT8 tensor cores on digit planes by default, FP64 DMMA with
+                 --contraction dmma), algorithmic 2 K^2 flops per chain
   cpu_baseline : the oracle's CPU port of the same evaluation on the box's host cores (bounded sample)
 
 --impl reference times the CPU implementation (oracle port; the Haskell reference cannot be built in
@@ -38,9 +39,12 @@ CHAINS_PER_GPU = 8192
 METRIC = "log-posterior+gradient evals/sec (batched chains)"
 UNIT = "evals/s"
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 FP64 FMA/clk/SM x 1965 MHz = 37.2
-# dram__bytes_read.sum + dram__bytes_write.sum of gemm_f64_dmma_kernel at this shape, one `ncu --set full`
-# capture (profiles/r01_ncu_summary.md, r01_kernels_final): 237.9 MB + 113.7 MB; algorithmic: 297 MB
-NCU_GEMM_DRAM_BYTES = 351.5e6
+INT8_NOMINAL_TOPS = 4500.0                           # dense int8 tensor peak (2x the 2.25 PFLOP/s bf16 figure)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the contraction kernel at this shape, from one
+# `ncu --set full` capture of this command (profiles/r01_ncu_summary.md):
+#   gemm_f64_dmma_kernel      237.9 MB + 113.7 MB (algorithmic: P 32 MB + DX 131 MB + Y 134 MB = 297 MB)
+#   gemm_i8_ozaki_kernel<8>   see NCU_DRAM_BYTES below (algorithmic: P planes 34 MB + DX planes 134 MB + Y 134 MB)
+NCU_DRAM_BYTES = {0: 351.5e6, 8: 294.5e6, 7: 257.1e6}
 
 
 def workload_config(n_gpus, chains):
@@ -161,6 +165,45 @@ def run_reference(args):
     return 0
 
 
+# --------------------------------------------------------------------------------- roofline of the dominant kernel
+def roofline(oz_s, K, B, gemm_ms, kms, ncalls, args):
+    """The precision-matrix contraction Y = DX . Sigma^-1 dominates the step.  Algorithmic work: 2 K^2 FP64 flops per
+    chain.  On the INT8 tensor pipe (default) the same product costs S(S+1)/2 int8 products of that
+    size (S digit planes per operand, gemm_i8_ozaki.cuh); the roofline fraction is quoted on the pipe the kernel runs
+    on, and the FP64-equivalent rate against the FP64 peak is given beside it."""
+    flops_alg = 2.0 * K * K * B
+    share = {"residual_ms": kms[0] / max(1, ncalls), "contraction_ms": gemm_ms, "posterior_ms": kms[2] / max(1, ncalls)}
+    traffic = args.traffic if args.traffic is not None else NCU_DRAM_BYTES.get(oz_s)
+    if B != CHAINS_PER_GPU:
+        traffic = None
+    fp64_equiv = flops_alg / (gemm_ms * 1e-3) / 1e12
+    if oz_s == 0:
+        return {"kernel": "gemm_f64_dmma_kernel", "bound": "tensor", "achieved": fp64_equiv, "peak": FP64_NOMINAL_TFLOPS,
+                "unit": "TFLOP/s", "frac": fp64_equiv / FP64_NOMINAL_TFLOPS, "traffic": traffic,
+                "peak_source": "nominal FP64 (148 SMs x 64 FMA/clk x 1965 MHz); MEASURED_PEAKS.json has no FP64 entry; "
+                               "cublasDgemm on this shape measured 35.6 TFLOP/s executed (profiles/)",
+                "kernel_ms": gemm_ms, "algorithmic_flops_per_launch": flops_alg, "step_share": share}
+    pairs = oz_s * (oz_s + 1) // 2
+    ops = pairs * flops_alg                                # int8 multiply-adds x 2 the split needs, unpadded K
+    achieved = ops / (gemm_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    return {"kernel": f"gemm_i8_ozaki_kernel<{oz_s}>", "bound": "tensor", "achieved": achieved, "peak": INT8_NOMINAL_TOPS,
+            "unit": "TOP/s (int8)", "frac": achieved / INT8_NOMINAL_TOPS, "traffic": traffic,
+            "peak_source": "nominal dense INT8 tensor peak (4.5 POP/s); MEASURED_PEAKS.json has no int8 entry -- twice its "
+                           f"measured bf16 burst figure would be {2 * peaks.get('bf16_tflops', 1662.5):.0f} TOP/s",
+            "kernel_ms": gemm_ms, "algorithmic_int8_ops_per_launch": ops, "int8_products": pairs,
+            "algorithmic_flops_per_launch": flops_alg,
+            "fp64_equivalent": {"achieved_tflops": fp64_equiv, "fp64_nominal_peak_tflops": FP64_NOMINAL_TFLOPS,
+                                "ratio_to_fp64_peak": fp64_equiv / FP64_NOMINAL_TFLOPS,
+                                "note": "2 K^2 FP64 flops per chain delivered by exact int8 products (Ozaki split); "
+                                        "the FP64 DMMA kernel it replaces reaches 0.92 of that peak"},
+            "step_share": share}
+
+
 # --------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch
@@ -181,6 +224,9 @@ def run_gpu(args):
     md, X = build_workload(B, seed_offset=rank)
     S, K = md.state_len, md.dim
     ev = binding.Evaluator(md, device=local, max_batch=B)
+    if args.contraction:
+        ev.set_contraction(args.contraction)
+    oz_s = ev.get_contraction()      # 0: FP64 DMMA, 6..8: INT8 tensor cores with that many digit planes
 
     d_states = torch.from_numpy(X).to(dev)
     d_out = torch.empty((B, model.OUT_COLS), dtype=torch.float64, device=dev)
@@ -273,12 +319,11 @@ def run_gpu(args):
         value = total * args.steps / (ms_max * 1e-3)
         e2e_value = total * args.steps / (e2e_ms_max * 1e-3)
         gemm_ms = kms[1] / max(1, ncalls)
-        flops_alg = 2.0 * K * K * B                      # 2 K^2 per chain, per launch
-        achieved = flops_alg / (gemm_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(world, B),
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(world, B), contraction=("fp64 dmma" if oz_s == 0 else f"int8 tensor cores, {oz_s} digit planes (FP64-exact split)")),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 8 + S * 8,
                     "d2h_bytes_per_step": B * (D + model.OUT_COLS) * 8 + B * 4,
                     "note": "mcd_eval_grad_theta on pinned host buffers (HMC position vectors in, packed gradient + "
@@ -288,16 +333,7 @@ def run_gpu(args):
                                        "d2h_bytes_per_step": B * (S + model.OUT_COLS) * 8 + B * 4,
                                        "note": "mcd_eval_grad (full canonical states in, full-layout gradient out)"}},
             "gpu_launches": int(launches),
-            "roofline": {
-                "kernel": "gemm_f64_dmma_kernel", "bound": "tensor", "achieved": achieved, "peak": FP64_NOMINAL_TFLOPS,
-                "unit": "TFLOP/s", "frac": achieved / FP64_NOMINAL_TFLOPS,
-                "traffic": args.traffic if B == CHAINS_PER_GPU else None,
-                "peak_source": "nominal FP64 (148 SMs x 64 FMA/clk x 1965 MHz); MEASURED_PEAKS.json has no FP64 entry; "
-                               "cublasDgemm on this shape measured 35.6 TFLOP/s executed (profiles/)",
-                "kernel_ms": gemm_ms, "algorithmic_flops_per_launch": flops_alg,
-                "step_share": {"residual_ms": kms[0] / max(1, ncalls), "contraction_ms": gemm_ms,
-                               "posterior_ms": kms[2] / max(1, ncalls)},
-            },
+            "roofline": roofline(oz_s, K, B, gemm_ms, kms, ncalls, args),
             "clocks": clocks, "outputs_ok": ok,
         }
         if world == 1 and not args.no_cpu:
@@ -323,8 +359,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--traffic", type=float, default=NCU_GEMM_DRAM_BYTES,
-                    help="dram bytes per launch of the contraction kernel from ncu (profiles/r01_ncu_summary.md)")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes per launch of the contraction kernel from ncu (default: the committed capture)")
+    ap.add_argument("--contraction", default=None, choices=["dmma", "i8s6", "i8s7", "i8s8"],
+                    help="arithmetic pipe of the contraction (default: the library's default, i8s8)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
