@@ -43,8 +43,8 @@ INT8_NOMINAL_TOPS = 4500.0                           # dense int8 tensor peak (2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the contraction kernel at this shape, from one
 # `ncu --set full` capture of this command (profiles/r01_ncu_summary.md):
 #   gemm_f64_dmma_kernel      237.9 MB + 113.7 MB (algorithmic: P 32 MB + DX 131 MB + Y 134 MB = 297 MB)
-#   gemm_i8_ozaki_kernel<8>   see NCU_DRAM_BYTES below (algorithmic: P planes 34 MB + DX planes 134 MB + Y 134 MB)
-NCU_DRAM_BYTES = {0: 351.5e6, 8: 294.5e6, 7: 257.1e6}
+#   gemm_i8_ozaki_kernel<7>   see NCU_DRAM_BYTES below (algorithmic: P planes 29 MB + DX planes 117 MB + Y 134 MB)
+NCU_DRAM_BYTES = {0: 351.5e6, 7: 308.1e6}
 
 
 def workload_config(n_gpus, chains):
@@ -323,7 +323,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(world, B), contraction=("fp64 dmma" if oz_s == 0 else f"int8 tensor cores, {oz_s} digit planes (FP64-exact split)")),
+            "config": dict(workload_config(world, B), contraction=("fp64 dmma" if oz_s == 0 else f"int8 tensor cores, {oz_s} base-256 digit planes per operand (error-free split)")),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 8 + S * 8,
                     "d2h_bytes_per_step": B * (D + model.OUT_COLS) * 8 + B * 4,
                     "note": "mcd_eval_grad_theta on pinned host buffers (HMC position vectors in, packed gradient + "
@@ -361,8 +361,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the contraction kernel from ncu (default: the committed capture)")
-    ap.add_argument("--contraction", default=None, choices=["dmma", "i8s6", "i8s7", "i8s8"],
-                    help="arithmetic pipe of the contraction (default: the library's default, i8s8)")
+    ap.add_argument("--contraction", default=None, choices=["dmma", "i8s6", "i8s7"],
+                    help="arithmetic pipe of the contraction (default: the library's default, i8s7)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

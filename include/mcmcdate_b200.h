@@ -136,12 +136,13 @@ int mcd_leapfrog(mcd_handle* h, int32_t n_chains, int32_t n_steps, const double*
 
 /* Arithmetic pipe of the precision-matrix contraction Y = DX . Sigma^-1 on large trees (the dominant kernel).
  *   MCD_CONTRACT_DMMA   FP64 tensor instructions (mma.sync m8n8k4.f64), plain FP64 GEMM rounding
- *   MCD_CONTRACT_I8_Sn  INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators) on n 7-bit digit planes per
- *                       operand row (error-free "Ozaki" splitting; integer dot products are exact, so results
- *                       are bit-reproducible).  S8 (default): error of the order of an FP64 GEMM's rounding;
- *                       S7 / S6: ~2^-7 / ~2^-14 times coarser, relative to |Sigma^-1 row| . |dx|  (DESIGN.md).
- * The environment variable MCD_CONTRACTION = dmma | i8s6 | i8s7 | i8s8 picks the default of new handles. */
-enum { MCD_CONTRACT_DMMA = 0, MCD_CONTRACT_I8_S6 = 6, MCD_CONTRACT_I8_S7 = 7, MCD_CONTRACT_I8_S8 = 8 };
+ *   MCD_CONTRACT_I8_Sn  INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators) on n balanced base-256 digit
+ *                       planes per operand row (error-free "Ozaki" splitting; integer dot products are exact, so
+ *                       results are bit-reproducible).  S7 (default): 56 bits per operand, error of the order of
+ *                       an FP64 GEMM's rounding; S6: 48 bits, ~2^-8 times coarser, relative to
+ *                       |Sigma^-1 row| . |dx|  (DESIGN.md).
+ * The environment variable MCD_CONTRACTION = dmma | i8s6 | i8s7 picks the default of new handles. */
+enum { MCD_CONTRACT_DMMA = 0, MCD_CONTRACT_I8_S6 = 6, MCD_CONTRACT_I8_S7 = 7 };
 int mcd_set_contraction(mcd_handle* h, int32_t mode);
 int mcd_get_contraction(const mcd_handle* h);
 

@@ -241,8 +241,8 @@ class Evaluator:
         return int(self._L.mcd_kernel_launches(self.h))
 
     def set_contraction(self, mode):
-        """'dmma' (FP64 tensor instructions) or 'i8s6' / 'i8s7' / 'i8s8' (INT8 tensor cores, n digit planes)"""
-        modes = {"dmma": 0, "i8s6": 6, "i8s7": 7, "i8s8": 8}
+        """'dmma' (FP64 tensor instructions) or 'i8s6' / 'i8s7' (INT8 tensor cores, n base-256 digit planes)"""
+        modes = {"dmma": 0, "i8s6": 6, "i8s7": 7}
         self._check(self._L.mcd_set_contraction(self.h, modes[mode] if isinstance(mode, str) else int(mode)))
 
     def get_contraction(self) -> int:

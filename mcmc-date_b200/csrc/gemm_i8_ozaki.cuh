@@ -5,15 +5,16 @@
 // Same product as gemm_f64.cuh (the batched  dxs <# sigmaInv  of app/Probability.hs:169), evaluated with
 // the error-free integer splitting of Ozaki et al.: every row of an operand is written as
 //
-//   x[k] = scale * sum_{s=0}^{S-1} q_s[k] * 2^(-7 (s+1)),      q_0 in [-127, 127], q_s in [-64, 64]  (int8 "digit planes")
+//   x[k] = scale * sum_{s=0}^{S-1} q_s[k] * 256^-(s+1) + tail,     q_s[k] in [-128, 127]  (int8 "digit planes")
 //
-// (scale = a power of two per row, so the split is exact up to the dropped tail 2^(-7S-1) * scale).  The
-// product of two rows is then sum_{s,t} 2^(-7(s+t+2)) * <q_s, p_t>; the integer dot products are EXACT on
-// the INT8 tensor cores (int32 accumulation: |q p| <= 2^14, K <= 2^13, at most S pairs per accumulator),
-// pairs with s + t >= S are below the dropped tail and skipped, and all pairs with the same s + t share
-// one TMEM accumulator.  S = 8: 36 int8 products, error ~ the rounding error of an FP64 GEMM;
-// S = 7: 28 products, ~2^-45 relative to |P|.|dx|.  Integer accumulation makes the result
-// bit-reproducible and independent of tiling / summation order.
+// scale = a power of two per row with |x| <= 0.498 scale; the digits are the balanced base-256 digits of the
+// integer rint(x / scale * 2^(8S)), so the split is exact up to the rounding of that integer (|tail| <=
+// 2^(-8S-1) scale).  The product of two rows is sum_{s,t} 256^-(s+t+2) <q_s, p_t>; the integer dot products are
+// EXACT on the INT8 tensor cores (int32 accumulation: |q p| <= 2^14, K <= 2^14, at most S pairs per
+// accumulator), pairs with s + t >= S are below the dropped tails and skipped, and all pairs with the same
+// s + t share one TMEM accumulator.  S = 7 (56 bits per operand, 28 int8 products): error of the order of the
+// rounding error of an FP64 GEMM; S = 6 (48 bits, 21 products): ~2^-8 times coarser.  Integer
+// accumulation makes the result bit-reproducible and independent of tiling / summation order.
 //
 // Kernel: persistent CTAs, one tile = 128 chains (UMMA M, TMEM lanes) x 64 P rows (UMMA N), S accumulators of
 // 64 TMEM columns (S*64 <= 512).  Warp-specialised: warp 0 = TMA producer (all digit planes of both operands
@@ -43,7 +44,7 @@ constexpr int OZ_STAGES = MCD_OZ_STAGES;
 constexpr int OZ_EPI_WARPS = 8;
 constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int OZ_TMEM_COLS = 512;
-constexpr int OZ_MAX_SLICES = 8;
+constexpr int OZ_MAX_SLICES = 7;  // 8 S bits must fit one int64
 
 template <int S>
 __host__ __device__ constexpr int oz_stage_bytes() { return S * (OZ_M + OZ_N) * OZ_KB; }
@@ -131,7 +132,7 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(O
 // tmA: digit planes of the residuals, [S][Bp][ld8] int8 seen as a 2-D [S*Bp][ld8] tensor, box 128 x OZ_KB
 // tmB: digit planes of P,             [S][Mp][ld8]                        [S*Mp][ld8],       box  64 x OZ_KB
 // scaleA[b] = row scale of chain b (NaN marks a chain with non-finite residuals), scaleB[m] = row scale of
-// P row m times 2^-14.
+// P row m times 2^-16.
 // Persistent: gridDim.x CTAs (one per SM) walk the tiles t = blockIdx.x, + gridDim.x, ...; tile t = (chain tile
 // t / n_pr, P-row tile t % n_pr), so CTAs that run together share the chains' planes and sweep P, which stays
 // L2-resident.  The shared-memory ring and its parities run on across tiles: the producer prefetches the next
@@ -272,8 +273,8 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
 #pragma unroll
           for (int d = S - 2; d >= 0; --d) {
-            r0 = fma(r0, 0.0078125, oz_i2d(v[d][j]));
-            r1 = fma(r1, 0.0078125, oz_i2d(v[d][j + 1]));
+            r0 = fma(r0, 0.00390625, oz_i2d(v[d][j]));
+            r1 = fma(r1, 0.00390625, oz_i2d(v[d][j + 1]));
           }
           const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
           *reinterpret_cast<double2*>(yrow + c * 16 + j) = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
@@ -291,28 +292,27 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 // ------------------------------------------------------------------------------ digit planes
-// One warp per row: x[k] (k < K) -> planes[s][row][k], s < S, and scale[row].  Rows are ld8 bytes apart,
-// planes plane_stride bytes apart; bytes k >= K of a row are left untouched (zero-initialised by the caller).
-// scale = 2^e with 2^(e-1) <= max|x| < 2^e (2^(e+1) if max|x| > 0.996 * 2^e), so |x / scale| <= 0.996: the leading
-// digit lies in [-127, 127], every later digit in [-64, 64].
-// A row holding a non-finite value gets scale = NaN (and zero digits): the whole output row becomes NaN.
-__device__ __forceinline__ double oz_row_scale(double amax, bool finite) {
+// scale = 2^(e+1) with 2^(e-1) <= max|x| < 2^e (2^(e+2) if max|x| > 0.996 * 2^e), so |x / scale| <= 0.498, the
+// range S balanced base-256 digits cover.  A row holding a non-finite value gets scale = NaN (and zero
+// digits): the whole output row becomes NaN.  Returns the scale; *mult = 2^(8S) / scale (0 for an all-zero or
+// non-finite row).
+template <int S>
+__device__ __forceinline__ double oz_row_scale(double amax, bool finite, double* mult) {
+  *mult = 0.0;
   if (!finite) return __longlong_as_double(0x7ff8000000000000LL);
   if (amax == 0.0) return 0.0;
   int e;
   const double f = frexp(amax, &e);  // amax = f * 2^e, f in [0.5, 1)
-  return ldexp(1.0, f > 0.996 ? e + 1 : e);
+  const int es = f > 0.996 ? e + 2 : e + 1;
+  *mult = ldexp(1.0, 8 * S - es);
+  return ldexp(1.0, es);
 }
+// The S digits of x as the low S bytes of a 64-bit word, least significant digit in byte 0:
+//   I = rint(x * mult) = sum_j d_j 256^j, d_j in [-128, 127]  <=>  d_j = byte_j(I + sum_j 128 * 256^j) XOR 0x80
 template <int S>
-__device__ __forceinline__ void oz_digits(double x, double inv_scale, signed char (&q)[S]) {
-  double r = x * inv_scale;  // exact (power of two), |r| <= 0.996
-#pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const double v = r * 128.0;
-    const double d = rint(v);
-    q[s] = (signed char)(int)d;
-    r = v - d;  // exact
-  }
+__device__ __forceinline__ unsigned long long oz_digit_bytes(double x, double mult) {
+  constexpr unsigned long long C = 0x8080808080808080ULL >> (8 * (8 - S));
+  return ((unsigned long long)__double2ll_rn(x * mult) + C) ^ C;
 }
 
 template <int S>
@@ -335,24 +335,22 @@ oz_split_rows_kernel(const double* __restrict__ X, int ldx, int rows, int K, sig
     amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, off));
     finite = __shfl_xor_sync(0xffffffffu, (int)finite, off) && finite;
   }
-  const double sc = oz_row_scale(amax, finite);
-  const double inv = (finite && amax > 0.0) ? 1.0 / sc : 0.0;
+  double mult;
+  const double sc = oz_row_scale<S>(amax, finite, &mult);
   if (lane == 0) scale[row] = sc * post_scale;
   signed char* out = planes + (size_t)row * ld8;
   for (int k = lane; k < K; k += 32) {
-    signed char q[S];
-    oz_digits<S>(finite ? x[k] : 0.0, inv, q);
+    const unsigned long long q = oz_digit_bytes<S>(finite ? x[k] : 0.0, mult);
 #pragma unroll
-    for (int s = 0; s < S; ++s) out[(size_t)s * plane_stride + k] = q[s];
+    for (int s = 0; s < S; ++s) out[(size_t)s * plane_stride + k] = (signed char)(q >> (8 * (S - 1 - s)));
   }
 }
 
 // ------------------------------------------------------------------------------ K1 fused with the split
 // One CTA per chain: residuals (residual_kernel's arithmetic: heightTreeToLengthTree, getBranches + sumFirstTwo,
 // scaling, minus the mean) into shared memory, block-wide max, then every thread turns 4 consecutive residuals
-// into one 32-bit word per digit plane and stores it (a warp writes 128 contiguous bytes per plane).  Digits
-// come from magic-number rounding (v + 1.5 * 2^52): two FP64 adds, the int8 digit is the low byte of the sum's
-// bit pattern -- no conversion instructions.  Reads 8S bytes per chain, writes S_planes * ld8 bytes (<= the 8K
+// into one 32-bit word per digit plane and stores it (a warp writes 128 contiguous bytes per plane).  All
+// digits of a residual come from ONE float-to-int64 conversion (oz_digit_bytes).  Reads 8S bytes per chain, writes S_planes * ld8 bytes (<= the 8K
 // bytes of the FP64 residual row it replaces).  Dynamic shared memory: 8 ld8 bytes.
 template <int S>
 __global__ void __launch_bounds__(256)
@@ -394,30 +392,24 @@ residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ 
 #pragma unroll
   for (int w = 0; w < 8; ++w) { amax = fmax(amax, s_amax[w]); bad |= s_bad[w]; }
   const bool finite = bad == 0;
-  const double scl = oz_row_scale(amax, finite);
-  const double inv = (finite && amax > 0.0) ? 1.0 / scl : 0.0;  // non-finite rows: zero digits, NaN scale
+  double mult;  // non-finite rows: zero digits, NaN scale
+  const double scl = oz_row_scale<S>(amax, finite, &mult);
   if (tid == 0) scale[chain] = scl;
-  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC = rint(v), low word = (int) rint(v)
   signed char* prow = planes + (size_t)chain * ld8;
   for (int q4 = tid; q4 < ld8 / 4; q4 += 256) {
     const double2 x01 = *reinterpret_cast<const double2*>(sdx + 4 * q4);
     const double2 x23 = *reinterpret_cast<const double2*>(sdx + 4 * q4 + 2);
-    double rr[4] = {x01.x * inv, x01.y * inv, x23.x * inv, x23.y * inv};
-    if (!finite) rr[0] = rr[1] = rr[2] = rr[3] = 0.0;
-    uint32_t w[S];
+    const unsigned long long j0 = oz_digit_bytes<S>(finite ? x01.x : 0.0, mult), j1 = oz_digit_bytes<S>(finite ? x01.y : 0.0, mult),
+                             j2 = oz_digit_bytes<S>(finite ? x23.x : 0.0, mult), j3 = oz_digit_bytes<S>(finite ? x23.y : 0.0, mult);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      w[s] = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double v = rr[j] * 128.0;
-        const double t = v + MAGIC;
-        w[s] |= ((uint32_t)__double2loint(t) & 0xffu) << (8 * j);
-        rr[j] = v - (t - MAGIC);
-      }
+      const int byte = S - 1 - s;  // plane s = digit S-1-s (most significant first)
+      const uint32_t a0 = byte < 4 ? (uint32_t)j0 : (uint32_t)(j0 >> 32), a1 = byte < 4 ? (uint32_t)j1 : (uint32_t)(j1 >> 32),
+                     a2 = byte < 4 ? (uint32_t)j2 : (uint32_t)(j2 >> 32), a3 = byte < 4 ? (uint32_t)j3 : (uint32_t)(j3 >> 32);
+      const uint32_t sel = (uint32_t)(byte & 3) | ((uint32_t)(4 + (byte & 3)) << 4);
+      const uint32_t lo = __byte_perm(a0, a1, sel), hi = __byte_perm(a2, a3, sel);   // {a0[b], a1[b]}, {a2[b], a3[b]}
+      *reinterpret_cast<uint32_t*>(prow + (size_t)s * plane_stride + 4 * q4) = __byte_perm(lo, hi, 0x5410);
     }
-#pragma unroll
-    for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t*>(prow + (size_t)s * plane_stride + 4 * q4) = w[s];
   }
 }
 

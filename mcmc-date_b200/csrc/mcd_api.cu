@@ -71,7 +71,7 @@ struct mcd_handle {
   DevBuf d_mom, d_eps, d_invmass, d_energy, d_status_acc;  // device-resident leapfrog trajectories
   // INT8 tensor-core contraction (gemm_i8_ozaki.cuh): digit planes of P (built once per plane count) and of
   // the chains' residuals (rebuilt by residual_split_kernel on every evaluation)
-  int oz_S = 0;                   // 0: FP64 DMMA contraction; 6..8: int8 digit planes
+  int oz_S = 0;                   // 0: FP64 DMMA contraction; 6, 7: int8 digit planes
   int oz_P_S = 0, oz_X_S = 0;     // plane counts the buffers below were built for
   int ld8 = 0, Mp8 = 0;
   DevBuf d_pP, d_sP, d_pX, d_sX;
@@ -199,7 +199,7 @@ int ensure_i8_planes(mcd_handle* h) {
     CU_TRY(h, cudaMalloc(&h->d_sP.p, (size_t)h->Mp8 * 8));
     CU_TRY(h, cudaMemset(h->d_sP.p, 0, (size_t)h->Mp8 * 8));
     oz_split_rows_kernel<S><<<(K + 7) / 8, 256>>>(h->d_P.as<double>(), h->ldk, K, K, h->d_pP.as<signed char>(), h->ld8,
-                                                   stride, h->d_sP.as<double>(), 6.103515625e-05 /* 2^-14 */);
+                                                   stride, h->d_sP.as<double>(), 1.52587890625e-05 /* 2^-16 */);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaDeviceSynchronize());
     if (oz_make_plane_map(&h->tmB8, h->d_pP.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ_N) != 0)
@@ -225,11 +225,7 @@ int ensure_i8_planes(mcd_handle* h) {
 }
 int ensure_i8(mcd_handle* h) {
   if (h->oz_S == 0 || h->dm.lik != MCD_LIK_FULL || h->sparse || h->N <= SMALL_TREE_MAX_NODES) return 0;
-  switch (h->oz_S) {
-    case 6: return ensure_i8_planes<6>(h);
-    case 7: return ensure_i8_planes<7>(h);
-    default: return ensure_i8_planes<8>(h);
-  }
+  return h->oz_S == 6 ? ensure_i8_planes<6>(h) : ensure_i8_planes<7>(h);
 }
 // K1 + contraction on the INT8 tensor pipe for chains [c0, c0 + n)
 template <int S>
@@ -319,12 +315,7 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     h->launches += 1;
     if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
   } else if (M.lik == MCD_LIK_FULL && h->oz_S != 0) {
-    int rc;
-    switch (h->oz_S) {
-      case 6: rc = enqueue_i8<6>(h, c0, n, xs, st, ev[1]); break;
-      case 7: rc = enqueue_i8<7>(h, c0, n, xs, st, ev[1]); break;
-      default: rc = enqueue_i8<8>(h, c0, n, xs, st, ev[1]); break;
-    }
+    const int rc = h->oz_S == 6 ? enqueue_i8<6>(h, c0, n, xs, st, ev[1]) : enqueue_i8<7>(h, c0, n, xs, st, ev[1]);
     if (rc) return rc;
     h->launches += 2;
   } else if (M.lik == MCD_LIK_FULL) {
@@ -590,14 +581,13 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   h->ldy = h->Mp;
   h->ld8 = (K + OZ_KB - 1) / OZ_KB * OZ_KB;
   h->Mp8 = (K + OZ_N - 1) / OZ_N * OZ_N;
-  {  // contraction pipe: INT8 tensor cores with 8 digit planes unless MCD_CONTRACTION says otherwise
+  {  // contraction pipe: INT8 tensor cores with 7 base-256 digit planes unless MCD_CONTRACTION says otherwise
     const char* e = getenv("MCD_CONTRACTION");
-    h->oz_S = 8;
+    h->oz_S = 7;
     if (e && !strcmp(e, "dmma")) h->oz_S = 0;
     else if (e && !strcmp(e, "i8s6")) h->oz_S = 6;
     else if (e && !strcmp(e, "i8s7")) h->oz_S = 7;
-    else if (e && !strcmp(e, "i8s8")) h->oz_S = 8;
-    else if (e && *e) return bail("mcd_create: MCD_CONTRACTION must be one of dmma, i8s6, i8s7, i8s8");
+    else if (e && *e) return bail("mcd_create: MCD_CONTRACTION must be one of dmma, i8s6, i8s7");
   }
   h->parent.assign(d->parent, d->parent + N);
   h->child1 = child1;
@@ -837,7 +827,7 @@ int mcd_eval_grad_device(mcd_handle* h, int32_t n, const double* d_states, doubl
 int mcd_set_contraction(mcd_handle* h, int32_t mode) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
-  if (mode != MCD_CONTRACT_DMMA && mode != MCD_CONTRACT_I8_S6 && mode != MCD_CONTRACT_I8_S7 && mode != MCD_CONTRACT_I8_S8)
+  if (mode != MCD_CONTRACT_DMMA && mode != MCD_CONTRACT_I8_S6 && mode != MCD_CONTRACT_I8_S7)
     return fail(h, "mcd_set_contraction: unknown mode");
   CU_TRY(h, cudaSetDevice(h->device));
   CU_TRY(h, cudaDeviceSynchronize());

@@ -36,7 +36,7 @@ def main():
     print(f"n_leaves {n_leaves}  K {md.dim}  B {B}  finite chains {ok.sum()}  spread {cond:g}")
     gsc = np.maximum(1.0, np.abs(og).max(axis=1, keepdims=True))
     res = {}
-    for mode in ("dmma", "i8s8", "i8s7", "i8s6"):
+    for mode in ("dmma", "i8s7", "i8s6"):
         ev.set_contraction(mode)
         out, grad, st = ev.eval_grad(X)
         e_lik = np.abs(out[ok, 4] - oo[ok, 4]) / np.maximum(1.0, np.abs(oo[ok, 4]))

@@ -86,7 +86,7 @@ int run(int K, int B, int iters, unsigned seed) {
     return 1;
   }
   CK(gemm_i8_ozaki_configure<S>());
-  oz_split_rows_kernel<S><<<(K + 7) / 8, 256>>>(dP, K, K, K, pB, ld8, strideB, dsb, ldexp(1.0, -14));
+  oz_split_rows_kernel<S><<<(K + 7) / 8, 256>>>(dP, K, K, K, pB, ld8, strideB, dsb, ldexp(1.0, -16));
   CK(cudaGetLastError());
   cudaEvent_t e0, e1, e2;
   cudaEventCreate(&e0);
@@ -175,7 +175,6 @@ int main(int argc, char** argv) {
     case 5: return run<5>(K, B, iters, seed);
     case 6: return run<6>(K, B, iters, seed);
     case 7: return run<7>(K, B, iters, seed);
-    case 8: return run<8>(K, B, iters, seed);
-    default: fprintf(stderr, "S must be 5..8\n"); return 1;
+    default: fprintf(stderr, "S must be 5..7\n"); return 1;
   }
 }
