@@ -14,7 +14,7 @@ import numpy as np
 from . import model as _m
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcmcdate_b200.so")
+LIB_PATH = os.environ.get("MCD_LIB_PATH") or os.path.join(_HERE, "libmcmcdate_b200.so")  # override: experiments only
 _LIB = None
 
 EXPORTS = [
