@@ -288,9 +288,33 @@ def run_gpu(args):
         ev.eval_grad_theta_ptr(B, h_theta.data_ptr(), h_base.data_ptr(), h_out2.data_ptr(), h_gtheta.data_ptr(),
                                h_status.data_ptr())
 
+    # HMC trajectory form (mcd_leapfrog): positions + momenta in, end point + energies out, TRAJ_L leapfrog steps
+    # (= TRAJ_L + 1 value+gradient evaluations per chain) resident on the device in between
+    TRAJ_L = 10
+    h_mom = torch.from_numpy(np.random.default_rng(11 + rank).normal(size=(B, D)) * 1e-3).pin_memory()
+    h_invm = torch.ones(D, dtype=torch.float64).pin_memory()
+    h_eps = torch.full((B,), 1e-6, dtype=torch.float64).pin_memory()
+    h_th_out = torch.empty((B, D), dtype=torch.float64).pin_memory()
+    h_mom_out = torch.empty((B, D), dtype=torch.float64).pin_memory()
+    h_out3 = torch.empty((B, model.OUT_COLS), dtype=torch.float64).pin_memory()
+    h_energy = torch.empty((B, 2), dtype=torch.float64).pin_memory()
+    h_status3 = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def traj_step():
+        ev.leapfrog_ptr(B, TRAJ_L, h_theta.data_ptr(), h_mom.data_ptr(), h_base.data_ptr(), h_invm.data_ptr(),
+                        h_eps.data_ptr(), h_th_out.data_ptr(), h_mom_out.data_ptr(), h_out3.data_ptr(),
+                        h_energy.data_ptr(), h_status3.data_ptr())
+
     for _ in range(2):
         e2e_state_step()
         e2e_step()
+    traj_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 4)):
+        traj_step()
+    torch.cuda.synchronize()
+    traj_s = (time.perf_counter() - t0) / max(1, args.steps // 4)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -310,10 +334,10 @@ def run_gpu(args):
         torch.equal(h_out2, h_out)) and bool(torch.equal(h_gtheta, torch.from_numpy(
             np.ascontiguousarray(h_grad.numpy()[:, mask][:, ::-1]))))
 
-    t = torch.tensor([ms, e2e_s * 1e3, e2e_state_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, e2e_state_s * 1e3, traj_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, e2e_state_ms_max = float(t[0]), float(t[1]), float(t[2])
+    ms_max, e2e_ms_max, e2e_state_ms_max, traj_ms_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank == 0:
         total = B * world
         value = total * args.steps / (ms_max * 1e-3)
@@ -331,7 +355,14 @@ def run_gpu(args):
                     "full_state_api": {"value": total * args.steps / (e2e_state_ms_max * 1e-3), "unit": UNIT,
                                        "h2d_bytes_per_step": B * S * 8,
                                        "d2h_bytes_per_step": B * (S + model.OUT_COLS) * 8 + B * 4,
-                                       "note": "mcd_eval_grad (full canonical states in, full-layout gradient out)"}},
+                                       "note": "mcd_eval_grad (full canonical states in, full-layout gradient out)"},
+                    "hmc_trajectory_api": {"value": total * (TRAJ_L + 1) / (traj_ms_max * 1e-3), "unit": UNIT,
+                                           "leapfrog_steps": TRAJ_L, "ms_per_call": traj_ms_max,
+                                           "h2d_bytes_per_step": 2 * B * D * 8 + (S + D + B) * 8,
+                                           "d2h_bytes_per_step": B * (2 * D + model.OUT_COLS + 2) * 8 + B * 4,
+                                           "note": "mcd_leapfrog: one call = positions + momenta in, TRAJ_L leapfrog steps "
+                                                   "(TRAJ_L + 1 value+gradient evaluations per chain) resident in HBM, end "
+                                                   "point + energies out; what the reference's Hamiltonian proposal asks for"}},
             "gpu_launches": int(launches),
             "roofline": roofline(oz_s, K, B, gemm_ms, kms, ncalls, args),
             "clocks": clocks, "outputs_ok": ok,

@@ -216,6 +216,14 @@ class Evaluator:
                                          _dp(pm), _dp(out), _dp(en), _ip(st)))
         return th, pm, out, en, st
 
+    def leapfrog_ptr(self, B: int, n_steps: int, theta0: int, mom0: int, base: int, inv_mass: int, eps: int, theta_out: int,
+                     mom_out: int, out: int, energy: int, status: int):
+        """mcd_leapfrog on caller-owned (e.g. pinned) host buffers given as raw addresses"""
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        c = lambda a: C.cast(a, dp)
+        self._check(self._L.mcd_leapfrog(self.h, B, int(n_steps), c(theta0), c(mom0), c(base), c(inv_mass), c(eps), c(theta_out),
+                                         c(mom_out), c(out), c(energy), C.cast(status, ip)))
+
     def eval_grad_theta_ptr(self, B: int, theta_ptr: int, base_ptr: int, out_ptr: int, gtheta_ptr: int, status_ptr: int):
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         self._check(self._L.mcd_eval_grad_theta(self.h, B, C.cast(theta_ptr, dp), C.cast(base_ptr, dp), C.cast(out_ptr, dp),
