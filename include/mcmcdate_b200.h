@@ -134,6 +134,19 @@ int mcd_leapfrog(mcd_handle* h, int32_t n_chains, int32_t n_steps, const double*
                  double* momentum_out /*[B][D]*/, double* out /*[B][MCD_OUT_COLS]*/, double* energy /*[B][2]*/,
                  int32_t* status /*[B]*/);
 
+/* One No-U-Turn-sampler transition per chain, resident on the device (the reference's proposal is
+ * `nuts defaultNParams ...` of the `mcmc` package, app/Hamiltonian.hs:95-104): Hoffman & Gelman (2014) Algorithm 3 --
+ * slice variable, doubling in random directions, U-turn checks on every balanced sub-trajectory, divergence at an
+ * energy error > 1000 -- for every chain at once, the chains ticking in lockstep (one leapfrog step per tick).
+ * Random numbers are Philox4x32-10 with key `seed` and counter (chain, iteration, draw, stream): reproducible and
+ * restated bit for bit in tests/nuts_ref.py.  momentum0 == NULL: momenta ~ N(0, M) are drawn on the device.
+ * info[b] = (tree depth, leapfrog steps, diverged, valid points); accept_stat[b] = mean min(1, exp(-dH)) over the
+ * leaves (the statistic dual averaging tunes the step size with). */
+int mcd_nuts(mcd_handle* h, int32_t n_chains, const double* theta0 /*[B][D]*/, const double* base_state /*[S]*/,
+             const double* inv_mass /*[D]*/, const double* step_size /*[B]*/, const double* momentum0 /*[B][D] or NULL*/,
+             int32_t max_depth, uint64_t seed, uint32_t iteration, double* theta_out /*[B][D]*/,
+             double* out /*[B][MCD_OUT_COLS]*/, double* accept_stat /*[B]*/, int32_t* info /*[B][4]*/, int32_t* status /*[B]*/);
+
 /* Arithmetic pipe of the precision-matrix contraction Y = DX . Sigma^-1 on large trees (the dominant kernel).
  *   MCD_CONTRACT_DMMA   FP64 tensor instructions (mma.sync m8n8k4.f64), plain FP64 GEMM rounding
  *   MCD_CONTRACT_I8_Sn  INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators) on n balanced base-256 digit

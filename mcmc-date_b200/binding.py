@@ -19,7 +19,7 @@ _LIB = None
 
 EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
-    "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_leapfrog",
+    "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_leapfrog", "mcd_nuts",
     "mcd_eval_device", "mcd_set_contraction", "mcd_get_contraction",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
     "mcd_kernel_times",
@@ -73,6 +73,7 @@ def load_library():
     L.mcd_eval_grad.argtypes = [vp, i32, dp, dp, dp, ip]
     L.mcd_eval_grad_theta.argtypes = [vp, i32, dp, dp, dp, dp, ip]
     L.mcd_leapfrog.argtypes = [vp, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip]
+    L.mcd_nuts.argtypes = [vp, i32, dp, dp, dp, dp, dp, i32, C.c_uint64, C.c_uint32, dp, dp, dp, ip, ip]
     L.mcd_eval_device.argtypes = [vp, i32, vp, vp, vp, vp]
     L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mcd_set_contraction.argtypes = [vp, i32]
@@ -215,6 +216,23 @@ class Evaluator:
         self._check(self._L.mcd_leapfrog(self.h, B, int(n_steps), _dp(T), _dp(P), _dp(base), _dp(im), _dp(eps), _dp(th),
                                          _dp(pm), _dp(out), _dp(en), _ip(st)))
         return th, pm, out, en, st
+
+    def nuts(self, theta0, base_state, inv_mass, step_size, max_depth: int = 10, seed: int = 0, iteration: int = 0,
+             momentum0=None):
+        """one NUTS transition per chain on the device -> (theta, out, accept_stat, info[B,4], status);
+        info = (depth, leapfrog steps, diverged, valid points)"""
+        T = np.ascontiguousarray(theta0, dtype=np.float64).reshape(-1, self.D)
+        B = T.shape[0]
+        base = np.ascontiguousarray(base_state, dtype=np.float64)
+        im = np.ascontiguousarray(inv_mass, dtype=np.float64)
+        eps = np.ascontiguousarray(np.broadcast_to(np.asarray(step_size, dtype=np.float64), (B,)))
+        mom = None if momentum0 is None else np.ascontiguousarray(momentum0, dtype=np.float64).reshape(B, self.D)
+        th = np.empty_like(T)
+        out, acc = np.empty((B, _m.OUT_COLS)), np.empty(B)
+        info, st = np.empty((B, 4), np.int32), np.empty(B, np.int32)
+        self._check(self._L.mcd_nuts(self.h, B, _dp(T), _dp(base), _dp(im), _dp(eps), _dp(mom) if mom is not None else None,
+                                     int(max_depth), int(seed), int(iteration), _dp(th), _dp(out), _dp(acc), _ip(info), _ip(st)))
+        return th, out, acc, info, st
 
     def leapfrog_ptr(self, B: int, n_steps: int, theta0: int, mom0: int, base: int, inv_mass: int, eps: int, theta_out: int,
                      mom_out: int, out: int, energy: int, status: int):

@@ -69,6 +69,8 @@ struct mcd_handle {
   DevBuf d_states, d_out, d_grad, d_status;  // staging for the host-buffer API
   DevBuf d_theta, d_gtheta, d_base, d_tidx, d_sidx;  // theta-packed API
   DevBuf d_mom, d_eps, d_invmass, d_energy, d_status_acc;  // device-resident leapfrog trajectories
+  DevBuf d_nuts;                  // batched NUTS: trajectory ends, checkpoints, candidates, per-chain scalars
+  size_t nuts_bytes = 0;
   // INT8 tensor-core contraction (gemm_i8_ozaki.cuh): digit planes of P (built once per plane count) and of
   // the chains' residuals (rebuilt by residual_split_kernel on every evaluation)
   int oz_S = 0;                   // 0: FP64 DMMA contraction; 6, 7: int8 digit planes
@@ -502,6 +504,99 @@ int leapfrog_host(mcd_handle* h, int n, int L, const double* theta0, const doubl
   return 0;
 }
 
+// One NUTS transition for n chains (hmc_kernels.cuh): all chains tick in lockstep, one leapfrog step per tick, until
+// every chain has made its U-turn (or reached max_depth / diverged); the host only reads the number of still
+// active chains after each tick.
+int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, const double* inv_mass, const double* eps,
+              const double* mom0, int max_depth, uint64_t seed, uint32_t iteration, double* theta_out, double* out,
+              double* accept_stat, int32_t* info, int32_t* status) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (n <= 0) return 0;
+  if (max_depth < 1 || max_depth > 16) return fail(h, "mcd_nuts: max_depth must be in 1..16");
+  if (!theta0 || !base || !inv_mass || !eps || !theta_out || !out || !accept_stat || !info || !status)
+    return fail(h, "null host buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (ensure_capacity(h, n, true, true)) return -1;
+  const int S = h->S, D = h->D;
+  const size_t BD = (size_t)n * D;
+  const size_t n_vec = 8 + 2 * (size_t)max_depth + (mom0 ? 1 : 0) + 1;   // + theta0 staging
+  const size_t bytes = n_vec * BD * 8 + (size_t)n * (2 * 8 + NR_COLS) * 8 + (size_t)n * NI_COLS * 4 + 256 + (size_t)D * 8 + (size_t)n * 8;
+  if (bytes > h->nuts_bytes) {
+    CU_TRY(h, cudaDeviceSynchronize());
+    if (h->d_nuts.p) cudaFree(h->d_nuts.p);
+    h->d_nuts.p = nullptr;
+    h->nuts_bytes = 0;
+    CU_TRY(h, cudaMalloc(&h->d_nuts.p, bytes));
+    h->nuts_bytes = bytes;
+  }
+  double* p = h->d_nuts.as<double>();
+  auto take = [&](size_t count) { double* r = p; p += count; return r; };
+  NutsBuffers nb;
+  for (int e = 0; e < 2; ++e) { nb.thE[e] = take(BD); nb.rE[e] = take(BD); nb.gE[e] = take(BD); }
+  nb.thM = take(BD); nb.thC = take(BD);
+  nb.ck_th = take(BD * max_depth); nb.ck_r = take(BD * max_depth);
+  double* d_theta0 = take(BD);
+  double* d_mom0 = mom0 ? take(BD) : nullptr;
+  nb.outM = take((size_t)n * 8); nb.outC = take((size_t)n * 8);
+  nb.nr = take((size_t)n * NR_COLS);
+  double* d_invm = take(D);
+  double* d_eps = take(n);
+  nb.n_active = reinterpret_cast<int*>(take(32));
+  nb.ni = reinterpret_cast<int*>(p);
+  cudaStream_t st = h->streams[0];
+  double* xs = h->d_states.as<double>();
+  double* o = h->d_out.as<double>();
+  double* gr = h->d_grad.as<double>();
+  int32_t* stp = h->d_status.as<int32_t>();
+  CU_TRY(h, cudaMemcpyAsync(d_theta0, theta0, BD * 8, cudaMemcpyHostToDevice, st));
+  if (mom0) CU_TRY(h, cudaMemcpyAsync(d_mom0, mom0, BD * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(d_invm, inv_mass, (size_t)D * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(d_eps, eps, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemsetAsync(nb.n_active, 0, 4, st));
+  const dim3 gS((S + POST_THREADS - 1) / POST_THREADS, n);
+  unpack_theta_kernel<<<gS, POST_THREADS, 0, st>>>(d_theta0, h->d_base.as<double>(), h->d_tidx.as<int>(), xs, S, D, n);
+  if (enqueue<true>(h, 0, n, xs, o, gr, stp, st)) return -1;
+  nuts_init_kernel<<<n, HMC_THREADS, 0, st>>>(nb, d_theta0, d_mom0, gr, h->d_sidx.as<int>(), d_invm, d_eps, o, stp, seed,
+                                              iteration, S, D, n);
+  h->launches += 2;
+  CU_TRY(h, cudaGetLastError());
+  int active = 0;
+  CU_TRY(h, cudaMemcpyAsync(&active, nb.n_active, 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  const long max_ticks = (1L << max_depth);
+  for (long tick = 0; tick < max_ticks && active > 0; ++tick) {
+    nuts_kick_drift_kernel<<<gS, HMC_THREADS, 0, st>>>(nb, h->d_tidx.as<int>(), d_invm, xs, S, D, n);
+    if (enqueue<true>(h, 0, n, xs, o, gr, stp, st)) return -1;
+    CU_TRY(h, cudaMemsetAsync(nb.n_active, 0, 4, st));
+    nuts_leaf_kernel<<<n, HMC_THREADS, 0, st>>>(nb, gr, h->d_sidx.as<int>(), d_invm, o, stp, seed, iteration, max_depth, S,
+                                                D, n);
+    h->launches += 2;
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(&active, nb.n_active, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+  }
+  // results
+  std::vector<int32_t> ni((size_t)n * NI_COLS);
+  std::vector<double> nr((size_t)n * NR_COLS);
+  CU_TRY(h, cudaMemcpyAsync(theta_out, nb.thM, BD * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(out, nb.outM, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(ni.data(), nb.ni, ni.size() * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpyAsync(nr.data(), nb.nr, nr.size() * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  for (int b = 0; b < n; ++b) {
+    const int32_t* r = &ni[(size_t)b * NI_COLS];
+    info[4 * b + 0] = r[NI_DEPTH];
+    info[4 * b + 1] = r[NI_NLEAP];
+    info[4 * b + 2] = r[NI_DIVERGED];
+    info[4 * b + 3] = r[NI_N];
+    status[b] = r[NI_STATUS];
+    accept_stat[b] = r[NI_NALPHA] > 0 ? nr[(size_t)b * NR_COLS + NR_ALPHA] / r[NI_NALPHA] : 0.0;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -816,6 +911,12 @@ int mcd_leapfrog(mcd_handle* h, int32_t n, int32_t n_steps, const double* theta0
                  double* momentum_out, double* out, double* energy, int32_t* status) {
   return leapfrog_host(h, n, n_steps, theta0, momentum0, base_state, inv_mass, step_size, theta_out, momentum_out, out,
                        energy, status);
+}
+int mcd_nuts(mcd_handle* h, int32_t n, const double* theta0, const double* base_state, const double* inv_mass,
+             const double* step_size, const double* momentum0, int32_t max_depth, uint64_t seed, uint32_t iteration,
+             double* theta_out, double* out, double* accept_stat, int32_t* info, int32_t* status) {
+  return nuts_host(h, n, theta0, base_state, inv_mass, step_size, momentum0, max_depth, seed, iteration, theta_out, out,
+                   accept_stat, info, status);
 }
 int mcd_eval_device(mcd_handle* h, int32_t n, const double* d_states, double* d_out, int32_t* d_status, void* stream) {
   return eval_device<false>(h, n, d_states, d_out, nullptr, d_status, stream);

@@ -411,6 +411,65 @@ def test_device_resident_leapfrog(n_leaves, B, L):
     ev.close()
 
 
+@pytest.mark.parametrize("n_leaves,B,eps0,max_depth", [(24, 24, 0.02, 6), (300, 12, 0.004, 5)])
+def test_device_nuts_matches_host_restatement(n_leaves, B, eps0, max_depth):
+    """mcd_nuts == the same Algorithm-3 tree building driven chain by chain from the host with the oracle's
+    gradient and bit-identical Philox uniforms (tests/nuts_ref.py): tree depths, leapfrog counts, valid-point counts
+    and the chosen points agree"""
+    import nuts_ref
+    md, h = synth.synthetic_model(n_leaves, seed=61 + n_leaves, n_cal=3, n_con=2, n_brace=0)
+    X = synth.synthetic_states(md, h, B)
+    ev = binding.Evaluator(md)
+    orc = O.Oracle(md)
+    theta = np.array([orc.to_vector(x) for x in X])
+    _, g0, _ = orc.eval_grad(X)
+    gth = np.array([orc.to_vector(gi) for gi in g0])
+    inv_mass = 1.0 / np.maximum(1.0, np.abs(gth).max(axis=0)) ** 2
+    rng = np.random.default_rng(8)
+    mom = rng.normal(size=theta.shape) / np.sqrt(inv_mass)
+    eps = eps0 * np.exp(rng.uniform(np.log(0.3), np.log(60.0), B))   # short trees, deep trees and divergences
+    seed, iteration = 0x1234567890ABCDEF, 7
+    th, out, acc, info, st = ev.nuts(theta, X[0], inv_mass, eps, max_depth=max_depth, seed=seed, iteration=iteration,
+                                     momentum0=mom)
+    depths = set()
+    for b in range(B):
+        rt, ro, ra, rinfo, rst = nuts_ref.nuts_chain(orc, X[0], theta[b], mom[b], inv_mass, eps[b], max_depth, seed,
+                                                     iteration, b)
+        assert tuple(info[b]) == tuple(rinfo), (b, info[b], rinfo)
+        assert st[b] == rst
+        assert (np.abs(th[b] - rt) <= 1e-8 * np.maximum(1.0, np.abs(rt))).all()
+        assert relerr(out[b, :7], ro).max() < 1e-8 and abs(acc[b] - ra) < 1e-8
+        depths.add(int(info[b, 0]))
+    assert len(depths) >= 3          # the batch really mixes trees of different depths
+    # same seed / iteration: bit-identical; another iteration: other slice variables and directions
+    th2, out2, acc2, info2, _ = ev.nuts(theta, X[0], inv_mass, eps, max_depth=max_depth, seed=seed, iteration=iteration,
+                                        momentum0=mom)
+    assert np.array_equal(th, th2) and np.array_equal(info, info2)
+    ev.close()
+
+
+def test_device_nuts_draws_its_own_momenta():
+    """momentum0 = NULL: momenta ~ N(0, M) from Philox on the device; reproducible, and the chain moves"""
+    md, h = synth.synthetic_model(24, seed=85, n_cal=3, n_con=2, n_brace=0)
+    X = synth.synthetic_states(md, h, 512)
+    ev = binding.Evaluator(md)
+    orc = O.Oracle(md)
+    theta = np.array([orc.to_vector(x) for x in X])
+    inv_mass = np.full(ev.D, 1e-4)
+    a = ev.nuts(theta, X[0], inv_mass, 0.01, max_depth=5, seed=99, iteration=3)
+    b = ev.nuts(theta, X[0], inv_mass, 0.01, max_depth=5, seed=99, iteration=3)
+    c = ev.nuts(theta, X[0], inv_mass, 0.01, max_depth=5, seed=99, iteration=4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+    assert not np.array_equal(a[0], c[0])
+    moved = (np.abs(a[0] - theta).max(axis=1) > 0)
+    assert moved.mean() > 0.5 and (a[3][:, 1] >= 1).all()
+    assert np.isfinite(a[1][:, 6]).all() and (a[2] >= 0).all() and (a[2] <= 1).all()
+    # the returned ln-posterior parts are those of the returned point
+    o2, _, _ = ev.eval_grad(np.array([orc.from_vector(X[0], t) for t in a[0]]))
+    assert relerr(a[1][:, :7], o2[:, :7]).max() < 1e-9
+    ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)

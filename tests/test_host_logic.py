@@ -193,3 +193,14 @@ def test_create_fails_loudly_without_gpu_or_with_bad_model():
                           logdet_sigma=0.0)
     with pytest.raises(RuntimeError):
         binding.Evaluator(bad)
+
+
+def test_philox_known_answers():
+    """the counter-based generator behind mcd_nuts: Random123's published Philox4x32-10 vectors"""
+    import nuts_ref
+    assert nuts_ref.philox4x32_10((0, 0, 0, 0), (0, 0)) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert nuts_ref.philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert nuts_ref.philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0)) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    u = [nuts_ref.uniform(5, 1, 2, d) for d in range(2000)]
+    assert 0 < min(u) and max(u) < 1 and abs(sum(u) / len(u) - 0.5) < 0.03
