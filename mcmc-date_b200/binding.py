@@ -234,6 +234,15 @@ class Evaluator:
                                      int(max_depth), int(seed), int(iteration), _dp(th), _dp(out), _dp(acc), _ip(info), _ip(st)))
         return th, out, acc, info, st
 
+    def nuts_ptr(self, B: int, theta0: int, base: int, inv_mass: int, eps: int, momentum0: int, max_depth: int, seed: int,
+                 iteration: int, theta_out: int, out: int, accept_stat: int, info: int, status: int):
+        """mcd_nuts on caller-owned (e.g. pinned) host buffers given as raw addresses; momentum0 = 0: drawn on the device"""
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        c = lambda a: C.cast(a, dp)
+        self._check(self._L.mcd_nuts(self.h, B, c(theta0), c(base), c(inv_mass), c(eps), c(momentum0) if momentum0 else None,
+                                     int(max_depth), int(seed), int(iteration), c(theta_out), c(out), c(accept_stat),
+                                     C.cast(info, ip), C.cast(status, ip)))
+
     def leapfrog_ptr(self, B: int, n_steps: int, theta0: int, mom0: int, base: int, inv_mass: int, eps: int, theta_out: int,
                      mom_out: int, out: int, energy: int, status: int):
         """mcd_leapfrog on caller-owned (e.g. pinned) host buffers given as raw addresses"""

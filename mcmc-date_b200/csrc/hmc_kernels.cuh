@@ -60,8 +60,8 @@ hamiltonian_kernel(const double* __restrict__ mom, const double* __restrict__ in
 // point of every still-open balanced sub-trajectory is kept; a leaf with odd index closes as many
 // sub-trajectories as it has trailing one bits), the uniform choice among the valid points of the new half is
 // reservoir sampling (same distribution as the recursive n''/(n'+n'') rule).  Positions, momenta, gradients,
-// checkpoints and candidates of all chains stay in HBM; per tick only the three evaluation kernels and the two
-// kernels below run.
+// checkpoints and candidates of all chains stay in HBM; per tick only the three evaluation kernels and
+// nuts_leaf_kernel run.
 //
 // Random numbers: Philox4x32-10, key = seed, counter = (chain, iteration, draw index, stream), so a host
 // restatement draws bit-identical uniforms (tests/nuts_ref.py).
@@ -140,12 +140,49 @@ __device__ __forceinline__ void nuts_block_sum(double (&v)[NV], double* scratch 
   }
 }
 
+// first half of the next leapfrog step at the active end of a chain that goes on: half kick, drift, and the new
+// position written straight into the chain's state row (fromVectorWith layout) for the evaluation kernels.
+// Called by all threads of the chain's CTA after its scalars have been updated (and a __syncthreads()).
+__device__ __forceinline__ void nuts_kick_drift(const NutsBuffers& nb, int b, const int* __restrict__ sidx,
+                                                const double* __restrict__ inv_mass, double* __restrict__ states, int S, int D) {
+  const int* ni = nb.ni + (size_t)b * NI_COLS;
+  if (!ni[NI_ACTIVE]) return;
+  const int dir = ni[NI_DIR];
+  const double e = (dir ? 1.0 : -1.0) * nb.nr[(size_t)b * NR_COLS + NR_EPS];
+  const size_t o = (size_t)b * D;
+  double* __restrict__ th = nb.thE[dir] + o;
+  double* __restrict__ rr = nb.rE[dir] + o;
+  const double* __restrict__ gg = nb.gE[dir] + o;
+  double* __restrict__ x = states + (size_t)b * S;
+  // 4 independent elements per thread and trip: all loads of a trip are in flight before the first store
+  for (int t0 = threadIdx.x; t0 < D; t0 += 4 * HMC_THREADS) {
+    double r4[4], g4[4], q4[4], m4[4];
+    int j4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * HMC_THREADS;
+      if (t < D) { r4[u] = rr[t]; g4[u] = gg[t]; q4[u] = th[t]; m4[u] = inv_mass[t]; j4[u] = sidx[t]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * HMC_THREADS;
+      if (t < D) {
+        const double p = r4[u] + 0.5 * e * g4[u];
+        const double q = q4[u] + e * m4[u] * p;
+        rr[t] = p;
+        th[t] = q;
+        x[j4[u]] = q;
+      }
+    }
+  }
+}
+
 // after the evaluation at theta0: momenta, slice variable, both trajectory ends = the start point
 __global__ void __launch_bounds__(HMC_THREADS)
 nuts_init_kernel(NutsBuffers nb, const double* __restrict__ theta0, const double* __restrict__ mom0 /*nullable*/,
                  const double* __restrict__ grad, const int* __restrict__ sidx, const double* __restrict__ inv_mass,
-                 const double* __restrict__ eps, const double* __restrict__ out, const int* __restrict__ status, uint64_t seed,
-                 uint32_t iteration, int S, int D, int B) {
+                 const double* __restrict__ eps, const double* __restrict__ out, const int* __restrict__ status,
+                 double* __restrict__ states, uint64_t seed, uint32_t iteration, int S, int D, int B) {
   __shared__ double scratch[4 * 8];
   const int b = blockIdx.x;
   if (b >= B) return;
@@ -184,35 +221,20 @@ nuts_init_kernel(NutsBuffers nb, const double* __restrict__ theta0, const double
     ni[NI_NLEAP] = 0; ni[NI_STATUS] = status[b]; ni[NI_DRAW] = 2; ni[NI_DIVERGED] = 0; ni[NI_TURNED] = 0;
     if (ok) atomicAdd(nb.n_active, 1);
   }
+  __syncthreads();
+  nuts_kick_drift(nb, b, sidx, inv_mass, states, S, D);
 }
 
-// first half of a leapfrog step at the active end of every active chain: half kick, drift, and the new position
-// written straight into the chain's state row (fromVectorWith layout) for the evaluation kernels
-__global__ void __launch_bounds__(HMC_THREADS)
-nuts_kick_drift_kernel(NutsBuffers nb, const int* __restrict__ tidx, const double* __restrict__ inv_mass,
-                       double* __restrict__ states, int S, int D, int B) {
-  const int b = blockIdx.y;
-  const int j = blockIdx.x * HMC_THREADS + threadIdx.x;
-  if (b >= B || j >= S) return;
-  const int* ni = nb.ni + (size_t)b * NI_COLS;
-  if (!ni[NI_ACTIVE]) return;
-  const int t = tidx[j];
-  if (t < 0) return;  // fixed entries keep the base state's values
-  const int dir = ni[NI_DIR];
-  const double e = (dir ? 1.0 : -1.0) * nb.nr[(size_t)b * NR_COLS + NR_EPS];
-  const size_t o = (size_t)b * D + t;
-  const double p = nb.rE[dir][o] + 0.5 * e * nb.gE[dir][o];
-  const double th = nb.thE[dir][o] + e * inv_mass[t] * p;
-  nb.rE[dir][o] = p;
-  nb.thE[dir][o] = th;
-  states[(size_t)b * S + j] = th;
-}
-
-// second half kick + all tree bookkeeping of the new leaf; one CTA per chain
-__global__ void __launch_bounds__(HMC_THREADS)
+// second half kick + all tree bookkeeping of the new leaf + (if the chain goes on) the first half of its next
+// leapfrog step; one CTA per chain.  Every thread keeps its NE elements (t = tid + 256 i) of the active end's
+// position / momentum / gradient in registers from the first pass to the last, so that per tick the end is read
+// once and written once (a chain that continues at the same end never writes its gradient at all).
+// Requires D <= 256 NE.
+template <int NE>
+__global__ void __launch_bounds__(HMC_THREADS, NE <= 12 ? 2 : 1)
 nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __restrict__ sidx,
                  const double* __restrict__ inv_mass, const double* __restrict__ out, const int* __restrict__ status,
-                 uint64_t seed, uint32_t iteration, int max_depth, int S, int D, int B) {
+                 double* __restrict__ states, uint64_t seed, uint32_t iteration, int max_depth, int S, int D, int B) {
   __shared__ double scratch[4 * 8];
   __shared__ int sh[4];
   const int b = blockIdx.x;
@@ -223,21 +245,51 @@ nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __r
   const int dir = ni[NI_DIR], depth = ni[NI_DEPTH], leaf = ni[NI_LEAF];
   const double vsgn = dir ? 1.0 : -1.0, e = vsgn * nr[NR_EPS];
   const size_t o = (size_t)b * D, BD = (size_t)B * D;
-  double* th = nb.thE[dir] + o;
-  double* rr = nb.rE[dir] + o;
-  double* gg = nb.gE[dir] + o;
-  // ---- second half kick, kinetic energy
-  double v1[1] = {0.0};
-  for (int t = threadIdx.x; t < D; t += HMC_THREADS) {
-    const double g = grad[(size_t)b * S + sidx[t]];
-    const double p = rr[t] + 0.5 * e * g;
-    rr[t] = p;
-    gg[t] = g;
-    v1[0] = fma(p * p, inv_mass[t], v1[0]);
+  double* __restrict__ th = nb.thE[dir] + o;
+  double* __restrict__ rr = nb.rE[dir] + o;
+  double* __restrict__ gg = nb.gE[dir] + o;
+  const int tid = threadIdx.x;
+  // ---- second half kick and kinetic energy, fused with the checkpoint work of this leaf: an even leaf opens a
+  // balanced sub-trajectory (its position / momentum are parked at level idx_max), an odd leaf closes nsub of them
+  // (first one checked here, deeper ones below); both are harmless if the leaf turns out to be divergent
+  const int idx_max = __popc((unsigned)leaf >> 1);
+  const bool even = (leaf & 1) == 0;
+  double* __restrict__ cth0 = nb.ck_th + (size_t)idx_max * BD + o;
+  double* __restrict__ cr0 = nb.ck_r + (size_t)idx_max * BD + o;
+  const double* __restrict__ grow = grad + (size_t)b * S;
+  double P[NE], G[NE], Q[NE];
+  double v1[3] = {0.0, 0.0, 0.0};
+  {
+    double A[NE], C[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int t = tid + i * HMC_THREADS;
+      if (t < D) {
+        G[i] = grow[sidx[t]]; P[i] = rr[t]; Q[i] = th[t];
+        if (!even) { A[i] = cth0[t]; C[i] = cr0[t]; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int t = tid + i * HMC_THREADS;
+      if (t < D) {
+        const double m = inv_mass[t];
+        P[i] = P[i] + 0.5 * e * G[i];
+        v1[0] = fma(P[i] * P[i], m, v1[0]);
+        if (even) {
+          cth0[t] = Q[i];
+          cr0[t] = P[i];
+        } else {
+          const double dth = (Q[i] - A[i]) * m;
+          v1[1] = fma(dth, C[i], v1[1]);
+          v1[2] = fma(dth, P[i], v1[2]);
+        }
+      }
+    }
   }
-  nuts_block_sum<1>(v1, scratch);
+  nuts_block_sum<3>(v1, scratch);
   // ---- leaf: validity under the slice, divergence, acceptance statistic, reservoir choice
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     const double hneg = out[(size_t)b * 8 + 6] - 0.5 * v1[0];
     const double logu = nr[NR_LOGU];
     const int valid = logu <= hneg;                       // false for NaN
@@ -262,48 +314,55 @@ nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __r
   __syncthreads();
   const int take = sh[0], diverged = sh[1];
   if (take) {
-    for (int t = threadIdx.x; t < D; t += HMC_THREADS) nb.thC[o + t] = th[t];
-    if (threadIdx.x < 8) nb.outC[(size_t)b * 8 + threadIdx.x] = out[(size_t)b * 8 + threadIdx.x];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int t = tid + i * HMC_THREADS;
+      if (t < D) nb.thC[o + t] = Q[i];
+    }
+    if (tid < 8) nb.outC[(size_t)b * 8 + tid] = out[(size_t)b * 8 + tid];
   }
   // ---- U-turn checks of the balanced sub-trajectories this leaf closes (checkpoint scheme)
   int turned = 0;
-  if (!diverged) {
-    const int idx_max = __popc((unsigned)leaf >> 1);
-    if ((leaf & 1) == 0) {
-      double* cth = nb.ck_th + (size_t)idx_max * BD + o;
-      double* cr = nb.ck_r + (size_t)idx_max * BD + o;
-      for (int t = threadIdx.x; t < D; t += HMC_THREADS) { cth[t] = th[t]; cr[t] = rr[t]; }
-    } else {
-      const int nsub = __ffs(~(unsigned)leaf) - 1;  // trailing one bits of the leaf index
-      for (int k = idx_max; k > idx_max - nsub && !turned; --k) {
-        const double* cth = nb.ck_th + (size_t)k * BD + o;
-        const double* cr = nb.ck_r + (size_t)k * BD + o;
-        double d2[2] = {0.0, 0.0};
-        for (int t = threadIdx.x; t < D; t += HMC_THREADS) {
-          const double dth = (th[t] - cth[t]) * inv_mass[t];
+  if (!diverged && !even) {
+    const int nsub = __ffs(~(unsigned)leaf) - 1;  // trailing one bits of the leaf index
+    turned = (vsgn * v1[1] < 0.0) || (vsgn * v1[2] < 0.0);
+    for (int k = idx_max - 1; k > idx_max - nsub && !turned; --k) {
+      const double* __restrict__ cth = nb.ck_th + (size_t)k * BD + o;
+      const double* __restrict__ cr = nb.ck_r + (size_t)k * BD + o;
+      double d2[2] = {0.0, 0.0};
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const int t = tid + i * HMC_THREADS;
+        if (t < D) {
+          const double dth = (Q[i] - cth[t]) * inv_mass[t];
           d2[0] = fma(dth, cr[t], d2[0]);
-          d2[1] = fma(dth, rr[t], d2[1]);
+          d2[1] = fma(dth, P[i], d2[1]);
         }
-        nuts_block_sum<2>(d2, scratch);
-        turned = (vsgn * d2[0] < 0.0) || (vsgn * d2[1] < 0.0);
       }
+      nuts_block_sum<2>(d2, scratch);
+      turned = (vsgn * d2[0] < 0.0) || (vsgn * d2[1] < 0.0);
     }
   }
   // ---- end of the sub-trajectory / of the whole trajectory
   const int s_sub = !diverged && !turned;
   const int sub_done = s_sub && (leaf + 1 == (1 << depth));
-  int accept = 0;
   if (sub_done) {
-    // main tree: (theta+ - theta-) . M^-1 r- >= 0 and (theta+ - theta-) . M^-1 r+ >= 0
+    // main tree: (theta+ - theta-) . M^-1 r- >= 0 and (theta+ - theta-) . M^-1 r+ >= 0; the active end is in
+    // registers, the other one in memory
     double d2[2] = {0.0, 0.0};
-    const double *tL = nb.thE[0] + o, *tR = nb.thE[1] + o, *rL = nb.rE[0] + o, *rR = nb.rE[1] + o;
-    for (int t = threadIdx.x; t < D; t += HMC_THREADS) {
-      const double dth = (tR[t] - tL[t]) * inv_mass[t];
-      d2[0] = fma(dth, rL[t], d2[0]);
-      d2[1] = fma(dth, rR[t], d2[1]);
+    const double* __restrict__ tO = nb.thE[1 - dir] + o;
+    const double* __restrict__ rO = nb.rE[1 - dir] + o;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int t = tid + i * HMC_THREADS;
+      if (t < D) {
+        const double dth = vsgn * (Q[i] - tO[t]) * inv_mass[t];  // theta_right - theta_left
+        d2[0] = fma(dth, rO[t], d2[0]);
+        d2[1] = fma(dth, P[i], d2[1]);
+      }
     }
     nuts_block_sum<2>(d2, scratch);
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       const int n = ni[NI_N], ns = ni[NI_NSUB];
       const double u = nuts_uniform(seed, (uint32_t)b, iteration, (uint32_t)ni[NI_DRAW]);
       ni[NI_DRAW] += 1;
@@ -325,20 +384,46 @@ nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __r
       }
     }
     __syncthreads();
-    accept = sh[2];
-    if (accept) {
-      for (int t = threadIdx.x; t < D; t += HMC_THREADS) nb.thM[o + t] = nb.thC[o + t];
-      if (threadIdx.x < 8) nb.outM[(size_t)b * 8 + threadIdx.x] = nb.outC[(size_t)b * 8 + threadIdx.x];
+    if (sh[2]) {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const int t = tid + i * HMC_THREADS;
+        if (t < D) nb.thM[o + t] = nb.thC[o + t];
+      }
+      if (tid < 8) nb.outM[(size_t)b * 8 + tid] = nb.outC[(size_t)b * 8 + tid];
     }
-  } else if (threadIdx.x == 0) {
-    if (!s_sub) {
-      if (turned) ni[NI_TURNED] = 1;
-      ni[NI_ACTIVE] = 0;  // the new half is discarded and the trajectory ends
-    } else {
-      ni[NI_LEAF] = leaf + 1;
-      atomicAdd(nb.n_active, 1);
+  } else {
+    if (tid == 0) {
+      if (!s_sub) {
+        if (turned) ni[NI_TURNED] = 1;
+        ni[NI_ACTIVE] = 0;  // the new half is discarded and the trajectory ends
+      } else {
+        ni[NI_LEAF] = leaf + 1;
+        atomicAdd(nb.n_active, 1);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- write the end back; a chain that goes on at the same end takes the first half of its next step first
+  const bool same_end = ni[NI_ACTIVE] && ni[NI_DIR] == dir;
+  double* __restrict__ x = states + (size_t)b * S;
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const int t = tid + i * HMC_THREADS;
+    if (t < D) {
+      if (same_end) {
+        const double p = P[i] + 0.5 * e * G[i];
+        const double q = Q[i] + e * inv_mass[t] * p;
+        rr[t] = p;
+        th[t] = q;
+        x[sidx[t]] = q;
+      } else {
+        rr[t] = P[i];
+        gg[t] = G[i];
+      }
     }
   }
+  if (!same_end) nuts_kick_drift(nb, b, sidx, inv_mass, states, S, D);  // other end (its data are in memory), or nothing
 }
 
 }  // namespace mcd

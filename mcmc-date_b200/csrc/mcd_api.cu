@@ -71,6 +71,8 @@ struct mcd_handle {
   DevBuf d_mom, d_eps, d_invmass, d_energy, d_status_acc;  // device-resident leapfrog trajectories
   DevBuf d_nuts;                  // batched NUTS: trajectory ends, checkpoints, candidates, per-chain scalars
   size_t nuts_bytes = 0;
+  int* nuts_flags = nullptr;      // pinned: active-chain counts of the last two ticks
+  cudaEvent_t nuts_ev[2] = {nullptr, nullptr};
   // INT8 tensor-core contraction (gemm_i8_ozaki.cuh): digit planes of P (built once per plane count) and of
   // the chains' residuals (rebuilt by residual_split_kernel on every evaluation)
   int oz_S = 0;                   // 0: FP64 DMMA contraction; 6, 7: int8 digit planes
@@ -558,25 +560,49 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
   const dim3 gS((S + POST_THREADS - 1) / POST_THREADS, n);
   unpack_theta_kernel<<<gS, POST_THREADS, 0, st>>>(d_theta0, h->d_base.as<double>(), h->d_tidx.as<int>(), xs, S, D, n);
   if (enqueue<true>(h, 0, n, xs, o, gr, stp, st)) return -1;
-  nuts_init_kernel<<<n, HMC_THREADS, 0, st>>>(nb, d_theta0, d_mom0, gr, h->d_sidx.as<int>(), d_invm, d_eps, o, stp, seed,
+  nuts_init_kernel<<<n, HMC_THREADS, 0, st>>>(nb, d_theta0, d_mom0, gr, h->d_sidx.as<int>(), d_invm, d_eps, o, stp, xs, seed,
                                               iteration, S, D, n);
   h->launches += 2;
   CU_TRY(h, cudaGetLastError());
-  int active = 0;
-  CU_TRY(h, cudaMemcpyAsync(&active, nb.n_active, 4, cudaMemcpyDeviceToHost, st));
+  // The number of still-active chains is read back with one tick of lag (pinned flags + events): tick k + 1 is already
+  // queued when the host looks at tick k's count, so the GPU never waits for the host; at most one surplus tick runs at
+  // the end (every kernel of it is a no-op for finished chains).
+  if (!h->nuts_flags) {
+    CU_TRY(h, cudaMallocHost(&h->nuts_flags, 2 * sizeof(int)));
+    for (int i = 0; i < 2; ++i) CU_TRY(h, cudaEventCreateWithFlags(&h->nuts_ev[i], cudaEventDisableTiming));
+  }
+  volatile int* flags = h->nuts_flags;
+  CU_TRY(h, cudaMemcpyAsync(h->nuts_flags, nb.n_active, 4, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaStreamSynchronize(st));
   const long max_ticks = (1L << max_depth);
-  for (long tick = 0; tick < max_ticks && active > 0; ++tick) {
-    nuts_kick_drift_kernel<<<gS, HMC_THREADS, 0, st>>>(nb, h->d_tidx.as<int>(), d_invm, xs, S, D, n);
-    if (enqueue<true>(h, 0, n, xs, o, gr, stp, st)) return -1;
-    CU_TRY(h, cudaMemsetAsync(nb.n_active, 0, 4, st));
-    nuts_leaf_kernel<<<n, HMC_THREADS, 0, st>>>(nb, gr, h->d_sidx.as<int>(), d_invm, o, stp, seed, iteration, max_depth, S,
-                                                D, n);
-    h->launches += 2;
-    CU_TRY(h, cudaGetLastError());
-    CU_TRY(h, cudaMemcpyAsync(&active, nb.n_active, 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaStreamSynchronize(st));
+  bool pending = false;
+  if (flags[0] > 0) {
+    for (long tick = 0; tick < max_ticks; ++tick) {
+      if (enqueue<true>(h, 0, n, xs, o, gr, stp, st)) return -1;
+      CU_TRY(h, cudaMemsetAsync(nb.n_active, 0, 4, st));
+#define MCD_NUTS_LEAF(NE) \
+  nuts_leaf_kernel<NE><<<n, HMC_THREADS, 0, st>>>(nb, gr, h->d_sidx.as<int>(), d_invm, o, stp, xs, seed, iteration, max_depth, S, D, n)
+      if (D <= 1 * HMC_THREADS) MCD_NUTS_LEAF(1);
+      else if (D <= 2 * HMC_THREADS) MCD_NUTS_LEAF(2);
+      else if (D <= 4 * HMC_THREADS) MCD_NUTS_LEAF(4);
+      else if (D <= 8 * HMC_THREADS) MCD_NUTS_LEAF(8);
+      else if (D <= 12 * HMC_THREADS) MCD_NUTS_LEAF(12);
+      else if (D <= 16 * HMC_THREADS) MCD_NUTS_LEAF(16);
+      else if (D <= 24 * HMC_THREADS) MCD_NUTS_LEAF(24);
+      else MCD_NUTS_LEAF(56);   /* D <= 14336 (trees of up to ~4700 leaves; larger ones exceed K3's staging anyway) */
+#undef MCD_NUTS_LEAF
+      h->launches += 1;
+      CU_TRY(h, cudaGetLastError());
+      CU_TRY(h, cudaMemcpyAsync(h->nuts_flags + (tick & 1), nb.n_active, 4, cudaMemcpyDeviceToHost, st));
+      CU_TRY(h, cudaEventRecord(h->nuts_ev[tick & 1], st));
+      if (pending) {  // look at the previous tick's count while this one runs
+        CU_TRY(h, cudaEventSynchronize(h->nuts_ev[(tick - 1) & 1]));
+        if (flags[(tick - 1) & 1] == 0) break;
+      }
+      pending = true;
+    }
   }
+  CU_TRY(h, cudaStreamSynchronize(st));
   // results
   std::vector<int32_t> ni((size_t)n * NI_COLS);
   std::vector<double> nr((size_t)n * NR_COLS);
@@ -864,6 +890,9 @@ void mcd_destroy(mcd_handle* h) {
   cudaDeviceSynchronize();
   for (int i = 0; i < N_STREAMS; ++i)
     if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+  if (h->nuts_flags) cudaFreeHost(h->nuts_flags);
+  for (int i = 0; i < 2; ++i)
+    if (h->nuts_ev[i]) cudaEventDestroy(h->nuts_ev[i]);
   delete h;
 }
 
