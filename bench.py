@@ -267,6 +267,21 @@ def run_gpu(args):
     kms, ncalls = ev.kernel_times()
     ev.set_kernel_timing(False)
     launches = ev.kernel_launches() - launches0
+    # value-only evaluation (what the Metropolis-Hastings proposals need): triangular contraction on the Cholesky factor
+    ev.eval_device(B, d_states.data_ptr(), d_out.data_ptr(), d_status.data_ptr(), stream.cuda_stream)  # factorises once
+    for _ in range(2):
+        ev.eval_device(B, d_states.data_ptr(), d_out.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+    barrier()
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    v0.record()
+    for _ in range(args.steps):
+        ev.eval_device(B, d_states.data_ptr(), d_out.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+    v1.record()
+    barrier()
+    value_only_ms = v0.elapsed_time(v1) / args.steps
+    # leave d_out as the value+gradient call wrote it (the parity guard below compares it with the host entry points)
+    ev.eval_grad_device(B, d_states.data_ptr(), d_out.data_ptr(), d_grad.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+    barrier()
     # --- end-to-end through the host-buffer C ABI (pinned host memory, copies inside) ---------
     h_states = torch.from_numpy(X).pin_memory()
     h_out = torch.empty((B, model.OUT_COLS), dtype=torch.float64).pin_memory()
@@ -364,6 +379,9 @@ def run_gpu(args):
                                                    "(TRAJ_L + 1 value+gradient evaluations per chain) resident in HBM, end "
                                                    "point + energies out; what the reference's Hamiltonian proposal asks for"}},
             "gpu_launches": int(launches),
+            "value_only": {"value": B * world / (value_only_ms * 1e-3), "unit": "evals/s", "ms_per_step": value_only_ms,
+                           "note": "mcd_eval_device (no gradient), per-rank time of this rank x world; quadratic form from the "
+                                   "triangular Cholesky-factor contraction"},
             "roofline": roofline(oz_s, K, B, gemm_ms, kms, ncalls, args),
             "clocks": clocks, "outputs_ok": ok,
         }

@@ -141,7 +141,7 @@ template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ Y,
-                     int nkb, int ldy, int Bp, int Mp, int bt_base, int n_pr, int n_tiles) {
+                     int nkb, int ldy, int Bp, int Mp, int bt_base, int n_pr, int n_tiles, int upper_tri) {
   static_assert(S >= 2 && S <= OZ_MAX_SLICES && S * OZ_N <= OZ_TMEM_COLS, "digit planes must fit TMEM");
   constexpr int STAGE = oz_stage_bytes<S>();
   constexpr int A_PLANE = OZ_M * OZ_KB, B_PLANE = OZ_N * OZ_KB;
@@ -193,7 +193,9 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int g = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int pr0 = (t % n_pr) * OZ_N, bt0 = bt_base + (t / n_pr) * OZ_M;
-      for (int kb = 0; kb < nkb; ++kb, ++g) {
+      // upper-triangular operand (U = L^T of the Cholesky factor, value-only path): row m only has entries at
+      // k >= m, so this tile's reduction starts at its own diagonal block
+      for (int kb = upper_tri ? pr0 / OZ_KB : 0; kb < nkb; ++kb, ++g) {
         if (g >= OZ_STAGES) mbar_wait(&empty[g % OZ_STAGES], ((g / OZ_STAGES) - 1) & 1);
         if (leader) load_kblock(g, kb, bt0, pr0);
         __syncwarp();
@@ -208,7 +210,8 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(acc_empty, (it - 1) & 1);
         tc_fence_after();
       }
-      for (int kb = 0; kb < nkb; ++kb, ++g) {
+      const int kb0 = upper_tri ? ((t % n_pr) * OZ_N) / OZ_KB : 0;
+      for (int kb = kb0; kb < nkb; ++kb, ++g) {
         const int st = g % OZ_STAGES;
 #ifdef MCD_OZ_NO_REFILL
         if (g < OZ_STAGES)
@@ -227,7 +230,7 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               for (int b = 0; b + a < S; ++b) {
                 const uint64_t db = dbase + (uint64_t)((S * A_PLANE + b * B_PLANE + ks * OZ_UK) >> 4);
                 // the first product into accumulator d = a + b is (a = 0, b = d) of the tile's first k-step
-                const uint32_t acc = (kb | ks | a) != 0 ? 1u : 0u;
+                const uint32_t acc = ((kb - kb0) | ks | a) != 0 ? 1u : 0u;
                 const uint32_t td = tmem_base + (uint32_t)((a + b) * OZ_N);
                 // plane a of the chains is shared by the S - a products of this inner loop: keep it in the collector
                 if (S - a == 1) umma_i8<OZ_A_DISCARD>(td, da, db, OZ_IDESC, acc);
@@ -439,11 +442,11 @@ inline cudaError_t gemm_i8_ozaki_configure() {
 template <int S>
 inline cudaError_t gemm_i8_ozaki_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const double* scaleA,
                                         const double* scaleB, double* Y, int Mp, int n_chains_padded, int ld8, int ldy,
-                                        int Bp_total, cudaStream_t st, int bt_base = 0, int n_sms = 148) {
+                                        int Bp_total, cudaStream_t st, int bt_base = 0, int n_sms = 148, int upper_tri = 0) {
   const int n_pr = Mp / OZ_N, n_tiles = n_pr * (n_chains_padded / OZ_M);
   const int grid = n_tiles < n_sms ? n_tiles : n_sms;
   gemm_i8_ozaki_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), st>>>(tmA, tmB, scaleA, scaleB, Y, ld8 / OZ_KB, ldy,
-                                                                         Bp_total, Mp, bt_base, n_pr, n_tiles);
+                                                                         Bp_total, Mp, bt_base, n_pr, n_tiles, upper_tri);
   return cudaGetLastError();
 }
 

@@ -78,8 +78,9 @@ struct mcd_handle {
   int oz_S = 0;                   // 0: FP64 DMMA contraction; 6, 7: int8 digit planes
   int oz_P_S = 0, oz_X_S = 0;     // plane counts the buffers below were built for
   int ld8 = 0, Mp8 = 0;
-  DevBuf d_pP, d_sP, d_pX, d_sX;
-  CUtensorMap tmA8{}, tmB8{};
+  DevBuf d_pP, d_sP, d_pX, d_sX, d_pU, d_sU;   // planes + scales of Sigma^-1, of the residuals, of U = L^T
+  int oz_U_S = 0;
+  CUtensorMap tmA8{}, tmB8{}, tmU8{};
   cudaStream_t streams[N_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
   std::mutex mtx;
   std::string err;
@@ -213,6 +214,22 @@ int ensure_i8_planes(mcd_handle* h) {
                                    (int)((size_t)h->ld8 * 8)));
     h->oz_P_S = S;
   }
+  if (h->chol_state == 1 && h->oz_U_S != S) {  // value-only path: digit planes of the upper-triangular factor U = L^T
+    if (h->d_pU.p) { CU_TRY(h, cudaDeviceSynchronize()); cudaFree(h->d_pU.p); h->d_pU.p = nullptr; }
+    if (h->d_sU.p) { cudaFree(h->d_sU.p); h->d_sU.p = nullptr; }
+    const size_t stride = (size_t)h->Mp8 * h->ld8;
+    CU_TRY(h, cudaMalloc(&h->d_pU.p, stride * S));
+    CU_TRY(h, cudaMemset(h->d_pU.p, 0, stride * S));
+    CU_TRY(h, cudaMalloc(&h->d_sU.p, (size_t)h->Mp8 * 8));
+    CU_TRY(h, cudaMemset(h->d_sU.p, 0, (size_t)h->Mp8 * 8));
+    oz_split_rows_kernel<S><<<(K + 7) / 8, 256>>>(h->d_U.as<double>(), h->ldk, K, K, h->d_pU.as<signed char>(), h->ld8,
+                                                   stride, h->d_sU.as<double>(), 1.52587890625e-05 /* 2^-16 */);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaDeviceSynchronize());
+    if (oz_make_plane_map(&h->tmU8, h->d_pU.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ_N) != 0)
+      return fail(h, "cuTensorMapEncodeTiled failed for the Cholesky-factor digit planes");
+    h->oz_U_S = S;
+  }
   if (h->oz_X_S != S) {
     if (h->d_pX.p) { CU_TRY(h, cudaDeviceSynchronize()); cudaFree(h->d_pX.p); h->d_pX.p = nullptr; }
     if (h->d_sX.p) { cudaFree(h->d_sX.p); h->d_sX.p = nullptr; }
@@ -233,7 +250,7 @@ int ensure_i8(mcd_handle* h) {
 }
 // K1 + contraction on the INT8 tensor pipe for chains [c0, c0 + n)
 template <int S>
-int enqueue_i8(mcd_handle* h, int c0, int n, const double* xs, cudaStream_t st, cudaEvent_t ev_mid) {
+int enqueue_i8(mcd_handle* h, int c0, int n, const double* xs, cudaStream_t st, cudaEvent_t ev_mid, bool tri) {
   const DevModel& M = h->dm;
   const size_t stride = (size_t)h->cap * h->ld8;
   residual_split_kernel<S><<<n, 256, (size_t)h->ld8 * 8, st>>>(
@@ -241,8 +258,9 @@ int enqueue_i8(mcd_handle* h, int c0, int n, const double* xs, cudaStream_t st, 
       h->d_sX.as<double>() + c0, n);
   if (ev_mid) CU_TRY(h, cudaEventRecord(ev_mid, st));
   const int np = (n + OZ_M - 1) / OZ_M * OZ_M;
-  CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, h->tmB8, h->d_sX.as<double>(), h->d_sP.as<double>(), h->d_y.as<double>(),
-                                    h->Mp8, np, h->ld8, M.ldy, h->cap, st, c0, h->n_sms));
+  CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, tri ? h->tmU8 : h->tmB8, h->d_sX.as<double>(),
+                                    (tri ? h->d_sU : h->d_sP).as<double>(), h->d_y.as<double>(), h->Mp8, np, h->ld8, M.ldy,
+                                    h->cap, st, c0, h->n_sms, tri ? 1 : 0));
   return 0;
 }
 
@@ -273,7 +291,8 @@ template <bool GRAD>
 int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
             cudaStream_t st) {
   DevModel M = h->dm;
-  const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1 && !h->sparse && h->oz_S == 0;
+  const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1 && !h->sparse &&
+                   (h->oz_S == 0 || h->oz_U_S == h->oz_S);
   M.quad_from_z = tri ? 1 : 0;
   const bool small = M.N <= SMALL_TREE_MAX_NODES;
   const int cpb = small ? POST_THREADS / 32 : 1;
@@ -319,7 +338,7 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     h->launches += 1;
     if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
   } else if (M.lik == MCD_LIK_FULL && h->oz_S != 0) {
-    const int rc = h->oz_S == 6 ? enqueue_i8<6>(h, c0, n, xs, st, ev[1]) : enqueue_i8<7>(h, c0, n, xs, st, ev[1]);
+    const int rc = h->oz_S == 6 ? enqueue_i8<6>(h, c0, n, xs, st, ev[1], tri) : enqueue_i8<7>(h, c0, n, xs, st, ev[1], tri);
     if (rc) return rc;
     h->launches += 2;
   } else if (M.lik == MCD_LIK_FULL) {
@@ -365,7 +384,7 @@ int eval_device(mcd_handle* h, int n, const double* d_states, double* d_out, dou
   if (!d_states || !d_out || !d_status || (GRAD && !d_grad)) return fail(h, "null device buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, false, GRAD)) return -1;
-  if (!GRAD && h->dm.lik == MCD_LIK_FULL && h->oz_S == 0 && !getenv("MCD_NO_CHOLESKY") && ensure_cholesky(h, nullptr)) return -1;
+  if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && (ensure_cholesky(h, nullptr) || ensure_i8(h))) return -1;
   return enqueue<GRAD>(h, 0, n, d_states, d_out, d_grad, d_status, static_cast<cudaStream_t>(stream));
 }
 
@@ -379,7 +398,7 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
   if (!states || !out || !status || (GRAD && !grad)) return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, true, GRAD)) return -1;
-  if (!GRAD && h->dm.lik == MCD_LIK_FULL && h->oz_S == 0 && !getenv("MCD_NO_CHOLESKY") && ensure_cholesky(h, nullptr)) return -1;
+  if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && (ensure_cholesky(h, nullptr) || ensure_i8(h))) return -1;
   const int S = h->S;
   int ci = 0;
   for (const auto& cm : chunk_schedule(n, S)) {
