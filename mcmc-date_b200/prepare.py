@@ -10,8 +10,8 @@ the data formats either side of the hot path.  numpy only.
 
 Restrictions (documented): the trees of the list must already be rooted at the outgroup
 and bifurcating (the reference re-roots with elynx `outgroup`, app/Main.hs:179-180; all of its own
-tests/*/data/test.treelist files already are); constraint redundancy/conflict pruning
-(Constraint.hs:306-374) is not restated -- constraints are taken as given.
+tests/*/data/test.treelist files already are).  Constraint validation, conflict detection and the pruning of
+duplicate / redundant constraints (Constraint.hs:117-146, 211-253, 306-374) are restated in load_constraints.
 """
 from __future__ import annotations
 
@@ -100,17 +100,79 @@ def load_calibrations(text: str, parent, names):
             "hi": np.array(hi), "hi_p": np.array(hip)}
 
 
-def load_constraints(text: str, parent, names):
-    """CSV `Name,YoungerLeafA,YoungerLeafB,OlderLeafA,OlderLeafB,ProbabilityMass`."""
-    y, o, p, nm = [], [], [], []
+def _is_ancestor(parent, x: int, y: int) -> bool:
+    """x is an ancestor of y or y itself (the reference compares node PATHS with isPrefixOf, Internal.hs:69-75)"""
+    while y >= 0:
+        if y == x:
+            return True
+        y = int(parent[y])
+    return False
+
+
+def load_constraints(text: str, parent, names, on_problem: str = "drop", log=None):
+    """CSV `Name,YoungerLeafA,YoungerLeafB,OlderLeafA,OlderLeafB,ProbabilityMass` -> validated, pruned table
+    (loadConstraints, Constraint.hs:275-374):
+
+    * a constraint whose two nodes coincide, or whose younger node is an ancestor of the older one, is an error
+      (validateConstraint, :117-146); one whose older node is an ancestor of the younger one is vacuous and is
+      dropped with a warning (`on_problem="drop"`, WarnAboutAndDropProblematicConstraints) or an error (`"error"`);
+    * conflicting pairs are an error: given a < b, the constraint c < d conflicts iff c is an ancestor of b and d a
+      descendant of a or of b (isConflictingWith, :233-235);
+    * of constraints on the same pair of nodes the later ones are removed (duplicate, :101-102, :333-349);
+    * given a < b, the constraint c < d is redundant iff c is a descendant of a and d an ancestor of b
+      (isRedundantWith, :222-224); redundant ones are removed (:351-369).
+
+    "ancestor" / "descendant" include the node itself, as path-prefix tests do."""
+    say = log if log is not None else (lambda msg: None)
+    rows = []
     for row in csv.reader(io.StringIO(text)):
         if not row or row[0].strip() == "Name":
             continue
-        nm.append(row[0])
-        y.append(_mrca(parent, names, row[1].strip(), row[2].strip()))
-        o.append(_mrca(parent, names, row[3].strip(), row[4].strip()))
-        p.append(float(row[5]))
-    return {"names": nm, "young": np.array(y, np.int32), "old": np.array(o, np.int32), "p": np.array(p)}
+        name, pm = row[0], float(row[5])
+        if not 0.0 < pm < 1.0:
+            raise ValueError(f"constraintDataToConstraint: {name}: probabilityMass: out of (0, 1)")
+        y = _mrca(parent, names, row[1].strip(), row[2].strip())
+        o = _mrca(parent, names, row[3].strip(), row[4].strip())
+        if y == o:
+            raise ValueError(f"validateConstraint: {name!r}: Bogus constraint; both nodes are equal (?).")
+        if _is_ancestor(parent, y, o):
+            raise ValueError(f"validateConstraint: {name!r}: Bogus constraint; younger node is direct ancestor of older node (?).")
+        if _is_ancestor(parent, o, y):
+            msg = f"validateConstraint: {name!r}: Redundant constraint; old node is direct ancestor of young node."
+            if on_problem == "error":
+                raise ValueError(msg)
+            say("WARNING: Dropping constraint: " + msg)
+            continue
+        rows.append((name, y, o, pm))
+    if not rows and not text.strip():
+        raise ValueError("loadConstraints: No constraints found.")
+    anc = lambda x, y: _is_ancestor(parent, x, y)          # A(x, y)
+    desc = lambda x, y: _is_ancestor(parent, y, x)         # D(x, y)
+    # conflicts (validateWith: ordered pairs of different constraints)
+    for l in rows:
+        for r in rows:
+            if l != r and anc(r[1], l[2]) and (desc(r[2], l[1]) or desc(r[2], l[2])):
+                raise ValueError(f"loadConstraints: Constraint {r[0]} is conflicting given constraint {l[0]}.")
+    # duplicates (validateWithCommutative: the later one of each pair goes)
+    dup = []
+    for i, l in enumerate(rows):
+        for r in rows[i + 1:]:
+            if l != r and l[1] == r[1] and l[2] == r[2] and r not in dup:
+                dup.append(r)
+                say(f"Constraints {l[0]} and {r[0]} affect the same nodes.")
+    for r in dup:
+        rows.remove(r)
+    # redundancies
+    red = []
+    for l in rows:
+        for r in rows:
+            if l != r and desc(r[1], l[1]) and anc(r[2], l[2]) and r not in red:
+                red.append(r)
+                say(f"Constraint {r[0]} is redundant given constraint {l[0]}.")
+    for r in red:
+        rows.remove(r)
+    return {"names": [r[0] for r in rows], "young": np.array([r[1] for r in rows], np.int32),
+            "old": np.array([r[2] for r in rows], np.int32), "p": np.array([r[3] for r in rows], dtype=float)}
 
 
 def load_braces(text: str, parent, names):

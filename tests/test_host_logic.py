@@ -204,3 +204,47 @@ def test_philox_known_answers():
         0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
     u = [nuts_ref.uniform(5, 1, 2, d) for d in range(2000)]
     assert 0 < min(u) and max(u) < 1 and abs(sum(u) / len(u) - 0.5) < 0.03
+
+
+def test_constraint_validation_and_pruning():
+    """loadConstraints (Constraint.hs:275-374): bogus constraints are errors, a vacuous one is dropped, conflicts are
+    errors, duplicates and redundant constraints are pruned"""
+    #            0
+    #       1          6
+    #    2     5(e)  7(f)  8
+    #  3(a) 4(b)         9(c) 10(d)      pre-order; internal: 0, 1, 2, 6, 8
+    t = tree.parse_newick("(((a:1,b:1):1,e:2):1,(f:1,(c:1,d:1):1):1);")
+    parent, c0, c1, names, lens = tree.flatten_preorder(t)
+    assert parent.tolist() == [-1, 0, 1, 2, 2, 1, 0, 6, 6, 8, 8]
+    hdr = "Name,YoungerLeafA,YoungerLeafB,OlderLeafA,OlderLeafB,ProbabilityMass\n"
+    load = lambda body, **kw: prepare.load_constraints(hdr + body, parent, names, **kw)
+    # plain: (a,b) younger than (c,d)
+    c = load("c1,a,b,c,d,0.025\n")
+    assert c["young"].tolist() == [2] and c["old"].tolist() == [8] and c["p"].tolist() == [0.025]
+    # both nodes equal / younger node is an ancestor of the older one: errors
+    with pytest.raises(ValueError, match="both nodes are equal"):
+        load("bad,a,b,a,b,0.025\n")
+    with pytest.raises(ValueError, match="younger node is direct ancestor"):
+        load("bad,a,e,a,b,0.025\n")
+    # older node is an ancestor of the younger one: vacuous -> dropped with a warning (or an error on request)
+    msgs = []
+    c = load("vac,a,b,a,e,0.025\nc1,a,b,c,d,0.025\n", log=msgs.append)
+    assert c["names"] == ["c1"] and any("Dropping constraint" in m for m in msgs)
+    with pytest.raises(ValueError, match="old node is direct ancestor"):
+        load("vac,a,b,a,e,0.025\n", on_problem="error")
+    # duplicates: the later one goes
+    c = load("c1,a,b,c,d,0.025\nc1again,b,a,d,c,0.1\n")
+    assert c["names"] == ["c1"]
+    # redundancy: given (a,e) < (c,d), the constraint (a,b) < (f,c) [descendant of the young, ancestor of the old] is implied
+    c = load("strong,a,e,c,d,0.025\nweak,a,b,f,c,0.025\n")
+    assert c["names"] == ["strong"] and c["young"].tolist() == [1] and c["old"].tolist() == [8]
+    c = load("weak,a,b,f,c,0.025\nstrong,a,e,c,d,0.025\n")          # order of the file does not matter
+    assert c["names"] == ["strong"]
+    # conflict: (a,b) < (c,d) and (f,c) < (a,b): the second one's young node is an ancestor of the first one's old node
+    with pytest.raises(ValueError, match="conflicting"):
+        load("c1,a,b,c,d,0.025\nc2,f,c,a,b,0.025\n")
+    # unrelated constraints all survive, order kept
+    c = load("c1,a,b,c,d,0.025\nc5,c,d,a,e,0.05\n")   # (a,b) < (c,d) < (a,e): a chain, neither implied by the other
+    assert c["names"] == ["c1", "c5"]
+    with pytest.raises(ValueError, match="probabilityMass"):
+        load("c1,a,b,c,d,1.5\n")
