@@ -126,12 +126,15 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
     }
     h->oz_X_S = 0;
     h->cap = need;
-    if (h->dm.lik == MCD_LIK_FULL) {
-      size_t ndx = (size_t)need * h->ldk, ny = (size_t)need * h->ldy;
-      CU_TRY(h, cudaMalloc(&h->d_dx.p, ndx * 8));
-      CU_TRY(h, cudaMemset(h->d_dx.p, 0, ndx * 8));  // k-padding columns and tail chains stay 0
+    {  // y = P dx (and scratch of the posterior kernel) exists for every likelihood kind
+      const size_t ny = (size_t)need * h->ldy;
       CU_TRY(h, cudaMalloc(&h->d_y.p, ny * 8));
       CU_TRY(h, cudaMemset(h->d_y.p, 0, ny * 8));
+    }
+    if (h->dm.lik == MCD_LIK_FULL) {
+      size_t ndx = (size_t)need * h->ldk;
+      CU_TRY(h, cudaMalloc(&h->d_dx.p, ndx * 8));
+      CU_TRY(h, cudaMemset(h->d_dx.p, 0, ndx * 8));  // k-padding columns and tail chains stay 0
       if (make_tile_map(&h->tmX, h->d_dx.as<double>(), need, h->ldk) != 0)
         return fail(h, "cuTensorMapEncodeTiled failed for the residual matrix");
     }
@@ -356,7 +359,7 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   double* g = GRAD ? d_grad + (size_t)c0 * M.S : nullptr;
   int32_t* s = d_status + c0;
   // shared memory: reduction scratch + per chain group the staged state row [S] and contraction result [K]
-  const size_t smem = POST_SMEM_FIXED + (size_t)cpb * (M.S + M.N) * 8;
+  const size_t smem = POST_SMEM_FIXED + (size_t)cpb * M.S * 8;
 #define MCD_LAUNCH_POST(GG, CC, MB) \
   posterior_kernel<GG, CC, GRAD, MB><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n)
 #define MCD_LAUNCH_POST_G(GG, MB)                                              \
@@ -718,7 +721,7 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   h->N = N; h->K = K; h->S = 5 + 2 * N;
   h->ldk = (K + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
   h->Mp = (K + GEMM_PR - 1) / GEMM_PR * GEMM_PR;
-  h->ldy = h->Mp;
+  h->ldy = (N + GEMM_PR - 1) / GEMM_PR * GEMM_PR;  // >= Mp, and >= N: the near-critical sweep parks E[1..N-1] in the row
   h->ld8 = (K + OZ_KB - 1) / OZ_KB * OZ_KB;
   h->Mp8 = (K + OZ_N - 1) / OZ_N * OZ_N;
   {  // contraction pipe: INT8 tensor cores with 7 base-256 digit planes unless MCD_CONTRACTION says otherwise
@@ -883,7 +886,7 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
     if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
   // posterior kernels may need > 48 KiB dynamic smem on large trees
   {
-    const size_t post_smem = POST_SMEM_FIXED + (size_t)(N <= SMALL_TREE_MAX_NODES ? POST_THREADS / 32 : 1) * (h->S + N) * 8;
+    const size_t post_smem = POST_SMEM_FIXED + (size_t)(N <= SMALL_TREE_MAX_NODES ? POST_THREADS / 32 : 1) * (h->S + N + h->K) * 8;
     if (post_smem > 220 * 1024) return bail("mcd_create: tree too large for the posterior kernel's shared-memory staging (N > 9000)");
     const int lim = 225 * 1024;
 #define MCD_SET_SMEM(CC)                                                                                               \
