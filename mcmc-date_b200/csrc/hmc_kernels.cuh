@@ -105,6 +105,7 @@ __device__ __forceinline__ void nuts_normal2(uint64_t seed, uint32_t chain, uint
 
 // per-chain integer / real scalars
 enum { NI_ACTIVE = 0, NI_DEPTH, NI_LEAF, NI_DIR, NI_N, NI_NSUB, NI_NALPHA, NI_NLEAP, NI_STATUS, NI_DRAW, NI_DIVERGED, NI_TURNED,
+       NI_SLOT,  // row of the compacted evaluation batch this chain's next leaf is evaluated in
        NI_COLS = 16 };
 enum { NR_LOGU = 0, NR_H0NEG, NR_ALPHA, NR_EPS, NR_COLS = 4 };
 constexpr double NUTS_DELTA_MAX = 1000.0;
@@ -153,7 +154,7 @@ __device__ __forceinline__ void nuts_kick_drift(const NutsBuffers& nb, int b, co
   double* __restrict__ th = nb.thE[dir] + o;
   double* __restrict__ rr = nb.rE[dir] + o;
   const double* __restrict__ gg = nb.gE[dir] + o;
-  double* __restrict__ x = states + (size_t)b * S;
+  double* __restrict__ x = states + (size_t)ni[NI_SLOT] * S;
   // 4 independent elements per thread and trip: all loads of a trip are in flight before the first store
   for (int t0 = threadIdx.x; t0 < D; t0 += 4 * HMC_THREADS) {
     double r4[4], g4[4], q4[4], m4[4];
@@ -219,7 +220,9 @@ nuts_init_kernel(NutsBuffers nb, const double* __restrict__ theta0, const double
     ni[NI_ACTIVE] = ok;  // a chain that starts at a point of zero / undefined density stays where it is
     ni[NI_DEPTH] = 0; ni[NI_LEAF] = 0; ni[NI_DIR] = ud < 0.5 ? 0 : 1; ni[NI_N] = 1; ni[NI_NSUB] = 0; ni[NI_NALPHA] = 0;
     ni[NI_NLEAP] = 0; ni[NI_STATUS] = status[b]; ni[NI_DRAW] = 2; ni[NI_DIVERGED] = 0; ni[NI_TURNED] = 0;
-    if (ok) atomicAdd(nb.n_active, 1);
+    // still-active chains are compacted: each takes the next free row of the evaluation batch (the order is
+    // arbitrary, the chains are independent, so the results do not depend on it)
+    if (ok) ni[NI_SLOT] = atomicAdd(nb.n_active, 1);
   }
   __syncthreads();
   nuts_kick_drift(nb, b, sidx, inv_mass, states, S, D);
@@ -256,7 +259,9 @@ nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __r
   const bool even = (leaf & 1) == 0;
   double* __restrict__ cth0 = nb.ck_th + (size_t)idx_max * BD + o;
   double* __restrict__ cr0 = nb.ck_r + (size_t)idx_max * BD + o;
-  const double* __restrict__ grow = grad + (size_t)b * S;
+  const int slot = ni[NI_SLOT];  // row of this leaf in the compacted evaluation batch
+  const double* __restrict__ grow = grad + (size_t)slot * S;
+  out += (size_t)slot * 8;
   double P[NE], G[NE], Q[NE];
   double v1[3] = {0.0, 0.0, 0.0};
   {
@@ -290,7 +295,7 @@ nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __r
   nuts_block_sum<3>(v1, scratch);
   // ---- leaf: validity under the slice, divergence, acceptance statistic, reservoir choice
   if (tid == 0) {
-    const double hneg = out[(size_t)b * 8 + 6] - 0.5 * v1[0];
+    const double hneg = out[6] - 0.5 * v1[0];
     const double logu = nr[NR_LOGU];
     const int valid = logu <= hneg;                       // false for NaN
     const int diverged = !(hneg > logu - NUTS_DELTA_MAX);  // true for NaN
@@ -298,7 +303,7 @@ nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __r
     nr[NR_ALPHA] += (a == a) ? fmin(1.0, a) : 0.0;
     ni[NI_NALPHA] += 1;
     ni[NI_NLEAP] += 1;
-    ni[NI_STATUS] |= status[b];
+    ni[NI_STATUS] |= status[slot];
     int take = 0;
     if (valid) {
       const int ns = ni[NI_NSUB] + 1;
@@ -319,7 +324,7 @@ nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __r
       const int t = tid + i * HMC_THREADS;
       if (t < D) nb.thC[o + t] = Q[i];
     }
-    if (tid < 8) nb.outC[(size_t)b * 8 + tid] = out[(size_t)b * 8 + tid];
+    if (tid < 8) nb.outC[(size_t)b * 8 + tid] = out[tid];
   }
   // ---- U-turn checks of the balanced sub-trajectories this leaf closes (checkpoint scheme)
   int turned = 0;
@@ -380,7 +385,7 @@ nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __r
         ni[NI_DIR] = ud < 0.5 ? 0 : 1;
         ni[NI_NSUB] = 0;
         ni[NI_LEAF] = 0;
-        atomicAdd(nb.n_active, 1);
+        ni[NI_SLOT] = atomicAdd(nb.n_active, 1);
       }
     }
     __syncthreads();
@@ -399,14 +404,14 @@ nuts_leaf_kernel(NutsBuffers nb, const double* __restrict__ grad, const int* __r
         ni[NI_ACTIVE] = 0;  // the new half is discarded and the trajectory ends
       } else {
         ni[NI_LEAF] = leaf + 1;
-        atomicAdd(nb.n_active, 1);
+        ni[NI_SLOT] = atomicAdd(nb.n_active, 1);
       }
     }
     __syncthreads();
   }
   // ---- write the end back; a chain that goes on at the same end takes the first half of its next step first
   const bool same_end = ni[NI_ACTIVE] && ni[NI_DIR] == dir;
-  double* __restrict__ x = states + (size_t)b * S;
+  double* __restrict__ x = states + (size_t)ni[NI_SLOT] * S;
 #pragma unroll
   for (int i = 0; i < NE; ++i) {
     const int t = tid + i * HMC_THREADS;

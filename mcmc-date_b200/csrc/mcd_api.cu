@@ -598,9 +598,14 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
   CU_TRY(h, cudaStreamSynchronize(st));
   const long max_ticks = (1L << max_depth);
   bool pending = false;
-  if (flags[0] > 0) {
+  // The still-active chains are compacted into the first rows of the evaluation batch (each takes a row with an
+  // atomic counter when it decides to go on), so a tick evaluates only as many states as were active one tick
+  // earlier (the count the host knows; the real count can only be smaller, the surplus rows hold stale but valid
+  // states).
+  int n_eval = flags[0];
+  if (n_eval > 0) {
     for (long tick = 0; tick < max_ticks; ++tick) {
-      if (enqueue<true>(h, 0, n, xs, o, gr, stp, st)) return -1;
+      if (enqueue<true>(h, 0, n_eval, xs, o, gr, stp, st)) return -1;
       CU_TRY(h, cudaMemsetAsync(nb.n_active, 0, 4, st));
 #define MCD_NUTS_LEAF(NE) \
   nuts_leaf_kernel<NE><<<n, HMC_THREADS, 0, st>>>(nb, gr, h->d_sidx.as<int>(), d_invm, o, stp, xs, seed, iteration, max_depth, S, D, n)
@@ -619,7 +624,8 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
       CU_TRY(h, cudaEventRecord(h->nuts_ev[tick & 1], st));
       if (pending) {  // look at the previous tick's count while this one runs
         CU_TRY(h, cudaEventSynchronize(h->nuts_ev[(tick - 1) & 1]));
-        if (flags[(tick - 1) & 1] == 0) break;
+        n_eval = flags[(tick - 1) & 1];
+        if (n_eval == 0) break;
       }
       pending = true;
     }
