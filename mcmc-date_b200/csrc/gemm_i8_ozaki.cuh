@@ -302,8 +302,10 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 template <int S>
 __device__ __forceinline__ double oz_row_scale(double amax, bool finite, double* mult) {
   *mult = 0.0;
-  if (!finite) return __longlong_as_double(0x7ff8000000000000LL);
-  if (amax == 0.0) return 0.0;
+  // rows beyond 2^+-900 would overflow the power-of-two multipliers: treated as non-finite / as zero (their
+  // contribution is below 1e-270 in absolute terms)
+  if (!finite || amax > 8.452712498170644e+270) return __longlong_as_double(0x7ff8000000000000LL);
+  if (amax < 1.1830521861667747e-271) return 0.0;
   int e;
   const double f = frexp(amax, &e);  // amax = f * 2^e, f in [0.5, 1)
   const int es = f > 0.996 ? e + 2 : e + 1;
