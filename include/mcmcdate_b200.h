@@ -147,6 +147,26 @@ int mcd_nuts(mcd_handle* h, int32_t n_chains, const double* theta0 /*[B][D]*/, c
              int32_t max_depth, uint64_t seed, uint32_t iteration, double* theta_out /*[B][D]*/,
              double* out /*[B][MCD_OUT_COLS]*/, double* accept_stat /*[B]*/, int32_t* info /*[B][4]*/, int32_t* status /*[B]*/);
 
+/* Metropolis-Hastings moves on chains that live in HBM (first part).  mcd_chains_set uploads the
+ * states of n chains and evaluates them; mcd_mh_step applies ONE proposal to every resident chain in place, evaluates
+ * the proposed states (value-only path), and accepts or rejects per chain; mcd_chains_get reads states / ln-posterior
+ * parts back.  Proposals (first-party code of the reference, lib/Mcmc/Tree/Proposal/Ultrametric.hs):
+ *   MCD_MH_SLIDE_NODE     slideNodeAtUltrametric    (:50-62)    truncated normal between the older child and the parent
+ *   MCD_MH_SCALE_SUBTREE  scaleSubTreeAtUltrametric (:126-147)  new height ~ truncated normal on (0, parent), the whole
+ *                                                               sub tree scaled, |J| = xi^(n_inner - 1)
+ * node: an inner node below the root (same node for every chain), or -1: every chain draws its own uniformly.
+ * sd, tune: standard deviation and tuning parameter of the proposal (sd' = tune * sd, Internal.hs:117).
+ * use_root_jacobian: include jacobianRootBranch in the ratio (proposals the reference lifts with it: children of the
+ * root, app/Definitions.hs:145-166).  accepted[b] (nullable) = 1 / 0, or -1 where the reference's truncatedNormalDistr
+ * would call `error` (bounds crossed: the chain's tree is invalid); such chains are left unchanged.
+ * Uniforms: Philox4x32-10, key = seed, counter = (chain, iteration, draw, 2); draws: 0 quantile, 1 acceptance, 2 node. */
+enum { MCD_MH_SLIDE_NODE = 0, MCD_MH_SCALE_SUBTREE = 1 };
+int mcd_chains_set(mcd_handle* h, int32_t n_chains, const double* states /*[B][S]*/);
+int mcd_chains_get(mcd_handle* h, int32_t n_chains, double* states /*[B][S] or NULL*/, double* out /*[B][8] or NULL*/,
+                   int32_t* status /*[B] or NULL*/);
+int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double sd, double tune, int32_t use_root_jacobian, uint64_t seed,
+                uint32_t iteration, int32_t* accepted /*[B] or NULL*/);
+
 /* Arithmetic pipe of the precision-matrix contraction Y = DX . Sigma^-1 on large trees (the dominant kernel).
  *   MCD_CONTRACT_DMMA   FP64 tensor instructions (mma.sync m8n8k4.f64), plain FP64 GEMM rounding
  *   MCD_CONTRACT_I8_Sn  INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators) on n balanced base-256 digit

@@ -20,6 +20,7 @@ _LIB = None
 EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
     "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_leapfrog", "mcd_nuts",
+    "mcd_chains_set", "mcd_chains_get", "mcd_mh_step",
     "mcd_eval_device", "mcd_set_contraction", "mcd_get_contraction",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
     "mcd_kernel_times",
@@ -74,6 +75,9 @@ def load_library():
     L.mcd_eval_grad_theta.argtypes = [vp, i32, dp, dp, dp, dp, ip]
     L.mcd_leapfrog.argtypes = [vp, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip]
     L.mcd_nuts.argtypes = [vp, i32, dp, dp, dp, dp, dp, i32, C.c_uint64, C.c_uint32, dp, dp, dp, ip, ip]
+    L.mcd_chains_set.argtypes = [vp, i32, dp]
+    L.mcd_chains_get.argtypes = [vp, i32, dp, dp, ip]
+    L.mcd_mh_step.argtypes = [vp, i32, i32, C.c_double, C.c_double, i32, C.c_uint64, C.c_uint32, ip]
     L.mcd_eval_device.argtypes = [vp, i32, vp, vp, vp, vp]
     L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mcd_set_contraction.argtypes = [vp, i32]
@@ -233,6 +237,26 @@ class Evaluator:
         self._check(self._L.mcd_nuts(self.h, B, _dp(T), _dp(base), _dp(im), _dp(eps), _dp(mom) if mom is not None else None,
                                      int(max_depth), int(seed), int(iteration), _dp(th), _dp(out), _dp(acc), _ip(info), _ip(st)))
         return th, out, acc, info, st
+
+    # ---- chains resident in HBM + Metropolis-Hastings moves
+    def chains_set(self, states):
+        X = np.ascontiguousarray(states, dtype=np.float64).reshape(-1, self.S)
+        self._n_resident = X.shape[0]
+        self._check(self._L.mcd_chains_set(self.h, X.shape[0], _dp(X)))
+
+    def chains_get(self):
+        B = self._n_resident
+        X, out, st = np.empty((B, self.S)), np.empty((B, _m.OUT_COLS)), np.empty(B, np.int32)
+        self._check(self._L.mcd_chains_get(self.h, B, _dp(X), _dp(out), _ip(st)))
+        return X, out, st
+
+    def mh_step(self, kind: int, node: int, sd: float, tune: float = 1.0, use_root_jacobian: bool = False, seed: int = 0,
+                iteration: int = 0, want_accepted: bool = True):
+        """one proposal (0: slide node, 1: scale sub tree) on every resident chain -> accepted flags (1 / 0 / -1)"""
+        acc = np.empty(self._n_resident, np.int32) if want_accepted else None
+        self._check(self._L.mcd_mh_step(self.h, int(kind), int(node), float(sd), float(tune), int(use_root_jacobian), int(seed),
+                                        int(iteration), _ip(acc) if acc is not None else None))
+        return acc
 
     def nuts_ptr(self, B: int, theta0: int, base: int, inv_mass: int, eps: int, momentum0: int, max_depth: int, seed: int,
                  iteration: int, theta_out: int, out: int, accept_stat: int, info: int, status: int):

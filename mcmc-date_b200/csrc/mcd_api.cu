@@ -26,6 +26,7 @@
 #include "gemm_f64.cuh"
 #include "gemm_i8_ozaki.cuh"
 #include "hmc_kernels.cuh"
+#include "mh_kernels.cuh"
 #include "posterior_kernels.cuh"
 
 using namespace mcd;
@@ -69,6 +70,10 @@ struct mcd_handle {
   DevBuf d_states, d_out, d_grad, d_status;  // staging for the host-buffer API
   DevBuf d_theta, d_gtheta, d_base, d_tidx, d_sidx;  // theta-packed API
   DevBuf d_mom, d_eps, d_invmass, d_energy, d_status_acc;  // device-resident leapfrog trajectories
+  // chains resident in HBM for Metropolis-Hastings moves (mh_kernels.cuh)
+  DevBuf d_chain, d_chain_out, d_chain_status, d_new_out, d_new_status, d_undo, d_meta, d_lq, d_accepted;
+  DevBuf d_mh_child1, d_mh_size, d_mh_inner_cnt, d_mh_inner_list;
+  int n_resident = 0, chain_cap = 0, n_inner_nonroot = 0;
   DevBuf d_nuts;                  // batched NUTS: trajectory ends, checkpoints, candidates, per-chain scalars
   size_t nuts_bytes = 0;
   int* nuts_flags = nullptr;      // pinned: active-chain counts of the last two ticks
@@ -651,6 +656,108 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
   return 0;
 }
 
+// ---- chains resident in HBM + Metropolis-Hastings steps (mh_kernels.cuh)
+int mh_prepare_value_path(mcd_handle* h, int n) {
+  if (ensure_capacity(h, n, false, false)) return -1;
+  if (h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && (ensure_cholesky(h, nullptr) || ensure_i8(h))) return -1;
+  return 0;
+}
+int chains_set(mcd_handle* h, int n, const double* states) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (n <= 0 || !states) return fail(h, "mcd_chains_set: need n > 0 and a state buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (mh_prepare_value_path(h, n)) return -1;
+  const int S = h->S, N = h->N;
+  if (n > h->chain_cap) {
+    CU_TRY(h, cudaDeviceSynchronize());
+    for (DevBuf* b : {&h->d_chain, &h->d_chain_out, &h->d_chain_status, &h->d_new_out, &h->d_new_status, &h->d_undo, &h->d_meta,
+                      &h->d_lq, &h->d_accepted}) {
+      if (b->p) cudaFree(b->p);
+      b->p = nullptr;
+    }
+    const int cap = (n + 127) / 128 * 128;
+    CU_TRY(h, cudaMalloc(&h->d_chain.p, (size_t)cap * S * 8));
+    CU_TRY(h, cudaMalloc(&h->d_chain_out.p, (size_t)cap * 8 * 8));
+    CU_TRY(h, cudaMalloc(&h->d_new_out.p, (size_t)cap * 8 * 8));
+    CU_TRY(h, cudaMalloc(&h->d_chain_status.p, (size_t)cap * 4));
+    CU_TRY(h, cudaMalloc(&h->d_new_status.p, (size_t)cap * 4));
+    CU_TRY(h, cudaMalloc(&h->d_undo.p, (size_t)cap * N * 8));
+    CU_TRY(h, cudaMalloc(&h->d_meta.p, (size_t)cap * sizeof(int4)));
+    CU_TRY(h, cudaMalloc(&h->d_lq.p, (size_t)cap * 8));
+    CU_TRY(h, cudaMalloc(&h->d_accepted.p, (size_t)cap * 4));
+    h->chain_cap = cap;
+  }
+  if (!h->d_mh_child1.p) {  // topology tables of the proposals: second children, sub-tree sizes, inner-node counts
+    std::vector<int> size(N, 1), inner(N, 0), list;
+    std::vector<int> child0(N, -1);
+    for (int i = N - 1; i >= 1; --i) {
+      size[h->parent[i]] += size[i];
+      child0[h->parent[i]] = i;  // descending i: the last one written is the first child
+    }
+    for (int i = N - 1; i >= 0; --i) {
+      if (child0[i] >= 0) inner[i] += 1;
+      if (i > 0) inner[h->parent[i]] += inner[i];
+    }
+    for (int i = 1; i < N; ++i)
+      if (child0[i] >= 0) list.push_back(i);
+    h->n_inner_nonroot = (int)list.size();
+    if (upload(h, h->d_mh_child1, h->child1.data(), N) || upload(h, h->d_mh_size, size.data(), N) ||
+        upload(h, h->d_mh_inner_cnt, inner.data(), N) || upload(h, h->d_mh_inner_list, list.data(), list.size()))
+      return -1;
+  }
+  cudaStream_t st = h->streams[0];
+  CU_TRY(h, cudaMemcpyAsync(h->d_chain.p, states, (size_t)n * S * 8, cudaMemcpyHostToDevice, st));
+  if (enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_chain_out.as<double>(), nullptr, h->d_chain_status.as<int32_t>(), st))
+    return -1;
+  CU_TRY(h, cudaStreamSynchronize(st));
+  h->n_resident = n;
+  return 0;
+}
+int chains_get(mcd_handle* h, int n, double* states, double* out, int32_t* status) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (n <= 0 || n > h->n_resident) return fail(h, "mcd_chains_get: more chains requested than are resident");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->streams[0];
+  if (states) CU_TRY(h, cudaMemcpyAsync(states, h->d_chain.p, (size_t)n * h->S * 8, cudaMemcpyDeviceToHost, st));
+  if (out) CU_TRY(h, cudaMemcpyAsync(out, h->d_chain_out.p, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost, st));
+  if (status) CU_TRY(h, cudaMemcpyAsync(status, h->d_chain_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return 0;
+}
+int mh_step(mcd_handle* h, int kind, int node, double sd, double tune, int use_root_jacobian, uint64_t seed, uint32_t iteration,
+            int32_t* accepted) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  const int n = h->n_resident, N = h->N, S = h->S;
+  if (n <= 0) return fail(h, "mcd_mh_step: no resident chains (call mcd_chains_set first)");
+  if (kind != MH_SLIDE_NODE && kind != MH_SCALE_SUBTREE) return fail(h, "mcd_mh_step: unknown proposal kind");
+  if (h->n_inner_nonroot == 0) return fail(h, "mcd_mh_step: the tree has no inner node below the root");
+  if (node >= 0 && (node == 0 || node >= N || h->child1[node] < 0))
+    return fail(h, "mcd_mh_step: the node must be an inner node below the root (slideNodeAtUltrametric: path leads to a leaf)");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (mh_prepare_value_path(h, n)) return -1;
+  cudaStream_t st = h->streams[0];
+  mh_propose_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_meta.as<int4>(), h->d_lq.as<double>(),
+                                       h->dm.parent, h->d_mh_child1.as<int>(), h->d_mh_size.as<int>(), h->d_mh_inner_cnt.as<int>(),
+                                       h->d_mh_inner_list.as<int>(), h->n_inner_nonroot, kind, node, sd * tune, seed, iteration, S,
+                                       N, n);
+  if (enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st))
+    return -1;
+  mh_accept_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_meta.as<int4>(), h->d_lq.as<double>(),
+                                      h->d_chain_out.as<double>(), h->d_new_out.as<double>(), h->d_chain_status.as<int32_t>(),
+                                      h->d_new_status.as<int32_t>(), h->d_accepted.as<int32_t>(), use_root_jacobian, seed,
+                                      iteration, S, N, n);
+  h->launches += 2;
+  CU_TRY(h, cudaGetLastError());
+  if (accepted) {
+    CU_TRY(h, cudaMemcpyAsync(accepted, h->d_accepted.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -974,6 +1081,14 @@ int mcd_nuts(mcd_handle* h, int32_t n, const double* theta0, const double* base_
              double* theta_out, double* out, double* accept_stat, int32_t* info, int32_t* status) {
   return nuts_host(h, n, theta0, base_state, inv_mass, step_size, momentum0, max_depth, seed, iteration, theta_out, out,
                    accept_stat, info, status);
+}
+int mcd_chains_set(mcd_handle* h, int32_t n, const double* states) { return chains_set(h, n, states); }
+int mcd_chains_get(mcd_handle* h, int32_t n, double* states, double* out, int32_t* status) {
+  return chains_get(h, n, states, out, status);
+}
+int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double sd, double tune, int32_t use_root_jacobian, uint64_t seed,
+                uint32_t iteration, int32_t* accepted) {
+  return mh_step(h, kind, node, sd, tune, use_root_jacobian, seed, iteration, accepted);
 }
 int mcd_eval_device(mcd_handle* h, int32_t n, const double* d_states, double* d_out, int32_t* d_status, void* stream) {
   return eval_device<false>(h, n, d_states, d_out, nullptr, d_status, stream);

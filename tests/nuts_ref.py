@@ -20,8 +20,8 @@ def philox4x32_10(counter, key):
     return c
 
 
-def uniform(seed, chain, iteration, draw):
-    c = philox4x32_10((chain, iteration, draw, 0), (seed & MASK, (seed >> 32) & MASK))
+def uniform(seed, chain, iteration, draw, stream=0):
+    c = philox4x32_10((chain, iteration, draw, stream), (seed & MASK, (seed >> 32) & MASK))
     k = ((c[0] >> 5) << 26) | (c[1] >> 6)
     return (k + 0.5) * 2.0 ** -53
 

@@ -470,6 +470,47 @@ def test_device_nuts_draws_its_own_momenta():
     ev.close()
 
 
+@pytest.mark.parametrize("n_leaves,B", [(24, 64), (300, 40)])
+def test_device_resident_mh_proposals_match_host_restatement(n_leaves, B):
+    """chains resident in HBM: slide-node and scale-sub-tree proposals (first-party code of the reference), value-only
+    evaluation, accept / restore -- step by step against tests/mh_ref.py (oracle values, same Philox uniforms)"""
+    import mh_ref
+    md, h = synth.synthetic_model(n_leaves, seed=301 + n_leaves, n_cal=3, n_con=2, n_brace=0)
+    X = synth.synthetic_states(md, h, B)
+    ev = binding.Evaluator(md)
+    orc = O.Oracle(md)
+    parent = [int(p) for p in md.parent]
+    child, size, inner, inner_list = mh_ref.topology(parent)
+    ev.chains_set(X)
+    Xr = X.copy()
+    out_r, st_r = orc.eval(Xr)
+    out_r = np.concatenate([out_r, np.zeros((B, 1))], axis=1) if out_r.shape[1] == 7 else out_r
+    Xd, out_d, st_d = ev.chains_get()
+    assert np.array_equal(Xd, X) and relerr(out_d[:, :7], out_r[:, :7]).max() < TOL and np.array_equal(st_d, st_r)
+    root_child = 1 if child[1] else child[0][1]          # an inner child of the root: lifted with jacobianRootBranch
+    deep = max(inner_list, key=lambda i: (size[i] > 3, -size[i]))
+    steps = [(mh_ref.SLIDE_NODE, root_child, 0.05, True), (mh_ref.SCALE_SUBTREE, root_child, 0.05, True),
+             (mh_ref.SLIDE_NODE, -1, 0.02, False), (mh_ref.SCALE_SUBTREE, -1, 0.02, False), (mh_ref.SLIDE_NODE, deep, 0.5, False),
+             (mh_ref.SCALE_SUBTREE, deep, 0.01, False), (mh_ref.SLIDE_NODE, -1, 0.01, False), (mh_ref.SLIDE_NODE, -1, 0.01, False)]
+    n_acc = n_rej = 0
+    for it, (kind, node, sd, jac) in enumerate(steps):
+        acc_d = ev.mh_step(kind, node, sd, tune=1.3, use_root_jacobian=jac, seed=4242, iteration=it)
+        acc_r = mh_ref.mh_step(orc, parent, Xr, out_r, st_r, kind, node, sd, 1.3, jac, 4242, it)
+        assert np.array_equal(acc_d, acc_r), (it, np.nonzero(acc_d != acc_r))
+        n_acc += int((acc_r == 1).sum())
+        n_rej += int((acc_r == 0).sum())
+    assert n_acc > B and n_rej > B // 4                    # both branches of the accept kernel were exercised
+    Xd, out_d, st_d = ev.chains_get()
+    assert (np.abs(Xd - Xr) <= 1e-11 * np.maximum(1.0, np.abs(Xr))).all()
+    assert relerr(out_d[:, :7], out_r[:, :7]).max() < 1e-9 and np.array_equal(st_d, st_r)
+    # the resident ln-posterior parts are those of the resident states
+    o2, s2 = ev.eval(Xd)
+    assert relerr(out_d[:, :7], o2[:, :7]).max() < 1e-12
+    with pytest.raises(RuntimeError):
+        ev.mh_step(mh_ref.SLIDE_NODE, 0, 0.1)              # the root does not slide
+    ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
