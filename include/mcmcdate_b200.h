@@ -147,25 +147,80 @@ int mcd_nuts(mcd_handle* h, int32_t n_chains, const double* theta0 /*[B][D]*/, c
              int32_t max_depth, uint64_t seed, uint32_t iteration, double* theta_out /*[B][D]*/,
              double* out /*[B][MCD_OUT_COLS]*/, double* accept_stat /*[B]*/, int32_t* info /*[B][4]*/, int32_t* status /*[B]*/);
 
-/* Metropolis-Hastings moves on chains that live in HBM (first part).  mcd_chains_set uploads the
- * states of n chains and evaluates them; mcd_mh_step applies ONE proposal to every resident chain in place, evaluates
- * the proposed states (value-only path), and accepts or rejects per chain; mcd_chains_get reads states / ln-posterior
- * parts back.  Proposals (first-party code of the reference, lib/Mcmc/Tree/Proposal/Ultrametric.hs):
- *   MCD_MH_SLIDE_NODE     slideNodeAtUltrametric    (:50-62)    truncated normal between the older child and the parent
- *   MCD_MH_SCALE_SUBTREE  scaleSubTreeAtUltrametric (:126-147)  new height ~ truncated normal on (0, parent), the whole
- *                                                               sub tree scaled, |J| = xi^(n_inner - 1)
- * node: an inner node below the root (same node for every chain), or -1: every chain draws its own uniformly.
- * sd, tune: standard deviation and tuning parameter of the proposal (sd' = tune * sd, Internal.hs:117).
- * use_root_jacobian: include jacobianRootBranch in the ratio (proposals the reference lifts with it: children of the
- * root, app/Definitions.hs:145-166).  accepted[b] (nullable) = 1 / 0, or -1 where the reference's truncatedNormalDistr
- * would call `error` (bounds crossed: the chain's tree is invalid); such chains are left unchanged.
- * Uniforms: Philox4x32-10, key = seed, counter = (chain, iteration, draw, 2); draws: 0 quantile, 1 acceptance, 2 node. */
-enum { MCD_MH_SLIDE_NODE = 0, MCD_MH_SCALE_SUBTREE = 1 };
+/* Metropolis-Hastings-Green moves on chains that live in HBM.  mcd_chains_set uploads the states of
+ * n chains and evaluates them; mcd_mh_step applies ONE proposal to every resident chain in place, evaluates the proposed
+ * states (value-only path), and accepts or rejects per chain; mcd_mh_cycle runs sweeps over a whole list of proposals
+ * without a host round trip; mcd_chains_get reads states / ln-posterior parts back.
+ * Every proposal of the reference's cycle (app/Definitions.hs:145-278) is available; lib/ = lib/Mcmc/Tree/Proposal:
+ *   kind                            reference                                           `node` argument      `param`
+ *   MCD_MH_SLIDE_NODE               slideNodeAtUltrametric      lib/Ultrametric.hs:50-62     inner node | -1      sd
+ *   MCD_MH_SCALE_SUBTREE            scaleSubTreeAtUltrametric   lib/Ultrametric.hs:126-147   inner node | -1      sd
+ *   MCD_MH_PULLEY                   pulleyUltrametric           lib/Ultrametric.hs:219-316   ignored              sd
+ *   MCD_MH_SLIDE_BRACE              slideBracedNodesUltrametric lib/Brace.hs:30-82           brace index | -1     sd
+ *   MCD_MH_SCALE_BRANCH             scaleBranch (rate tree)     lib/Unconstrained.hs:52-92   node >= 1 | -1       shape k
+ *   MCD_MH_SCALE_RATE_SUBTREE       scaleSubTreeAt (rate tree)  lib/Unconstrained.hs:94-170  inner node | -1      shape k
+ *   MCD_MH_SCALE_NORM_TREE_CONTRA_M scaleNormAndTreeContrarily  lib/Unconstrained.hs:260-306 on (rateMean, rates)     k
+ *   MCD_MH_SCALE_NORM_TREE_CONTRA_H   "                         app/Definitions.hs:249-260   on (timeHeight, rates)   k
+ *   MCD_MH_SCALE_VAR_TREE           scaleVarianceAndTree        lib/Unconstrained.hs:308-371 ignored              shape k
+ *   MCD_MH_SCALE_VAR_TREE_AUTO      scaleVarianceAndTreeAutocorrelated  lib/Unconstrained.hs:380-439 ignored      shape k
+ *   MCD_MH_SLIDE_NODE_CONTRA        slideNodesAtContrarily      lib/Contrary.hs:60-131       inner node | -1      sd
+ *   MCD_MH_SCALE_SUBTREE_CONTRA     scaleSubTreesAtContrarily   lib/Contrary.hs:283-377      inner node | -1      sd
+ *   MCD_MH_SLIDE_BRACE_CONTRA       slideBracedNodesContrarily  lib/Brace.hs:88-209          brace index | -1     sd
+ *   MCD_MH_SLIDE_ROOT_CONTRA        slideRootContrarily         lib/Contrary.hs:172-246      ignored              sd
+ *   MCD_MH_SCALE_RATES_TREE_CONTRA  scaleRatesAndTreeContrarily lib/Contrary.hs:425-486      ignored              sd
+ *   MCD_MH_SCALE_SCALAR             scaleUnbiased (`mcmc`)      app/Definitions.hs:262-266   0 lambda 1 mu 2 H 3 m 4 v   k
+ *   MCD_MH_SCALE_H_M_CONTRA         scaleContrarily (`mcmc`)    app/Definitions.hs:251       ignored              shape k
+ * node = -1: every chain draws its own node / brace uniformly among the eligible ones.  Inner node = inner node below
+ * the root (the reference never builds these proposals for the root: HandleNode, app/Definitions.hs:132-138).
+ * param, tune: standard deviation sd (truncated-normal moves, sd' = tune * sd, Internal.hs:117) or shape k of the
+ * multiplier u ~ Gamma(k / tune, tune / k) (Unconstrained.hs:112, `mcmc` Scale proposals).
+ * use_root_jacobian: include jacobianRootBranch in the ratio (proposals the reference lifts with liftProposalWith
+ * jacobianRootBranch: the [R] ones of app/Definitions.hs).  accepted[b] (nullable) = 1 / 0, or -1 where the reference would
+ * call `error` (truncatedNormalDistr: bounds crossed -- the chain's tree is invalid); such chains are left unchanged.
+ * Heated chains (mcd_mc3_configure): ln r uses beta_prior * d ln prior + beta_lik * d ln lik.
+ * Uniforms: Philox4x32-10, key = seed, counter = (chain, iteration, draw, 2); draws: 0 quantile, 1 acceptance, 2 node,
+ * 7.. the gamma sampler (Marsaglia-Tsang).  Distinct proposals need distinct `iteration` values. */
+enum { MCD_MH_SLIDE_NODE = 0, MCD_MH_SCALE_SUBTREE = 1, MCD_MH_PULLEY = 2, MCD_MH_SLIDE_BRACE = 3, MCD_MH_SCALE_BRANCH = 4,
+       MCD_MH_SCALE_RATE_SUBTREE = 5, MCD_MH_SCALE_NORM_TREE_CONTRA_M = 6, MCD_MH_SCALE_NORM_TREE_CONTRA_H = 7,
+       MCD_MH_SCALE_VAR_TREE = 8, MCD_MH_SCALE_VAR_TREE_AUTO = 9, MCD_MH_SLIDE_NODE_CONTRA = 10,
+       MCD_MH_SCALE_SUBTREE_CONTRA = 11, MCD_MH_SLIDE_BRACE_CONTRA = 12, MCD_MH_SLIDE_ROOT_CONTRA = 13,
+       MCD_MH_SCALE_RATES_TREE_CONTRA = 14, MCD_MH_SCALE_SCALAR = 15, MCD_MH_SCALE_H_M_CONTRA = 16 };
 int mcd_chains_set(mcd_handle* h, int32_t n_chains, const double* states /*[B][S]*/);
 int mcd_chains_get(mcd_handle* h, int32_t n_chains, double* states /*[B][S] or NULL*/, double* out /*[B][8] or NULL*/,
                    int32_t* status /*[B] or NULL*/);
-int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double sd, double tune, int32_t use_root_jacobian, uint64_t seed,
+int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double param, double tune, int32_t use_root_jacobian, uint64_t seed,
                 uint32_t iteration, int32_t* accepted /*[B] or NULL*/);
+/* One entry of a proposal cycle (the reference's `Cycle`, app/Definitions.hs:262-285): `repeat` = the proposal's weight. */
+typedef struct mcd_mh_proposal {
+  int32_t kind, node;
+  double param, tune;
+  int32_t use_root_jacobian, repeat;
+} mcd_mh_proposal;
+/* n_iterations sweeps over props[0..n_props) (each `repeat` times, in the given order), enqueued back to back; proposal
+ * number s of the call uses Philox iteration iteration0 + s.  accepted / invalid [n_props] (nullable): chains x steps
+ * accepted / rejected as invalid per list entry -- what the reference's auto tuner consumes.  *iteration_next (nullable):
+ * first unused iteration value.  At most 4096 list entries per call. */
+int mcd_mh_cycle(mcd_handle* h, int32_t n_props, const mcd_mh_proposal* props, int32_t n_iterations, uint64_t seed,
+                 uint32_t iteration0, uint64_t* accepted, uint64_t* invalid, uint32_t* iteration_next);
+
+/* Heated chains: Metropolis-coupled MCMC (`mc3`, app/Main.hs:476-479) and the stepping-stone / thermodynamic-integration
+ * points of `marginalLikelihood` (app/Main.hs:511-543); both live in the un-vendored `mcmc` package and are restated
+ * from their published definitions.  n_global chains (over all ranks; this handle's resident chains are
+ * [chain_offset, chain_offset + n_resident) of them) form groups of chains_per_group consecutive chains; chain c starts
+ * at temperature slot c % chains_per_group with heats (ladder_prior[slot], ladder_lik[slot]).  MC3: both ladders equal
+ * the beta_i; stepping stone: ladder_prior = 1, ladder_lik = beta_i, no swaps.  chains_per_group = 0: cold chains again.
+ * mcd_mc3_swap proposes, in every group, the exchange of the chains at slots (pair, pair + 1) (pair = -1: drawn per
+ * group): ln r = (beta_p - beta_{p+1}) (ln pi(x_{p+1}) - ln pi(x_p)); accepted exchanges swap the chains' SLOTS, states
+ * never move.  d_stats_global: DEVICE pointer to the (ln prior, ln likelihood) pairs of all n_global chains [n_global][2]
+ * (all-gathered over NCCL by the host from mcd_chains_out_device, columns MCD_OUT_LNPRIOR / MCD_OUT_LNLIK) or NULL when
+ * this handle holds all chains.  Every rank takes identical decisions (Philox counter (group, iteration, 0, 3)).
+ * accepted[g] (host, nullable) = 1 / 0 per group.  mcd_mc3_slots: current slot of every chain [n_global]. */
+int mcd_mc3_configure(mcd_handle* h, int32_t n_global, int32_t chain_offset, int32_t chains_per_group,
+                      const double* ladder_prior /*[chains_per_group]*/, const double* ladder_lik /*[chains_per_group]*/);
+int mcd_mc3_swap(mcd_handle* h, int32_t pair, uint64_t seed, uint32_t iteration, const double* d_stats_global,
+                 int32_t* accepted /*[n_global / chains_per_group] or NULL*/);
+int mcd_mc3_slots(mcd_handle* h, int32_t* slots /*[n_global]*/);
+void* mcd_chains_out_device(mcd_handle* h); /* device pointer: [n_resident][MCD_OUT_COLS] of the resident chains */
 
 /* Arithmetic pipe of the precision-matrix contraction Y = DX . Sigma^-1 on large trees (the dominant kernel).
  *   MCD_CONTRACT_DMMA   FP64 tensor instructions (mma.sync m8n8k4.f64), plain FP64 GEMM rounding

@@ -20,11 +20,24 @@ _LIB = None
 EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
     "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_leapfrog", "mcd_nuts",
-    "mcd_chains_set", "mcd_chains_get", "mcd_mh_step",
+    "mcd_chains_set", "mcd_chains_get", "mcd_mh_step", "mcd_mh_cycle", "mcd_mc3_configure", "mcd_mc3_swap", "mcd_mc3_slots",
+    "mcd_chains_out_device",
     "mcd_eval_device", "mcd_set_contraction", "mcd_get_contraction",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
     "mcd_kernel_times",
 ]
+
+
+class MhProposalC(C.Structure):
+    """struct mcd_mh_proposal"""
+    _fields_ = [("kind", C.c_int32), ("node", C.c_int32), ("param", C.c_double), ("tune", C.c_double),
+                ("use_root_jacobian", C.c_int32), ("repeat", C.c_int32)]
+
+
+# proposal kinds (include/mcmcdate_b200.h)
+(MH_SLIDE_NODE, MH_SCALE_SUBTREE, MH_PULLEY, MH_SLIDE_BRACE, MH_SCALE_BRANCH, MH_SCALE_RATE_SUBTREE, MH_SCALE_NORM_TREE_CONTRA_M,
+ MH_SCALE_NORM_TREE_CONTRA_H, MH_SCALE_VAR_TREE, MH_SCALE_VAR_TREE_AUTO, MH_SLIDE_NODE_CONTRA, MH_SCALE_SUBTREE_CONTRA,
+ MH_SLIDE_BRACE_CONTRA, MH_SLIDE_ROOT_CONTRA, MH_SCALE_RATES_TREE_CONTRA, MH_SCALE_SCALAR, MH_SCALE_H_M_CONTRA) = range(17)
 
 
 class ModelDescC(C.Structure):
@@ -78,6 +91,13 @@ def load_library():
     L.mcd_chains_set.argtypes = [vp, i32, dp]
     L.mcd_chains_get.argtypes = [vp, i32, dp, dp, ip]
     L.mcd_mh_step.argtypes = [vp, i32, i32, C.c_double, C.c_double, i32, C.c_uint64, C.c_uint32, ip]
+    u64p = C.POINTER(C.c_uint64)
+    L.mcd_mh_cycle.argtypes = [vp, i32, C.POINTER(MhProposalC), i32, C.c_uint64, C.c_uint32, u64p, u64p, C.POINTER(C.c_uint32)]
+    L.mcd_mc3_configure.argtypes = [vp, i32, i32, i32, dp, dp]
+    L.mcd_mc3_swap.argtypes = [vp, i32, C.c_uint64, C.c_uint32, vp, ip]
+    L.mcd_mc3_slots.argtypes = [vp, ip]
+    L.mcd_chains_out_device.argtypes = [vp]
+    L.mcd_chains_out_device.restype = vp
     L.mcd_eval_device.argtypes = [vp, i32, vp, vp, vp, vp]
     L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mcd_set_contraction.argtypes = [vp, i32]
@@ -252,11 +272,48 @@ class Evaluator:
 
     def mh_step(self, kind: int, node: int, sd: float, tune: float = 1.0, use_root_jacobian: bool = False, seed: int = 0,
                 iteration: int = 0, want_accepted: bool = True):
-        """one proposal (0: slide node, 1: scale sub tree) on every resident chain -> accepted flags (1 / 0 / -1)"""
+        """one proposal (MH_* kind; sd = standard deviation or gamma shape) on every resident chain -> accepted flags (1 / 0 / -1)"""
         acc = np.empty(self._n_resident, np.int32) if want_accepted else None
         self._check(self._L.mcd_mh_step(self.h, int(kind), int(node), float(sd), float(tune), int(use_root_jacobian), int(seed),
                                         int(iteration), _ip(acc) if acc is not None else None))
         return acc
+
+    def mh_cycle(self, proposals, n_iterations: int = 1, seed: int = 0, iteration0: int = 0):
+        """sweeps over a list of (kind, node, param, tune, use_root_jacobian, repeat) tuples, enqueued back to back
+        -> (accepted[n_props], invalid[n_props], next unused iteration value)"""
+        n = len(proposals)
+        arr = (MhProposalC * n)()
+        for i, (kind, node, param, tune, jac, rep) in enumerate(proposals):
+            arr[i] = MhProposalC(int(kind), int(node), float(param), float(tune), int(jac), int(rep))
+        acc, inv = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        nxt = C.c_uint32(0)
+        u64p = C.POINTER(C.c_uint64)
+        self._check(self._L.mcd_mh_cycle(self.h, n, arr, int(n_iterations), int(seed), int(iteration0), acc.ctypes.data_as(u64p),
+                                         inv.ctypes.data_as(u64p), C.byref(nxt)))
+        return acc, inv, int(nxt.value)
+
+    def mc3_configure(self, n_global: int, chain_offset: int, chains_per_group: int, ladder_prior=None, ladder_lik=None):
+        """heated chains: groups of chains_per_group temperatures (0: cold chains again)"""
+        lp = np.ascontiguousarray(ladder_prior if ladder_prior is not None else [1.0], dtype=np.float64)
+        ll = np.ascontiguousarray(ladder_lik if ladder_lik is not None else [1.0], dtype=np.float64)
+        self._mc3 = (int(n_global), int(chains_per_group))
+        self._check(self._L.mcd_mc3_configure(self.h, int(n_global), int(chain_offset), int(chains_per_group), _dp(lp), _dp(ll)))
+
+    def mc3_swap(self, pair: int = -1, seed: int = 0, iteration: int = 0, d_stats_global: int = 0, want_accepted: bool = True):
+        """one swap attempt per group between the slots (pair, pair + 1) -> accepted flag per group"""
+        n_global, Cg = self._mc3
+        acc = np.empty(n_global // Cg, np.int32) if want_accepted else None
+        self._check(self._L.mcd_mc3_swap(self.h, int(pair), int(seed), int(iteration), d_stats_global or None,
+                                         _ip(acc) if acc is not None else None))
+        return acc
+
+    def mc3_slots(self):
+        sl = np.empty(self._mc3[0], np.int32)
+        self._check(self._L.mcd_mc3_slots(self.h, _ip(sl)))
+        return sl
+
+    def chains_out_device(self) -> int:
+        return int(self._L.mcd_chains_out_device(self.h) or 0)
 
     def nuts_ptr(self, B: int, theta0: int, base: int, inv_mass: int, eps: int, momentum0: int, max_depth: int, seed: int,
                  iteration: int, theta_out: int, out: int, accept_stat: int, info: int, status: int):

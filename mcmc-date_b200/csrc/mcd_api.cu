@@ -35,6 +35,7 @@ namespace {
 
 std::string g_create_error;
 constexpr int N_STREAMS = 4;
+constexpr int MH_MAX_CYCLE = 4096;        // proposals per mcd_mh_cycle call
 constexpr int SMALL_TREE_MAX_NODES = 96;  // warp-per-chain kernels up to this many nodes
 #ifndef POST_MINB
 #define POST_MINB 4
@@ -71,9 +72,13 @@ struct mcd_handle {
   DevBuf d_theta, d_gtheta, d_base, d_tidx, d_sidx;  // theta-packed API
   DevBuf d_mom, d_eps, d_invmass, d_energy, d_status_acc;  // device-resident leapfrog trajectories
   // chains resident in HBM for Metropolis-Hastings moves (mh_kernels.cuh)
-  DevBuf d_chain, d_chain_out, d_chain_status, d_new_out, d_new_status, d_undo, d_meta, d_lq, d_accepted;
+  DevBuf d_chain, d_chain_out, d_chain_status, d_new_out, d_new_status, d_undo, d_rng, d_meta, d_lq, d_accepted, d_counters;
   DevBuf d_mh_child1, d_mh_size, d_mh_inner_cnt, d_mh_inner_list;
-  int n_resident = 0, chain_cap = 0, n_inner_nonroot = 0;
+  int n_resident = 0, chain_cap = 0, n_inner_nonroot = 0, undo_stride = 0;
+  std::vector<int32_t> br_off_h, br_node_h;  // host copies of the brace table (argument checks of the brace proposals)
+  // heated chains (MC3 / stepping stone): temperature ladders, slot of every chain of every rank, inverse table
+  DevBuf d_slot, d_chain_of_slot, d_ladder_p, d_ladder_l, d_swap_acc;
+  int mc3_C = 0, mc3_n_global = 0, mc3_offset = 0;
   DevBuf d_nuts;                  // batched NUTS: trajectory ends, checkpoints, candidates, per-chain scalars
   size_t nuts_bytes = 0;
   int* nuts_flags = nullptr;      // pinned: active-chain counts of the last two ticks
@@ -656,7 +661,7 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
   return 0;
 }
 
-// ---- chains resident in HBM + Metropolis-Hastings steps (mh_kernels.cuh)
+// ---- chains resident in HBM + Metropolis-Hastings steps, heated chains, MC3 swaps (mh_kernels.cuh)
 int mh_prepare_value_path(mcd_handle* h, int n) {
   if (ensure_capacity(h, n, false, false)) return -1;
   if (h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && (ensure_cholesky(h, nullptr) || ensure_i8(h))) return -1;
@@ -669,10 +674,11 @@ int chains_set(mcd_handle* h, int n, const double* states) {
   CU_TRY(h, cudaSetDevice(h->device));
   if (mh_prepare_value_path(h, n)) return -1;
   const int S = h->S, N = h->N;
+  h->undo_stride = S + MH_MAX_OPS;
   if (n > h->chain_cap) {
     CU_TRY(h, cudaDeviceSynchronize());
     for (DevBuf* b : {&h->d_chain, &h->d_chain_out, &h->d_chain_status, &h->d_new_out, &h->d_new_status, &h->d_undo, &h->d_meta,
-                      &h->d_lq, &h->d_accepted}) {
+                      &h->d_lq, &h->d_accepted, &h->d_rng}) {
       if (b->p) cudaFree(b->p);
       b->p = nullptr;
     }
@@ -682,7 +688,8 @@ int chains_set(mcd_handle* h, int n, const double* states) {
     CU_TRY(h, cudaMalloc(&h->d_new_out.p, (size_t)cap * 8 * 8));
     CU_TRY(h, cudaMalloc(&h->d_chain_status.p, (size_t)cap * 4));
     CU_TRY(h, cudaMalloc(&h->d_new_status.p, (size_t)cap * 4));
-    CU_TRY(h, cudaMalloc(&h->d_undo.p, (size_t)cap * N * 8));
+    CU_TRY(h, cudaMalloc(&h->d_undo.p, (size_t)cap * h->undo_stride * 8));
+    CU_TRY(h, cudaMalloc(&h->d_rng.p, (size_t)cap * MH_MAX_OPS * sizeof(int2)));
     CU_TRY(h, cudaMalloc(&h->d_meta.p, (size_t)cap * sizeof(int4)));
     CU_TRY(h, cudaMalloc(&h->d_lq.p, (size_t)cap * 8));
     CU_TRY(h, cudaMalloc(&h->d_accepted.p, (size_t)cap * 4));
@@ -705,6 +712,7 @@ int chains_set(mcd_handle* h, int n, const double* states) {
     if (upload(h, h->d_mh_child1, h->child1.data(), N) || upload(h, h->d_mh_size, size.data(), N) ||
         upload(h, h->d_mh_inner_cnt, inner.data(), N) || upload(h, h->d_mh_inner_list, list.data(), list.size()))
       return -1;
+    CU_TRY(h, cudaMalloc(&h->d_counters.p, (size_t)2 * MH_MAX_CYCLE * sizeof(unsigned long long)));
   }
   cudaStream_t st = h->streams[0];
   CU_TRY(h, cudaMemcpyAsync(h->d_chain.p, states, (size_t)n * S * 8, cudaMemcpyHostToDevice, st));
@@ -726,35 +734,179 @@ int chains_get(mcd_handle* h, int n, double* states, double* out, int32_t* statu
   CU_TRY(h, cudaStreamSynchronize(st));
   return 0;
 }
-int mh_step(mcd_handle* h, int kind, int node, double sd, double tune, int use_root_jacobian, uint64_t seed, uint32_t iteration,
+// argument checks of one proposal: what the reference's proposal constructors reject with `error`
+int mh_check(mcd_handle* h, int kind, int node, double param, double tune) {
+  const int N = h->N;
+  if (kind < 0 || kind >= MH_N_KINDS) return fail(h, "mcd_mh: unknown proposal kind");
+  if (!(param > 0.0) || !(tune > 0.0)) return fail(h, "mcd_mh: the standard deviation / shape and the tuning parameter must be positive");
+  auto inner_nonroot = [&](int i) { return i > 0 && i < N && h->child1[i] >= 0; };
+  switch (kind) {
+    case MH_SLIDE_NODE: case MH_SCALE_SUBTREE: case MH_SCALE_RATE_SUBTREE: case MH_SLIDE_NODE_CONTRA: case MH_SCALE_SUBTREE_CONTRA:
+      if (h->n_inner_nonroot == 0) return fail(h, "mcd_mh: the tree has no inner node below the root");
+      if (node >= 0 && !inner_nonroot(node))
+        return fail(h, "mcd_mh: the node must be an inner node below the root (slideNodeAtUltrametric: path leads to a leaf)");
+      break;
+    case MH_SCALE_BRANCH:
+      if (node == 0 || node >= N) return fail(h, "mcd_mh: scaleBranch needs a node below the root");
+      break;
+    case MH_PULLEY:
+      if (h->child1[1] < 0 || h->child1[h->child1[0]] < 0) return fail(h, "pulleyUltrametric: a sub tree of the root is a leaf");
+      break;
+    case MH_SLIDE_BRACE: case MH_SLIDE_BRACE_CONTRA: {
+      const int nb = (int)h->br_off_h.size() - 1;
+      if (nb <= 0) return fail(h, "mcd_mh: the model has no braces");
+      if (node >= nb) return fail(h, "mcd_mh: brace index out of range");
+      for (int b = (node < 0 ? 0 : node); b < (node < 0 ? nb : node + 1); ++b) {
+        if (h->br_off_h[b + 1] - h->br_off_h[b] > MH_MAX_BRACE_NODES) return fail(h, "mcd_mh: braces of more than 16 nodes are not supported");
+        for (int o = h->br_off_h[b]; o < h->br_off_h[b + 1]; ++o)
+          if (!inner_nonroot(h->br_node_h[o])) return fail(h, "slideBracedNodesUltrametric: braced root node or leaf");
+      }
+    } break;
+    case MH_SCALE_SCALAR:
+      if (node < 0 || node > 4) return fail(h, "mcd_mh: scalar index must be 0 (lambda), 1 (mu), 2 (H), 3 (m) or 4 (v)");
+      break;
+    case MH_SCALE_RATES_TREE_CONTRA:
+      if (h->n_inner_nonroot < 1) return fail(h, "scaleRatesAndTreeContrarilyPFunction: no internal nodes to scale");
+      break;
+    default: break;
+  }
+  return 0;
+}
+MhTopo mh_topo(mcd_handle* h) {
+  MhTopo T;
+  T.N = h->N; T.S = h->S; T.n_inner_nonroot = h->n_inner_nonroot; T.root_r = h->dm.root_r; T.n_brace = h->dm.n_brace;
+  T.parent = h->dm.parent; T.child1 = h->d_mh_child1.as<int>(); T.sub_size = h->d_mh_size.as<int>();
+  T.sub_inner = h->d_mh_inner_cnt.as<int>(); T.inner_list = h->d_mh_inner_list.as<int>();
+  T.br_off = h->dm.br_off; T.br_node = h->dm.br_node;
+  return T;
+}
+// enqueue propose -> value-only evaluation -> accept on stream 0 (no synchronisation)
+int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int use_root_jacobian, uint64_t seed,
+               uint32_t iteration, unsigned long long* d_counters) {
+  const int n = h->n_resident, S = h->S;
+  cudaStream_t st = h->streams[0];
+  MhParams P;
+  P.kind = kind; P.node = node; P.use_root_jacobian = use_root_jacobian; P.pad = 0; P.param = param; P.tune = tune;
+  P.seed = seed; P.iteration = iteration;
+  mh_propose_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
+                                       h->d_lq.as<double>(), mh_topo(h), P, h->undo_stride, n);
+  if (enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st))
+    return -1;
+  const bool heated = h->mc3_C > 0;
+  mh_accept_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
+                                      h->d_lq.as<double>(), h->d_chain_out.as<double>(), h->d_new_out.as<double>(),
+                                      h->d_chain_status.as<int32_t>(), h->d_new_status.as<int32_t>(), h->d_accepted.as<int32_t>(),
+                                      d_counters, heated ? h->d_slot.as<int>() : nullptr, h->d_ladder_p.as<double>(),
+                                      h->d_ladder_l.as<double>(), h->mc3_offset, use_root_jacobian, seed, iteration, S,
+                                      h->undo_stride, n);
+  h->launches += 2;
+  CU_TRY(h, cudaGetLastError());
+  return 0;
+}
+int mh_step(mcd_handle* h, int kind, int node, double param, double tune, int use_root_jacobian, uint64_t seed, uint32_t iteration,
             int32_t* accepted) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
-  const int n = h->n_resident, N = h->N, S = h->S;
+  const int n = h->n_resident;
   if (n <= 0) return fail(h, "mcd_mh_step: no resident chains (call mcd_chains_set first)");
-  if (kind != MH_SLIDE_NODE && kind != MH_SCALE_SUBTREE) return fail(h, "mcd_mh_step: unknown proposal kind");
-  if (h->n_inner_nonroot == 0) return fail(h, "mcd_mh_step: the tree has no inner node below the root");
-  if (node >= 0 && (node == 0 || node >= N || h->child1[node] < 0))
-    return fail(h, "mcd_mh_step: the node must be an inner node below the root (slideNodeAtUltrametric: path leads to a leaf)");
+  if (mh_check(h, kind, node, param, tune)) return -1;
   CU_TRY(h, cudaSetDevice(h->device));
   if (mh_prepare_value_path(h, n)) return -1;
-  cudaStream_t st = h->streams[0];
-  mh_propose_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_meta.as<int4>(), h->d_lq.as<double>(),
-                                       h->dm.parent, h->d_mh_child1.as<int>(), h->d_mh_size.as<int>(), h->d_mh_inner_cnt.as<int>(),
-                                       h->d_mh_inner_list.as<int>(), h->n_inner_nonroot, kind, node, sd * tune, seed, iteration, S,
-                                       N, n);
-  if (enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st))
-    return -1;
-  mh_accept_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_meta.as<int4>(), h->d_lq.as<double>(),
-                                      h->d_chain_out.as<double>(), h->d_new_out.as<double>(), h->d_chain_status.as<int32_t>(),
-                                      h->d_new_status.as<int32_t>(), h->d_accepted.as<int32_t>(), use_root_jacobian, seed,
-                                      iteration, S, N, n);
-  h->launches += 2;
-  CU_TRY(h, cudaGetLastError());
+  if (mh_enqueue(h, kind, node, param, tune, use_root_jacobian, seed, iteration, nullptr)) return -1;
   if (accepted) {
+    cudaStream_t st = h->streams[0];
     CU_TRY(h, cudaMemcpyAsync(accepted, h->d_accepted.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaStreamSynchronize(st));
   }
+  return 0;
+}
+// n_iterations sweeps over a list of proposals, everything enqueued back to back (no host round trip per proposal);
+// the acceptance / invalid counts per proposal come back once at the end (what the reference's auto tuner consumes).
+int mh_cycle(mcd_handle* h, int n_props, const mcd_mh_proposal* props, int n_iterations, uint64_t seed, uint32_t iteration0,
+             uint64_t* accepted, uint64_t* invalid, uint32_t* iteration_next) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  const int n = h->n_resident;
+  if (n <= 0) return fail(h, "mcd_mh_cycle: no resident chains (call mcd_chains_set first)");
+  if (n_props <= 0 || n_props > MH_MAX_CYCLE || !props || n_iterations < 0) return fail(h, "mcd_mh_cycle: bad proposal list");
+  for (int p = 0; p < n_props; ++p)
+    if (props[p].repeat < 0 || mh_check(h, props[p].kind, props[p].node, props[p].param, props[p].tune)) return -1;
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (mh_prepare_value_path(h, n)) return -1;
+  cudaStream_t st = h->streams[0];
+  unsigned long long* cnt = h->d_counters.as<unsigned long long>();
+  CU_TRY(h, cudaMemsetAsync(cnt, 0, (size_t)2 * n_props * sizeof(unsigned long long), st));
+  uint32_t it = iteration0;
+  for (int sweep = 0; sweep < n_iterations; ++sweep)
+    for (int p = 0; p < n_props; ++p)
+      for (int r = 0; r < props[p].repeat; ++r)
+        if (mh_enqueue(h, props[p].kind, props[p].node, props[p].param, props[p].tune, props[p].use_root_jacobian, seed, it++,
+                       cnt + 2 * p))
+          return -1;
+  std::vector<unsigned long long> host((size_t)2 * n_props);
+  CU_TRY(h, cudaMemcpyAsync(host.data(), cnt, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  for (int p = 0; p < n_props; ++p) {
+    if (accepted) accepted[p] = host[2 * p];
+    if (invalid) invalid[p] = host[2 * p + 1];
+  }
+  if (iteration_next) *iteration_next = it;
+  return 0;
+}
+// temperature ladders + slot tables of the heated chains (replicated on every rank: n_global chains in groups of C)
+int mc3_configure(mcd_handle* h, int n_global, int chain_offset, int C, const double* ladder_prior, const double* ladder_lik) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (C == 0) {  // back to cold chains
+    h->mc3_C = 0;
+    return 0;
+  }
+  if (C < 0 || n_global <= 0 || n_global % C != 0 || chain_offset < 0 || chain_offset > n_global || !ladder_prior || !ladder_lik)
+    return fail(h, "mcd_mc3_configure: n_global must be a positive multiple of chains_per_group, ladders must be given");
+  CU_TRY(h, cudaDeviceSynchronize());
+  for (DevBuf* b : {&h->d_slot, &h->d_chain_of_slot, &h->d_ladder_p, &h->d_ladder_l, &h->d_swap_acc}) {
+    if (b->p) cudaFree(b->p);
+    b->p = nullptr;
+  }
+  std::vector<int> slot(n_global), cos(n_global);
+  for (int c = 0; c < n_global; ++c) { slot[c] = c % C; cos[c] = c; }
+  if (upload(h, h->d_slot, slot.data(), n_global) || upload(h, h->d_chain_of_slot, cos.data(), n_global) ||
+      upload(h, h->d_ladder_p, ladder_prior, C) || upload(h, h->d_ladder_l, ladder_lik, C) ||
+      upload(h, h->d_swap_acc, (const int*)nullptr, n_global / C))
+    return -1;
+  h->mc3_C = C; h->mc3_n_global = n_global; h->mc3_offset = chain_offset;
+  return 0;
+}
+int mc3_swap(mcd_handle* h, int pair, uint64_t seed, uint32_t iteration, const double* d_stats_global, int32_t* accepted) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (h->mc3_C < 2) return fail(h, "mcd_mc3_swap: configure at least two temperatures first (mcd_mc3_configure)");
+  if (pair >= h->mc3_C - 1) return fail(h, "mcd_mc3_swap: pair index out of range");
+  if (!d_stats_global && (h->mc3_offset != 0 || h->mc3_n_global != h->n_resident))
+    return fail(h, "mcd_mc3_swap: groups span ranks -- pass the all-gathered (ln prior, ln likelihood) table");
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->streams[0];
+  const int G = h->mc3_n_global / h->mc3_C;
+  const double* stats = d_stats_global ? d_stats_global : h->d_chain_out.as<double>() + MCD_OUT_LNPRIOR;
+  mh_swap_kernel<<<(G + 127) / 128, 128, 0, st>>>(stats, d_stats_global ? 2 : MCD_OUT_COLS, h->d_slot.as<int>(),
+                                                  h->d_chain_of_slot.as<int>(), h->d_ladder_p.as<double>(), h->d_ladder_l.as<double>(),
+                                                  G, h->mc3_C, pair, seed, iteration, h->d_swap_acc.as<int>());
+  h->launches += 1;
+  CU_TRY(h, cudaGetLastError());
+  if (accepted) {
+    CU_TRY(h, cudaMemcpyAsync(accepted, h->d_swap_acc.p, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+int mc3_slots(mcd_handle* h, int32_t* slots) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (h->mc3_C <= 0 || !slots) return fail(h, "mcd_mc3_slots: no temperature ladder configured");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaMemcpyAsync(slots, h->d_slot.p, (size_t)h->mc3_n_global * 4, cudaMemcpyDeviceToHost, h->streams[0]));
+  CU_TRY(h, cudaStreamSynchronize(h->streams[0]));
   return 0;
 }
 
@@ -963,6 +1115,11 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   }
   inc_off[N] = (int)inc_ent.size();
   const int nbn = d->n_brace > 0 ? d->brace_off[d->n_brace] : 0;
+  h->br_off_h.assign(1, 0);
+  if (d->n_brace > 0) {
+    h->br_off_h.assign(d->brace_off, d->brace_off + d->n_brace + 1);
+    h->br_node_h.assign(d->brace_node, d->brace_node + nbn);
+  }
   std::vector<int> br_off0(1, 0);
   if (upload(h, h->d_cal_node, d->cal_node, d->n_cal) || upload(h, h->d_cal_lo, d->cal_lo, d->n_cal) ||
       upload(h, h->d_cal_hi, d->cal_hi, d->n_cal) || upload(h, h->d_cal_slo, slo.data(), d->n_cal) ||
@@ -1086,6 +1243,19 @@ int mcd_chains_set(mcd_handle* h, int32_t n, const double* states) { return chai
 int mcd_chains_get(mcd_handle* h, int32_t n, double* states, double* out, int32_t* status) {
   return chains_get(h, n, states, out, status);
 }
+int mcd_mh_cycle(mcd_handle* h, int32_t n_props, const mcd_mh_proposal* props, int32_t n_iterations, uint64_t seed,
+                 uint32_t iteration0, uint64_t* accepted, uint64_t* invalid, uint32_t* iteration_next) {
+  return mh_cycle(h, n_props, props, n_iterations, seed, iteration0, accepted, invalid, iteration_next);
+}
+int mcd_mc3_configure(mcd_handle* h, int32_t n_global, int32_t chain_offset, int32_t chains_per_group, const double* ladder_prior,
+                      const double* ladder_lik) {
+  return mc3_configure(h, n_global, chain_offset, chains_per_group, ladder_prior, ladder_lik);
+}
+int mcd_mc3_swap(mcd_handle* h, int32_t pair, uint64_t seed, uint32_t iteration, const double* d_stats_global, int32_t* accepted) {
+  return mc3_swap(h, pair, seed, iteration, d_stats_global, accepted);
+}
+int mcd_mc3_slots(mcd_handle* h, int32_t* slots) { return mc3_slots(h, slots); }
+void* mcd_chains_out_device(mcd_handle* h) { return h ? h->d_chain_out.p : nullptr; }
 int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double sd, double tune, int32_t use_root_jacobian, uint64_t seed,
                 uint32_t iteration, int32_t* accepted) {
   return mh_step(h, kind, node, sd, tune, use_root_jacobian, seed, iteration, accepted);

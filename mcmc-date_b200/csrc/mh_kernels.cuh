@@ -1,20 +1,38 @@
-// mh_kernels.cuh -- Metropolis-Hastings proposals on chains that live in HBM (first part).
+// mh_kernels.cuh -- Metropolis-Hastings-Green proposals, heated chains and MC3 swaps on chains that live in HBM
+// (SURVEY.md 8f rank 4).
 //
-// The reference's default sampler cycles through thousands of single-node proposals per iteration
-// (app/Definitions.hs:145-278), each followed by a full prior + likelihood evaluation.  Here the chains' states
-// stay resident on the device: one call applies one proposal to every chain (in place, with an undo log), the
-// batched value-only evaluation scores the proposed states, and an accept kernel keeps or restores them.
+// The reference's default sampler cycles through thousands of small proposals per iteration
+// (app/Definitions.hs:145-278), each followed by a full prior + likelihood evaluation.  Here the chains' states stay
+// resident on the device: one call applies one proposal to every chain (in place, with an undo log), the batched
+// value-only evaluation scores the proposed states, and an accept kernel keeps or restores them.
 //
-// Proposals restated (all first-party code of the reference, no third-party sampling involved):
-//   MH_SLIDE_NODE      slideNodeAtUltrametric      lib/Mcmc/Tree/Proposal/Ultrametric.hs:50-62
-//                      h' ~ truncated normal(mean h, sd t*s) on (max child height, parent height); |J| = 1
-//   MH_SCALE_SUBTREE   scaleSubTreeAtUltrametric   lib/Mcmc/Tree/Proposal/Ultrametric.hs:126-147
-//                      h' ~ truncated normal(mean h, sd t*s) on (0, parent height); every height of the sub tree is
-//                      scaled by xi = h'/h; |J| = xi^(n_inner - 1)
-// with truncatedNormalSample / the truncated normal of lib/Mcmc/Tree/Proposal/Internal.hs:100-137 and
-// lib/Statistics/Distribution/TruncatedNormal.hs:61-131:
+// Every proposal of the reference's cycle is restated (first-party code of the reference unless noted):
+//   kind                         reference                                                              state touched
+//   MH_SLIDE_NODE                slideNodeAtUltrametric          Proposal/Ultrametric.hs:50-62          h_j
+//   MH_SCALE_SUBTREE             scaleSubTreeAtUltrametric       Proposal/Ultrametric.hs:126-147        heights of sub tree j
+//   MH_PULLEY                    pulleyUltrametric               Proposal/Ultrametric.hs:219-316        all heights below the root
+//   MH_SLIDE_BRACE               slideBracedNodesUltrametric     Proposal/Brace.hs:30-51                heights of the braced nodes
+//   MH_SCALE_BRANCH              scaleBranch (rate tree)         Proposal/Unconstrained.hs:52-66        r_i
+//   MH_SCALE_RATE_SUBTREE        scaleTree on a sub tree         Proposal/Unconstrained.hs:105-139      rates of sub tree j (with stem)
+//   MH_SCALE_NORM_TREE_CONTRA_M  scaleNormAndTreeContrarily      Proposal/Unconstrained.hs:260-306      m, all rates
+//   MH_SCALE_NORM_TREE_CONTRA_H  (same, on timeHeight)           app/Definitions.hs:249-260             H, all rates
+//   MH_SCALE_VAR_TREE            scaleVarianceAndTree            Proposal/Unconstrained.hs:308-371      v, all rates
+//   MH_SCALE_VAR_TREE_AUTO       scaleVarianceAndTreeAutocorr.   Proposal/Unconstrained.hs:380-439      v, all rates
+//   MH_SLIDE_NODE_CONTRA         slideNodesAtContrarily          Proposal/Contrary.hs:60-131            h_j, r_j, rates of the children
+//   MH_SCALE_SUBTREE_CONTRA      scaleSubTreesAtContrarily       Proposal/Contrary.hs:283-377           heights + rates of sub tree j
+//   MH_SLIDE_BRACE_CONTRA        slideBracedNodesContrarily      Proposal/Brace.hs:88-143               braced heights + adjacent rates
+//   MH_SLIDE_ROOT_CONTRA         slideRootContrarily             Proposal/Contrary.hs:172-246           H, all heights, root-child rates
+//   MH_SCALE_RATES_TREE_CONTRA   scaleRatesAndTreeContrarily     Proposal/Contrary.hs:425-486           lambda, mu, all heights
+//   MH_SCALE_SCALAR              scaleUnbiased (`mcmc` package)  app/Definitions.hs:262-266             one of lambda, mu, H, m, v
+//   MH_SCALE_H_M_CONTRA          scaleContrarily (`mcmc`)        app/Definitions.hs:251                 H, m
+// Truncated-normal moves use truncatedNormalSample (Proposal/Internal.hs:100-137) on the reference's own truncated normal
+// (lib/Statistics/Distribution/TruncatedNormal.hs:61-131):
 //   z(m) = Phi((b-m)/s') - Phi((a-m)/s'),  quantile(p) = erfinv(2 (p z + Phi(alpha)) - 1) sqrt(2) s' + m,
-//   Hastings factor q = density_{h'}(h) / density_{h}(h') = z(h) / z(h').
+//   Hastings factor q = density_{x'}(x) / density_{x}(x') = z(x) / z(x').
+// Multiplier moves draw u ~ Gamma(shape k/t, scale t/k) (mean 1) and use `genericContinuous` of the un-vendored `mcmc`
+// package (rev 542c43f6, restated from its published source): q = pdf(1/u) / pdf(u), Jacobian as given by the caller.
+// The acceptance ratio is the package's mhgRatio: r = [prior(y) lik(y)]^beta / [prior(x) lik(x)]^beta . q . |J| (. the
+// ratio of jacobianRootBranch for proposals lifted with it); accept iff ln U < ln r.
 // Uniform random numbers: Philox4x32-10 (hmc_kernels.cuh), counter (chain, iteration, draw, 2).
 #pragma once
 #include <cuda_runtime.h>
@@ -25,123 +43,414 @@
 
 namespace mcd {
 
-enum { MH_SLIDE_NODE = 0, MH_SCALE_SUBTREE = 1 };
-enum { MH_ST_OK = 0, MH_ST_INVALID = 1 };  // invalid: the reference's truncatedNormalDistr would call `error`
+enum {
+  MH_SLIDE_NODE = 0, MH_SCALE_SUBTREE = 1, MH_PULLEY = 2, MH_SLIDE_BRACE = 3, MH_SCALE_BRANCH = 4, MH_SCALE_RATE_SUBTREE = 5,
+  MH_SCALE_NORM_TREE_CONTRA_M = 6, MH_SCALE_NORM_TREE_CONTRA_H = 7, MH_SCALE_VAR_TREE = 8, MH_SCALE_VAR_TREE_AUTO = 9,
+  MH_SLIDE_NODE_CONTRA = 10, MH_SCALE_SUBTREE_CONTRA = 11, MH_SLIDE_BRACE_CONTRA = 12, MH_SLIDE_ROOT_CONTRA = 13,
+  MH_SCALE_RATES_TREE_CONTRA = 14, MH_SCALE_SCALAR = 15, MH_SCALE_H_M_CONTRA = 16, MH_N_KINDS = 17
+};
+enum { MH_ST_OK = 0, MH_ST_INVALID = 1 };  // invalid: the reference would call `error` (bounds crossed, bad parameters)
+enum { MH_MAX_BRACE_NODES = 16, MH_MAX_OPS = 4 * MH_MAX_BRACE_NODES + 8 };
+enum { OP_SET = 0, OP_MUL = 1, OP_DIV = 2, OP_ADD = 3, OP_AFFINE_POS = 4 };
 
-__device__ __forceinline__ double mh_uniform(uint64_t seed, uint32_t chain, uint32_t iteration, uint32_t draw) {
+struct MhOp {
+  int off, cnt, mode, pad;
+  double a, b;
+};
+struct MhTopo {
+  int N, S, n_inner_nonroot, root_r, n_brace;
+  const int* parent;      // leaf flag in bit 31
+  const int* child1;      // second child (the first child of an inner node i is i + 1), -1 on leaves
+  const int* sub_size;    // nodes of the sub tree (= its branch labels, `length`)
+  const int* sub_inner;   // nInnerNodes of the sub tree
+  const int* inner_list;  // inner nodes below the root, ascending
+  const int *br_off, *br_node;
+};
+struct MhParams {
+  int kind, node, use_root_jacobian, pad;
+  double param, tune;  // standard deviation (truncated-normal moves) or shape k (multiplier moves); tuning parameter
+  uint64_t seed;
+  uint32_t iteration;
+};
+
+__device__ __forceinline__ void mh_uniform2(uint64_t seed, uint32_t chain, uint32_t iteration, uint32_t draw, double* u0, double* u1) {
   uint32_t c[4] = {chain, iteration, draw, 2u};
   Philox{(uint32_t)seed, (uint32_t)(seed >> 32)}(c);
-  const uint64_t k = ((uint64_t)(c[0] >> 5) << 26) | (uint64_t)(c[1] >> 6);
-  return ((double)k + 0.5) * 1.1102230246251565e-16;
+  *u0 = ((double)(((uint64_t)(c[0] >> 5) << 26) | (uint64_t)(c[1] >> 6)) + 0.5) * 1.1102230246251565e-16;
+  *u1 = ((double)(((uint64_t)(c[2] >> 5) << 26) | (uint64_t)(c[3] >> 6)) + 0.5) * 1.1102230246251565e-16;
+}
+__device__ __forceinline__ double mh_uniform(uint64_t seed, uint32_t chain, uint32_t iteration, uint32_t draw) {
+  double u0, u1;
+  mh_uniform2(seed, chain, iteration, draw, &u0, &u1);
+  return u0;
 }
 __device__ __forceinline__ double mh_phi2(double x) { return 0.5 * (1.0 + erf(x * 0.70710678118654752440)); }
 
-// Apply the proposal to node `node` (same node for all chains; node < 0: every chain draws its own inner non-root
-// node uniformly) of every chain IN PLACE.  One CTA per chain.  undo[b][0..] keeps the old heights of the modified
-// range, meta[b] = (first modified node, number of modified nodes, validity, -), lq[b] = ln(q |J|).
-__global__ void __launch_bounds__(256)
-mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int4* __restrict__ meta, double* __restrict__ lq,
-                  const int* __restrict__ parent /*leaf bit 31*/, const int* __restrict__ child1, const int* __restrict__ sub_size,
-                  const int* __restrict__ sub_inner, const int* __restrict__ inner_list, int n_inner_nonroot, int kind, int node,
-                  double sd_tuned, uint64_t seed, uint32_t iteration, int S, int N, int B) {
-  __shared__ double sh_xi;
-  __shared__ int sh_j, sh_cnt;
-  const int b = blockIdx.x;
-  if (b >= B) return;
-  double* h = states + (size_t)b * S + 3;
-  if (threadIdx.x == 0) {
-    int j = node;
-    if (j < 0) {
-      const double un = mh_uniform(seed, (uint32_t)b, iteration, 2u);
-      int pick = (int)(un * (double)n_inner_nonroot);
-      if (pick >= n_inner_nonroot) pick = n_inner_nonroot - 1;
-      j = inner_list[pick];
-    }
-    const double hj = h[j], hP = h[parent[j] & 0x7fffffff];
-    double a, bb;
-    if (kind == MH_SLIDE_NODE) {
-      a = fmax(h[j + 1], h[child1[j]]);  // hbdMaximumChildrenHeight
-      bb = hP;
-    } else {
-      a = 0.0;
-      bb = hP;
-    }
-    const double s = sd_tuned;
-    // truncatedNormalDistr's error conditions (TruncatedNormal.hs:61-79); NaNs fail the comparisons too
-    const bool ok = (s > 0.0) && (a < bb) && !(a > hj) && !(bb < hj) && (hj == hj);
-    double xi = 1.0, lnq = 0.0, hnew = hj;
-    int cnt = 0;
-    if (ok) {
-      const double p = mh_uniform(seed, (uint32_t)b, iteration, 0u);
-      const double phiA = mh_phi2((a - hj) / s), z = mh_phi2((bb - hj) / s) - phiA;
-      hnew = erfinv(2.0 * (p * z + phiA) - 1.0) * 1.41421356237309504880 * s + hj;
-      // truncatedNormalSample: a sample outside [a, b] is a numerical failure (`error` in the reference)
-      if (!(a > hnew || bb < hnew) && hnew == hnew && z > 0.0) {
-        const double z2 = mh_phi2((bb - hnew) / s) - mh_phi2((a - hnew) / s);
-        lnq = log(z) - log(z2);  // q = qYX / qXY = z(h) / z(h')
-        if (kind == MH_SCALE_SUBTREE) {
-          xi = hnew / hj;
-          lnq += (double)(sub_inner[j] - 1) * log(xi);
-          cnt = sub_size[j];
-        } else {
-          cnt = 1;
-        }
-      }
-    }
-    sh_xi = xi;
-    sh_j = j;
-    sh_cnt = cnt;
-    meta[b] = make_int4(j, cnt, cnt > 0 ? MH_ST_OK : MH_ST_INVALID, 0);
-    lq[b] = lnq;
-    if (cnt > 0) {
-      undo[(size_t)b * N] = hj;
-      h[j] = hnew;  // the sub tree's root gets the sampled height itself (scaleUltrametricTreeF)
+// truncatedNormalSample: value and ln(qYX / qXY); false where truncatedNormalDistr / the bounds check would `error`
+__device__ __forceinline__ bool mh_truncated_normal(double m, double s, double a, double b, double p, double* val, double* lnq) {
+  if (!(s > 0.0) || !(a < b) || (a > m) || (b < m) || !(m == m)) return false;
+  const double phiA = mh_phi2((a - m) / s), z = mh_phi2((b - m) / s) - phiA;
+  const double u = erfinv(2.0 * (p * z + phiA) - 1.0) * 1.41421356237309504880 * s + m;
+  if (a > u || b < u || !(u == u) || !(z > 0.0)) return false;
+  const double z2 = mh_phi2((b - u) / s) - mh_phi2((a - u) / s);
+  *val = u;
+  *lnq = log(z) - log(z2);
+  return true;
+}
+// u ~ Gamma(shape, scale): Marsaglia & Tsang (2000); attempt i uses draws 8 + 2 i (normal, Box-Muller on the two uniforms of
+// one Philox block) and 9 + 2 i (uniform); shape < 1 is boosted with draw 7.
+__device__ __forceinline__ bool mh_gamma(double shape, double scale, uint64_t seed, uint32_t chain, uint32_t iteration, double* out) {
+  if (!(shape > 0.0) || !(scale > 0.0)) return false;
+  double boost = 1.0, a = shape;
+  if (a < 1.0) {
+    boost = pow(mh_uniform(seed, chain, iteration, 7u), 1.0 / a);
+    a += 1.0;
+  }
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (uint32_t i = 0; i < 64u; ++i) {
+    double u0, u1;
+    mh_uniform2(seed, chain, iteration, 8u + 2u * i, &u0, &u1);
+    const double x = sqrt(-2.0 * log(u0)) * cospi(2.0 * u1);
+    const double t = 1.0 + c * x;
+    if (t <= 0.0) continue;
+    const double v = t * t * t;
+    const double uu = mh_uniform(seed, chain, iteration, 9u + 2u * i);
+    if (log(uu) < 0.5 * x * x + d - d * v + d * log(v)) {
+      *out = d * v * scale * boost;
+      return true;
     }
   }
-  __syncthreads();
-  const int j = sh_j, cnt = sh_cnt;
-  const double xi = sh_xi;
-  // scale the rest of the sub tree (pre-order: nodes j+1 .. j+cnt-1); leaves stay at 0 * xi = 0
-  for (int i = 1 + threadIdx.x; i < cnt; i += 256) {
-    const double old = h[j + i];
-    undo[(size_t)b * N + i] = old;
-    h[j + i] = old * xi;
-  }
+  return false;
 }
 
-// ln r = ln post(y) - ln post(x) + ln(q |J|); accept iff ln u < ln r.  post = prior * likelihood (* root-branch
-// Jacobian for proposals lifted with jacobianRootBranch, app/Definitions.hs:145-150).  Rejected chains get their
-// heights back from the undo log.  One CTA per chain.
+// Apply proposal P to every chain IN PLACE.  One CTA per chain: thread 0 draws and turns the move into a short list of
+// range operations on the state row, then all threads save the old values to the undo log and apply them.
+// undo[b][..]: old values, ranges packed in order; rng[b][o] = (offset, count); meta[b] = (ranges, validity, node, -);
+// lq[b] = ln(q |J|).
 __global__ void __launch_bounds__(256)
-mh_accept_kernel(double* __restrict__ states, const double* __restrict__ undo, const int4* __restrict__ meta,
-                 const double* __restrict__ lq, double* __restrict__ cur_out, const double* __restrict__ new_out,
-                 int* __restrict__ cur_status, const int* __restrict__ new_status, int* __restrict__ accepted,
-                 int use_root_jacobian, uint64_t seed, uint32_t iteration, int S, int N, int B) {
+mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* __restrict__ rng, int4* __restrict__ meta,
+                  double* __restrict__ lq, const MhTopo T, const MhParams P, int undo_stride, int B) {
+  __shared__ MhOp ops[MH_MAX_OPS];
+  __shared__ int sh_nops;
+  __shared__ double sh_warp[8], sh_sum;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (b >= B) return;
+  const int N = T.N, S = T.S;
+  double* row = states + (size_t)b * S;
+  const int OH = 3, OR = 5 + N, OM = 3 + N, OV = 4 + N;  // offsets: heights, rates, rate mean, rate variance
+  if (P.kind == MH_SCALE_VAR_TREE) {  // sample mean of the rates without the stem (scaleVarianceAndTreeF)
+    double s = 0.0;
+    for (int i = 1 + tid; i < N; i += 256) s += row[OR + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) sh_warp[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) sh_sum = ((sh_warp[0] + sh_warp[1]) + (sh_warp[2] + sh_warp[3])) + ((sh_warp[4] + sh_warp[5]) + (sh_warp[6] + sh_warp[7]));
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const double* h = row + OH;
+    int nops = 0, node = P.node;
+    bool ok = true;
+    double lnq = 0.0, lnj = 0.0;
+    auto push = [&](int off, int cnt, int mode, double a, double bb) {
+      if (cnt <= 0) return;
+      ops[nops].off = off; ops[nops].cnt = cnt; ops[nops].mode = mode; ops[nops].a = a; ops[nops].b = bb;
+      ++nops;
+    };
+    const double s = P.param * P.tune;  // sd' = t * s (Internal.hs:117)
+    const double p = mh_uniform(P.seed, (uint32_t)b, P.iteration, 0u);
+    const int kind = P.kind;
+    const bool node_kind = kind == MH_SLIDE_NODE || kind == MH_SCALE_SUBTREE || kind == MH_SCALE_RATE_SUBTREE ||
+                           kind == MH_SLIDE_NODE_CONTRA || kind == MH_SCALE_SUBTREE_CONTRA;
+    if (node < 0) {
+      const double un = mh_uniform(P.seed, (uint32_t)b, P.iteration, 2u);
+      if (node_kind) {
+        int pick = (int)(un * (double)T.n_inner_nonroot);
+        if (pick >= T.n_inner_nonroot) pick = T.n_inner_nonroot - 1;
+        node = T.inner_list[pick];
+      } else if (kind == MH_SCALE_BRANCH) {
+        int pick = (int)(un * (double)(N - 1));
+        if (pick >= N - 1) pick = N - 2;
+        node = 1 + pick;
+      } else if (kind == MH_SLIDE_BRACE || kind == MH_SLIDE_BRACE_CONTRA) {
+        int pick = (int)(un * (double)T.n_brace);
+        if (pick >= T.n_brace) pick = T.n_brace - 1;
+        node = pick;
+      }
+    }
+    const int j = node;
+    // multiplier u ~ Gamma(k / t, t / k) and its Hastings factor pdf(1/u) / pdf(u)  (genericContinuous)
+    double u = 1.0;
+    const bool mult_kind = kind == MH_SCALE_BRANCH || kind == MH_SCALE_RATE_SUBTREE || kind == MH_SCALE_NORM_TREE_CONTRA_M ||
+                           kind == MH_SCALE_NORM_TREE_CONTRA_H || kind == MH_SCALE_VAR_TREE || kind == MH_SCALE_VAR_TREE_AUTO ||
+                           kind == MH_SCALE_SCALAR || kind == MH_SCALE_H_M_CONTRA;
+    if (mult_kind) {
+      const double kk = P.param / P.tune, th = P.tune / P.param;
+      ok = mh_gamma(kk, th, P.seed, (uint32_t)b, P.iteration, &u);
+      if (ok) lnq = -2.0 * (kk - 1.0) * log(u) - (1.0 / u - u) / th;
+    }
+    if (ok) switch (kind) {
+      case MH_SLIDE_NODE:
+      case MH_SLIDE_NODE_CONTRA: {
+        const int c0 = j + 1, c1 = T.child1[j];
+        const double hj = h[j], hP = h[T.parent[j] & 0x7fffffff], h0 = h[c0], h1 = h[c1];
+        double hn;
+        ok = mh_truncated_normal(hj, s, fmax(h0, h1), hP, p, &hn, &lnq);  // hbdMaximumChildrenHeight .. hbdParentHeight
+        if (!ok) break;
+        push(OH + j, 1, OP_SET, 0.0, hn);
+        if (kind == MH_SLIDE_NODE_CONTRA) {  // rates scale inversely to their branches' lengths
+          const double xiS = (hP - hj) / (hP - hn), xi0 = (hj - h0) / (hn - h0), xi1 = (hj - h1) / (hn - h1);
+          push(OR + j, 1, OP_MUL, xiS, 0.0);
+          push(OR + c0, 1, OP_MUL, xi0, 0.0);
+          push(OR + c1, 1, OP_MUL, xi1, 0.0);
+          lnj = (log(xi0) + log(xi1)) + log(xiS);
+        }
+      } break;
+      case MH_SCALE_SUBTREE:
+      case MH_SCALE_SUBTREE_CONTRA: {
+        const double hj = h[j], hP = h[T.parent[j] & 0x7fffffff];
+        double hn;
+        ok = mh_truncated_normal(hj, s, 0.0, hP, p, &hn, &lnq);
+        if (!ok) break;
+        const double xi = hn / hj;
+        const int cnt = T.sub_size[j];
+        push(OH + j, 1, OP_SET, 0.0, hn);  // the sub tree's root gets the sampled height itself (scaleUltrametricTreeF)
+        push(OH + j + 1, cnt - 1, OP_MUL, xi, 0.0);
+        if (kind == MH_SCALE_SUBTREE) {
+          lnj = (double)(T.sub_inner[j] - 1) * log(xi);
+        } else {
+          const double xiR = 1.0 / xi, xiS = (hP - hj) / (hP - hn);
+          push(OR + j + 1, cnt - 1, OP_MUL, xiR, 0.0);
+          push(OR + j, 1, OP_MUL, xiS, 0.0);
+          lnj = (double)(T.sub_inner[j] - cnt) * log(xi) + log(xiS);
+        }
+      } break;
+      case MH_PULLEY: {
+        const int l = 1, r = T.root_r;
+        const double ht = h[0], hL = h[l], hR = h[r], brL = ht - hL, brR = ht - hR;
+        if (!(brL > 0.0) || !(brR > 0.0)) { ok = false; break; }
+        const double a = -fmin(brL, ht - brR), bb = fmin(brR, ht - brL);
+        double uu;
+        ok = mh_truncated_normal(0.0, s, a, bb, p, &uu, &lnq);
+        if (!ok) break;
+        const double hLn = hL - uu, hRn = hR + uu, xiL = hLn / hL, xiR = hRn / hR;
+        push(OH + l, 1, OP_SET, 0.0, hLn);
+        push(OH + l + 1, T.sub_size[l] - 1, OP_MUL, xiL, 0.0);
+        push(OH + r, 1, OP_SET, 0.0, hRn);
+        push(OH + r + 1, T.sub_size[r] - 1, OP_MUL, xiR, 0.0);
+        lnj = (double)(T.sub_inner[l] - 1) * log(xiL) + (double)(T.sub_inner[r] - 1) * log(xiR);
+      } break;
+      case MH_SLIDE_BRACE:
+      case MH_SLIDE_BRACE_CONTRA: {
+        const int o0 = T.br_off[j], o1 = T.br_off[j + 1];
+        double lo = -CUDART_INF, hi = CUDART_INF;
+        for (int o = o0; o < o1; ++o) {
+          const int x = T.br_node[o];
+          const double hx = h[x];
+          lo = fmax(lo, fmax(h[x + 1], h[T.child1[x]]) - hx);
+          hi = fmin(hi, h[T.parent[x] & 0x7fffffff] - hx);
+        }
+        double dl;
+        ok = mh_truncated_normal(0.0, s, lo, hi, p, &dl, &lnq);
+        if (!ok) break;
+        for (int o = o0; o < o1; ++o) push(OH + T.br_node[o], 1, OP_ADD, 0.0, dl);
+        if (kind == MH_SLIDE_BRACE_CONTRA) {
+          for (int o = o0; o < o1; ++o) {
+            const int x = T.br_node[o], c0 = x + 1, c1 = T.child1[x];
+            const double hx = h[x], hP = h[T.parent[x] & 0x7fffffff];
+            const double xiS = (hP - hx) / (hP - hx - dl), xi0 = (hx - h[c0]) / (hx + dl - h[c0]), xi1 = (hx - h[c1]) / (hx + dl - h[c1]);
+            push(OR + x, 1, OP_MUL, xiS, 0.0);
+            push(OR + c0, 1, OP_MUL, xi0, 0.0);
+            push(OR + c1, 1, OP_MUL, xi1, 0.0);
+            lnj += (log(xi0) + log(xi1)) + log(xiS);
+          }
+        }
+      } break;
+      case MH_SCALE_BRANCH:
+        push(OR + j, 1, OP_MUL, u, 0.0);
+        lnj = -log(u);  // scaleUnbiased: Jacobian 1 / u
+        break;
+      case MH_SCALE_RATE_SUBTREE:
+        push(OR + j, T.sub_size[j], OP_MUL, u, 0.0);  // stem included (scaleUnconstrainedTreeF)
+        lnj = (double)(T.sub_size[j] - 2) * log(u);
+        break;
+      case MH_SCALE_NORM_TREE_CONTRA_M:
+      case MH_SCALE_NORM_TREE_CONTRA_H:
+        push(kind == MH_SCALE_NORM_TREE_CONTRA_M ? OM : 2, 1, OP_DIV, u, 0.0);
+        push(OR + 1, N - 1, OP_MUL, u, 0.0);  // without the stem
+        lnj = (double)(N - 1 - 3) * log(u);
+        break;
+      case MH_SCALE_VAR_TREE: {
+        const double n = (double)(N - 1), n1 = 1.0 / n, mean = sh_sum / n;
+        push(OV, 1, OP_MUL, u * u, 0.0);
+        push(OR + 1, N - 1, OP_AFFINE_POS, u, mean);
+        lnj = n * log(u - n1 * u + n1);
+      } break;
+      case MH_SCALE_VAR_TREE_AUTO:
+        // r' = y_parent + u (r - r_parent) down the tree telescopes to m + u (r - m): closed form of scaleF
+        push(OV, 1, OP_MUL, u * u, 0.0);
+        push(OR + 1, N - 1, OP_AFFINE_POS, u, row[OM]);
+        lnj = (double)(N - 1) * log(u);
+        break;
+      case MH_SLIDE_ROOT_CONTRA: {
+        const int l = 1, r = T.root_r;
+        const double H = row[2], hL = h[l], hR = h[r];
+        if (fabs(h[0] - 1.0) > 1e-14) { ok = false; break; }
+        double Hn;
+        ok = mh_truncated_normal(H, s, H * fmax(hL, hR), CUDART_INF, p, &Hn, &lnq);
+        if (!ok) break;
+        const double uu = Hn / H, xiL = (1.0 - hL) / (uu - hL), xiR = (1.0 - hR) / (uu - hR);
+        push(2, 1, OP_SET, 0.0, Hn);
+        push(OH + 1, N - 1, OP_DIV, uu, 0.0);
+        push(OR + l, 1, OP_MUL, xiL, 0.0);
+        push(OR + r, 1, OP_MUL, xiR, 0.0);
+        lnj = -(double)T.sub_inner[0] * log(uu) + (log(xiL) + log(xiR));
+      } break;
+      case MH_SCALE_RATES_TREE_CONTRA: {
+        const int nn = T.sub_inner[0] - 1;
+        if (nn < 1) { ok = false; break; }
+        const double hc = fmax(h[1], h[T.root_r]);
+        double hn;
+        ok = mh_truncated_normal(hc, s, 0.0, h[0], p, &hn, &lnq);
+        if (!ok) break;
+        const double xi = hn / hc;
+        push(OH + 1, N - 1, OP_MUL, xi, 0.0);
+        push(0, 2, OP_DIV, xi, 0.0);  // lambda, mu
+        lnj = (double)(nn - 1 - 2) * log(xi);
+      } break;
+      case MH_SCALE_SCALAR: {
+        const int off = j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 2 : j == 3 ? OM : OV;
+        push(off, 1, OP_MUL, u, 0.0);
+        lnj = -log(u);
+      } break;
+      case MH_SCALE_H_M_CONTRA:
+        push(2, 1, OP_MUL, u, 0.0);
+        push(OM, 1, OP_DIV, u, 0.0);
+        lnj = -log(u * u);
+        break;
+      default: ok = false; break;
+    }
+    if (!ok) nops = 0;
+    sh_nops = nops;
+    meta[b] = make_int4(nops, ok ? MH_ST_OK : MH_ST_INVALID, node, 0);
+    lq[b] = ok ? lnq + lnj : 0.0;
+  }
+  __syncthreads();
+  const int nops = sh_nops;
+  double* ub = undo + (size_t)b * undo_stride;
+  int pos = 0;
+  for (int o = 0; o < nops; ++o) {
+    const MhOp op = ops[o];
+    for (int i = tid; i < op.cnt; i += 256) {
+      const double old = row[op.off + i];
+      ub[pos + i] = old;
+      double y;
+      switch (op.mode) {
+        case OP_SET: y = op.b; break;
+        case OP_MUL: y = old * op.a; break;
+        case OP_DIV: y = old / op.a; break;
+        case OP_ADD: y = old + op.b; break;
+        default: y = (old - op.b) * op.a + op.b; if (!(y > 0.0)) y = CUDART_NAN; break;  // "force NaN when the new value is negative"
+      }
+      row[op.off + i] = y;
+    }
+    pos += op.cnt;
+    __syncthreads();  // ranges may overlap (a braced node that is the child of another): strictly in order
+  }
+  if (tid < nops) rng[(size_t)b * MH_MAX_OPS + tid] = make_int2(ops[tid].off, ops[tid].cnt);
+}
+
+// ln r = beta_p (ln prior(y) - ln prior(x)) + beta_l (ln lik(y) - ln lik(x)) + ln(q |J|) (+ the change of the root-branch
+// Jacobian for proposals lifted with jacobianRootBranch, app/Definitions.hs:145-150); accept iff ln U < ln r.
+// beta: heat of the chain's current temperature slot (MC3: prior and likelihood; stepping stone: likelihood only);
+// slot == nullptr: cold chains.  Rejected chains get their values back from the undo log, ranges in reverse order.
+// counters[0] += accepted, counters[1] += invalid (nullable).  One CTA per chain.
+__global__ void __launch_bounds__(256)
+mh_accept_kernel(double* __restrict__ states, const double* __restrict__ undo, const int2* __restrict__ rng,
+                 const int4* __restrict__ meta, const double* __restrict__ lq, double* __restrict__ cur_out,
+                 const double* __restrict__ new_out, int* __restrict__ cur_status, const int* __restrict__ new_status,
+                 int* __restrict__ accepted, unsigned long long* __restrict__ counters, const int* __restrict__ slot,
+                 const double* __restrict__ ladder_prior, const double* __restrict__ ladder_lik, int chain_offset,
+                 int use_root_jacobian, uint64_t seed, uint32_t iteration, int S, int undo_stride, int B) {
   __shared__ int sh_acc;
-  const int b = blockIdx.x;
+  __shared__ int2 sh_rng[MH_MAX_OPS];
+  const int b = blockIdx.x, tid = threadIdx.x;
   if (b >= B) return;
   const int4 m = meta[b];
-  if (threadIdx.x == 0) {
+  if (tid < m.x) sh_rng[tid] = rng[(size_t)b * MH_MAX_OPS + tid];
+  if (tid == 0) {
     int acc = 0;
-    if (m.y > 0) {
+    if (m.y == MH_ST_OK) {
       const double* o1 = new_out + (size_t)b * 8;
       const double* o0 = cur_out + (size_t)b * 8;
-      double lr = (o1[3] + o1[4]) - (o0[3] + o0[4]) + lq[b];
+      double bp = 1.0, bl = 1.0;
+      if (slot) {
+        const int sl = slot[chain_offset + b];
+        bp = ladder_prior[sl];
+        bl = ladder_lik[sl];
+      }
+      double lr = bp * (o1[3] - o0[3]) + bl * (o1[4] - o0[4]) + lq[b];
       if (use_root_jacobian) lr += o1[5] - o0[5];
       const double u = mh_uniform(seed, (uint32_t)b, iteration, 1u);
       acc = log(u) < lr;  // false for NaN and for -inf
     }
     sh_acc = acc;
-    if (accepted) accepted[b] = m.z == MH_ST_INVALID ? -1 : acc;
+    if (accepted) accepted[b] = m.y == MH_ST_INVALID ? -1 : acc;
+    if (counters) {
+      if (acc) atomicAdd(counters, 1ull);
+      if (m.y == MH_ST_INVALID) atomicAdd(counters + 1, 1ull);
+    }
   }
   __syncthreads();
   if (sh_acc) {
-    if (threadIdx.x < 8) cur_out[(size_t)b * 8 + threadIdx.x] = new_out[(size_t)b * 8 + threadIdx.x];
-    if (threadIdx.x == 8) cur_status[b] = new_status[b];
-  } else {
-    double* h = states + (size_t)b * S + 3;
-    for (int i = threadIdx.x; i < m.y; i += 256) h[m.x + i] = undo[(size_t)b * N + i];
+    if (tid < 8) cur_out[(size_t)b * 8 + tid] = new_out[(size_t)b * 8 + tid];
+    if (tid == 8) cur_status[b] = new_status[b];
+  } else if (m.x > 0) {
+    double* row = states + (size_t)b * S;
+    const double* ub = undo + (size_t)b * undo_stride;
+    int pos = 0;
+    for (int o = 0; o < m.x; ++o) pos += sh_rng[o].y;
+    for (int o = m.x - 1; o >= 0; --o) {
+      const int2 r = sh_rng[o];
+      pos -= r.y;
+      for (int i = tid; i < r.y; i += 256) row[r.x + i] = ub[pos + i];
+      __syncthreads();
+    }
   }
+}
+
+// MC3 state swaps between neighbouring temperatures (the `mcmc` package's MC3 algorithm, called at app/Main.hs:476-479;
+// restated from Altekar et al. 2004 / the package's published source): for the chains x_i, x_j holding slots p, p + 1 of a
+// group, ln r = (beta_p - beta_{p+1}) (ln pi(x_j) - ln pi(x_i)) with prior and likelihood heated by their own ladders;
+// accept iff ln U < ln r.  States never move: the chains exchange their temperature slots.  stats[c] = (ln prior,
+// ln likelihood) of every chain of every rank (all-gathered by the host over NCCL when the groups span GPUs); every rank
+// takes the same decisions from the same Philox draws (counter (group, iteration, draw, 3)).  One thread per group.
+__global__ void mh_swap_kernel(const double* __restrict__ stats, int stats_stride, int* __restrict__ slot, int* __restrict__ chain_of_slot,
+                               const double* __restrict__ ladder_prior, const double* __restrict__ ladder_lik, int n_groups,
+                               int C, int pair, uint64_t seed, uint32_t iteration, int* __restrict__ accepted) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups || C < 2) return;
+  uint32_t c[4] = {(uint32_t)g, iteration, 0u, 3u};
+  Philox{(uint32_t)seed, (uint32_t)(seed >> 32)}(c);
+  const double u0 = ((double)(((uint64_t)(c[0] >> 5) << 26) | (uint64_t)(c[1] >> 6)) + 0.5) * 1.1102230246251565e-16;
+  const double u1 = ((double)(((uint64_t)(c[2] >> 5) << 26) | (uint64_t)(c[3] >> 6)) + 0.5) * 1.1102230246251565e-16;
+  int p = pair;
+  if (p < 0) {
+    p = (int)(u1 * (double)(C - 1));
+    if (p >= C - 1) p = C - 2;
+  }
+  const int i = chain_of_slot[g * C + p], j = chain_of_slot[g * C + p + 1];
+  const double* si = stats + (size_t)i * stats_stride;
+  const double* sj = stats + (size_t)j * stats_stride;
+  const double lr = (ladder_prior[p] - ladder_prior[p + 1]) * (sj[0] - si[0]) + (ladder_lik[p] - ladder_lik[p + 1]) * (sj[1] - si[1]);
+  const int acc = log(u0) < lr;
+  if (acc) {
+    slot[i] = p + 1;
+    slot[j] = p;
+    chain_of_slot[g * C + p] = j;
+    chain_of_slot[g * C + p + 1] = i;
+  }
+  if (accepted) accepted[g] = acc;
 }
 
 }  // namespace mcd

@@ -470,21 +470,34 @@ def test_device_nuts_draws_its_own_momenta():
     ev.close()
 
 
-@pytest.mark.parametrize("n_leaves,B", [(24, 64), (300, 40)])
-def test_device_resident_mh_proposals_match_host_restatement(n_leaves, B):
-    """chains resident in HBM: slide-node and scale-sub-tree proposals (first-party code of the reference), value-only
-    evaluation, accept / restore -- step by step against tests/mh_ref.py (oracle values, same Philox uniforms)"""
+def _mh_setup(n_leaves, B, clock=1, n_brace=1, seed_off=0):
     import mh_ref
-    md, h = synth.synthetic_model(n_leaves, seed=301 + n_leaves, n_cal=3, n_con=2, n_brace=0)
+    md, h = synth.synthetic_model(n_leaves, seed=301 + n_leaves + seed_off, clock_model=clock, n_cal=3, n_con=2, n_brace=n_brace)
     X = synth.synthetic_states(md, h, B)
     ev = binding.Evaluator(md)
     orc = O.Oracle(md)
     parent = [int(p) for p in md.parent]
-    child, size, inner, inner_list = mh_ref.topology(parent)
+    braces = [[int(x) for x in md.brace_node[md.brace_off[b]:md.brace_off[b + 1]]] for b in range(md.n_brace)]
     ev.chains_set(X)
     Xr = X.copy()
     out_r, st_r = orc.eval(Xr)
     out_r = np.concatenate([out_r, np.zeros((B, 1))], axis=1) if out_r.shape[1] == 7 else out_r
+    return mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r
+
+
+def _mh_compare(ev, Xr, out_r, st_r):
+    Xd, out_d, st_d = ev.chains_get()
+    assert (np.abs(Xd - Xr) <= 1e-11 * np.maximum(1.0, np.abs(Xr))).all()
+    assert relerr(out_d[:, :7], out_r[:, :7]).max() < 1e-9 and np.array_equal(st_d, st_r)
+    return Xd, out_d, st_d
+
+
+@pytest.mark.parametrize("n_leaves,B", [(24, 64), (300, 40)])
+def test_device_resident_mh_proposals_match_host_restatement(n_leaves, B):
+    """chains resident in HBM: slide-node and scale-sub-tree proposals (first-party code of the reference), value-only
+    evaluation, accept / restore -- step by step against tests/mh_ref.py (oracle values, same Philox uniforms)"""
+    mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r = _mh_setup(n_leaves, B, n_brace=0)
+    child, size, inner, inner_list = mh_ref.topology(parent)
     Xd, out_d, st_d = ev.chains_get()
     assert np.array_equal(Xd, X) and relerr(out_d[:, :7], out_r[:, :7]).max() < TOL and np.array_equal(st_d, st_r)
     root_child = 1 if child[1] else child[0][1]          # an inner child of the root: lifted with jacobianRootBranch
@@ -500,14 +513,120 @@ def test_device_resident_mh_proposals_match_host_restatement(n_leaves, B):
         n_acc += int((acc_r == 1).sum())
         n_rej += int((acc_r == 0).sum())
     assert n_acc > B and n_rej > B // 4                    # both branches of the accept kernel were exercised
-    Xd, out_d, st_d = ev.chains_get()
-    assert (np.abs(Xd - Xr) <= 1e-11 * np.maximum(1.0, np.abs(Xr))).all()
-    assert relerr(out_d[:, :7], out_r[:, :7]).max() < 1e-9 and np.array_equal(st_d, st_r)
+    Xd, out_d, st_d = _mh_compare(ev, Xr, out_r, st_r)
     # the resident ln-posterior parts are those of the resident states
     o2, s2 = ev.eval(Xd)
     assert relerr(out_d[:, :7], o2[:, :7]).max() < 1e-12
     with pytest.raises(RuntimeError):
         ev.mh_step(mh_ref.SLIDE_NODE, 0, 0.1)              # the root does not slide
+    ev.close()
+
+
+@pytest.mark.parametrize("n_leaves,B,clock", [(24, 48, 1), (24, 48, 3), (200, 24, 0)])
+def test_every_proposal_of_the_reference_cycle(n_leaves, B, clock):
+    """all 17 proposal kinds of app/Definitions.hs:145-278 (time tree, rate tree, contrary, braces, hyper-parameters),
+    each restated literally in tests/mh_ref.py: proposed state, Hastings factor, Jacobian, acceptance -- step by step"""
+    mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r = _mh_setup(n_leaves, B, clock=clock, n_brace=2, seed_off=7)
+    child, size, inner, inner_list = mh_ref.topology(parent)
+    assert child[1] and child[child[0][1]], "both root children must be inner nodes for the pulley (regenerate the tree)"
+    R = mh_ref
+    big = max(inner_list, key=lambda i: size[i])
+    # (kind, node, param, tune, lifted with jacobianRootBranch)   -- parameters as in app/Definitions.hs
+    pt = 1.0 if n_leaves < 100 else 0.02                   # the pulley moves every node: small steps on large trees
+    steps = [(R.PULLEY, 0, 0.01, pt, True), (R.SLIDE_NODE, 1, 0.01, 2.0, True), (R.SCALE_SUBTREE, big, 0.01, pt, False),
+             (R.SLIDE_BRACE, 0, 0.01, 0.01, False), (R.SLIDE_BRACE, -1, 0.01, 0.02, False),
+             (R.SCALE_BRANCH, 1, 100.0, 20.0, True), (R.SCALE_BRANCH, -1, 100.0, 20.0, False),
+             (R.SCALE_RATE_SUBTREE, big, 100.0, 2.0, False), (R.SCALE_RATE_SUBTREE, -1, 100.0, 5.0, False),
+             (R.SCALE_NORM_TREE_CONTRA_M, 0, 100.0, 1.0, True), (R.SCALE_NORM_TREE_CONTRA_H, 0, 100.0, 1.0, True),
+             (R.SCALE_VAR_TREE, 0, 100.0, 1.0, True), (R.SCALE_VAR_TREE_AUTO, 0, 100.0, 1.0, True),
+             (R.SLIDE_NODE_CONTRA, 1, 0.1, 0.3, True), (R.SLIDE_NODE_CONTRA, -1, 0.1, 0.1, False),
+             (R.SCALE_SUBTREE_CONTRA, big, 0.1, 0.1, False), (R.SCALE_SUBTREE_CONTRA, -1, 0.1, 0.05, False),
+             (R.SLIDE_BRACE_CONTRA, 1, 0.1, 0.002, False), (R.SLIDE_ROOT_CONTRA, 0, 10.0, 0.5, True),
+             (R.SCALE_RATES_TREE_CONTRA, 0, 0.1, 0.1, True),
+             (R.SCALE_SCALAR, 0, 10.0, 1.0, False), (R.SCALE_SCALAR, 1, 10.0, 1.0, False), (R.SCALE_SCALAR, 2, 3000.0, 1.0, False),
+             (R.SCALE_SCALAR, 3, 10.0, 1.0, False), (R.SCALE_SCALAR, 4, 10.0, 0.5, False), (R.SCALE_H_M_CONTRA, 0, 10.0, 1.0, False),
+             (R.SCALE_VAR_TREE, 0, 2.0, 4.0, True),          # shape 0.5 < 1: boosted gamma draw, many NaN rates
+             (R.PULLEY, 0, 0.01, 3.0 * pt, True), (R.SLIDE_NODE_CONTRA, -1, 0.1, 0.1, False)]
+    seen_acc, seen_rej = set(), set()
+    for it, (kind, node, param, tune, jac) in enumerate(steps):
+        acc_d = ev.mh_step(kind, node, param, tune=tune, use_root_jacobian=jac, seed=777, iteration=100 + it)
+        acc_r, lrs = R.mh_step(orc, parent, Xr, out_r, st_r, kind, node, param, tune, jac, 777, 100 + it, braces=braces,
+                               return_lr=True)
+        assert np.array_equal(acc_d, acc_r), (it, kind, np.nonzero(acc_d != acc_r), lrs[acc_d != acc_r])
+        _mh_compare(ev, Xr, out_r, st_r)
+        if (acc_r == 1).any():
+            seen_acc.add(kind)
+        if (acc_r == 0).any():
+            seen_rej.add(kind)
+    assert seen_acc == set(range(17)) and len(seen_rej) >= 15, (sorted(seen_acc), sorted(seen_rej))
+    with pytest.raises(RuntimeError):
+        ev.mh_step(R.SCALE_SCALAR, 7, 10.0)
+    with pytest.raises(RuntimeError):
+        ev.mh_step(R.SLIDE_BRACE, 5, 0.01)
+    ev.close()
+
+
+def test_mh_cycle_equals_single_steps_and_counts():
+    """mcd_mh_cycle = the same proposals enqueued back to back: identical chains, acceptance counts per list entry"""
+    mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r = _mh_setup(60, 96, n_brace=1)
+    R = mh_ref
+    props = [(R.SLIDE_NODE, -1, 0.01, 1.0, 0, 3), (R.SCALE_BRANCH, -1, 100.0, 10.0, 0, 2), (R.SCALE_SCALAR, 3, 10.0, 1.0, 0, 1),
+             (R.SLIDE_BRACE, 0, 0.01, 0.01, 0, 1), (R.SCALE_NORM_TREE_CONTRA_M, 0, 100.0, 1.0, 1, 1)]
+    acc, inv, nxt = ev.mh_cycle(props, n_iterations=2, seed=5, iteration0=10)
+    assert nxt == 10 + 2 * 8
+    Xc, out_c, st_c = ev.chains_get()
+    ev.chains_set(X)
+    it, acc2 = 10, np.zeros(len(props), np.int64)
+    for sweep in range(2):
+        for i, (kind, node, param, tune, jac, rep) in enumerate(props):
+            for _ in range(rep):
+                a = ev.mh_step(kind, node, param, tune=tune, use_root_jacobian=bool(jac), seed=5, iteration=it)
+                acc2[i] += int((a == 1).sum())
+                it += 1
+    Xs, out_s, st_s = ev.chains_get()
+    assert np.array_equal(Xc, Xs) and np.array_equal(out_c, out_s) and np.array_equal(st_c, st_s)
+    assert np.array_equal(acc.astype(np.int64), acc2) and (inv == 0).all() and (acc2 > 0).all()
+    ev.close()
+
+
+def test_heated_chains_and_mc3_swaps():
+    """MC3 (app/Main.hs:476-479): heated acceptance ratio and slot swaps against the host restatement; stepping-stone heats
+    (likelihood only, app/Main.hs:511-543)"""
+    C, G = 4, 12
+    mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r = _mh_setup(24, C * G, n_brace=0)
+    R = mh_ref
+    ladder = np.array([1.0, 0.7, 0.4, 0.1])
+    ev.mc3_configure(C * G, 0, C, ladder, ladder)
+    slot = np.arange(C * G) % C
+    cos = np.arange(C * G)
+    n_sw = 0
+    for it in range(6):
+        kind, node, param = [(R.SLIDE_NODE, -1, 0.05), (R.SCALE_BRANCH, -1, 20.0), (R.SCALE_SUBTREE, -1, 0.05)][it % 3]
+        beta = ladder[slot]
+        acc_d = ev.mh_step(kind, node, param, tune=1.0, seed=9, iteration=it)
+        acc_r = R.mh_step(orc, parent, Xr, out_r, st_r, kind, node, param, 1.0, False, 9, it, beta_prior=beta, beta_lik=beta)
+        assert np.array_equal(acc_d, acc_r)
+        pair = -1 if it % 2 else it // 2 % (C - 1)
+        sw_d = ev.mc3_swap(pair, seed=9, iteration=1000 + it)
+        sw_r = R.mc3_swap(out_r[:, 3:5], slot, cos, ladder, ladder, C, pair, 9, 1000 + it)
+        assert np.array_equal(sw_d, sw_r) and np.array_equal(ev.mc3_slots(), slot)
+        n_sw += int(sw_r.sum())
+    assert 0 < n_sw < 6 * G
+    _mh_compare(ev, Xr, out_r, st_r)
+    # every group still holds every temperature exactly once
+    assert (np.sort(slot.reshape(G, C), axis=1) == np.arange(C)).all()
+    # stepping stone: the likelihood alone is heated
+    betas = np.linspace(0.0, 1.0, C * G)
+    ev.mc3_configure(C * G, 0, C * G, np.ones(C * G), betas)
+    for it in range(3):
+        acc_d = ev.mh_step(R.SLIDE_NODE, -1, 0.05, seed=10, iteration=it)
+        acc_r = R.mh_step(orc, parent, Xr, out_r, st_r, R.SLIDE_NODE, -1, 0.05, 1.0, False, 10, it, beta_lik=betas)
+        assert np.array_equal(acc_d, acc_r)
+    _mh_compare(ev, Xr, out_r, st_r)
+    ev.mc3_configure(0, 0, 0)                                # cold again
+    acc_d = ev.mh_step(R.SLIDE_NODE, -1, 0.05, seed=11, iteration=0)
+    acc_r = R.mh_step(orc, parent, Xr, out_r, st_r, R.SLIDE_NODE, -1, 0.05, 1.0, False, 11, 0)
+    assert np.array_equal(acc_d, acc_r)
     ev.close()
 
 
