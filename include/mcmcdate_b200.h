@@ -208,7 +208,9 @@ int mcd_mh_cycle(mcd_handle* h, int32_t n_props, const mcd_mh_proposal* props, i
  * from their published definitions.  n_global chains (over all ranks; this handle's resident chains are
  * [chain_offset, chain_offset + n_resident) of them) form groups of chains_per_group consecutive chains; chain c starts
  * at temperature slot c % chains_per_group with heats (ladder_prior[slot], ladder_lik[slot]).  MC3: both ladders equal
- * the beta_i; stepping stone: ladder_prior = 1, ladder_lik = beta_i, no swaps.  chains_per_group = 0: cold chains again.
+ * the beta_i; stepping stone: ladder_prior = 1, ladder_lik = beta_i, no swaps.  chains_per_group = 0: cold chains again
+ * (chain_offset is still recorded).  chain_offset also enters the Philox counters of the proposals (global chain index),
+ * so a run does not depend on how the chains are split over handles / GPUs.
  * mcd_mc3_swap proposes, in every group, the exchange of the chains at slots (pair, pair + 1) (pair = -1: drawn per
  * group): ln r = (beta_p - beta_{p+1}) (ln pi(x_{p+1}) - ln pi(x_p)); accepted exchanges swap the chains' SLOTS, states
  * never move.  d_stats_global: DEVICE pointer to the (ln prior, ln likelihood) pairs of all n_global chains [n_global][2]
@@ -221,6 +223,10 @@ int mcd_mc3_swap(mcd_handle* h, int32_t pair, uint64_t seed, uint32_t iteration,
                  int32_t* accepted /*[n_global / chains_per_group] or NULL*/);
 int mcd_mc3_slots(mcd_handle* h, int32_t* slots /*[n_global]*/);
 void* mcd_chains_out_device(mcd_handle* h); /* device pointer: [n_resident][MCD_OUT_COLS] of the resident chains */
+/* (ln prior, ln likelihood) of the resident chains into a caller's DEVICE buffer [n_resident][2] -- the send buffer of
+ * the all-gather; returns after the copy has completed.  The caller synchronises its own collective before
+ * mcd_mc3_swap reads the gathered table. */
+int mcd_chains_stats_device(mcd_handle* h, double* d_stats);
 
 /* Arithmetic pipe of the precision-matrix contraction Y = DX . Sigma^-1 on large trees (the dominant kernel).
  *   MCD_CONTRACT_DMMA   FP64 tensor instructions (mma.sync m8n8k4.f64), plain FP64 GEMM rounding

@@ -21,7 +21,7 @@ EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
     "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_leapfrog", "mcd_nuts",
     "mcd_chains_set", "mcd_chains_get", "mcd_mh_step", "mcd_mh_cycle", "mcd_mc3_configure", "mcd_mc3_swap", "mcd_mc3_slots",
-    "mcd_chains_out_device",
+    "mcd_chains_out_device", "mcd_chains_stats_device",
     "mcd_eval_device", "mcd_set_contraction", "mcd_get_contraction",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
     "mcd_kernel_times",
@@ -98,6 +98,7 @@ def load_library():
     L.mcd_mc3_slots.argtypes = [vp, ip]
     L.mcd_chains_out_device.argtypes = [vp]
     L.mcd_chains_out_device.restype = vp
+    L.mcd_chains_stats_device.argtypes = [vp, vp]
     L.mcd_eval_device.argtypes = [vp, i32, vp, vp, vp, vp]
     L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mcd_set_contraction.argtypes = [vp, i32]
@@ -281,6 +282,14 @@ class Evaluator:
     def mh_cycle(self, proposals, n_iterations: int = 1, seed: int = 0, iteration0: int = 0):
         """sweeps over a list of (kind, node, param, tune, use_root_jacobian, repeat) tuples, enqueued back to back
         -> (accepted[n_props], invalid[n_props], next unused iteration value)"""
+        if len(proposals) > 4096:      # the C entry point takes 4096 list entries per call
+            acc, inv, k = [], [], int(iteration0)
+            assert n_iterations == 1, "long cycles: one sweep per call"
+            for c0 in range(0, len(proposals), 4096):
+                a, i, k = self.mh_cycle(proposals[c0:c0 + 4096], 1, seed, k)
+                acc.append(a)
+                inv.append(i)
+            return np.concatenate(acc), np.concatenate(inv), k
         n = len(proposals)
         arr = (MhProposalC * n)()
         for i, (kind, node, param, tune, jac, rep) in enumerate(proposals):
@@ -311,6 +320,10 @@ class Evaluator:
         sl = np.empty(self._mc3[0], np.int32)
         self._check(self._L.mcd_mc3_slots(self.h, _ip(sl)))
         return sl
+
+    def chains_stats_device(self, d_stats: int):
+        """(ln prior, ln lik) of the resident chains -> device buffer [n][2] (send buffer of the MC3 all-gather)"""
+        self._check(self._L.mcd_chains_stats_device(self.h, d_stats))
 
     def chains_out_device(self) -> int:
         return int(self._L.mcd_chains_out_device(self.h) or 0)

@@ -787,7 +787,7 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
   cudaStream_t st = h->streams[0];
   MhParams P;
   P.kind = kind; P.node = node; P.use_root_jacobian = use_root_jacobian; P.pad = 0; P.param = param; P.tune = tune;
-  P.seed = seed; P.iteration = iteration;
+  P.seed = seed; P.iteration = iteration; P.chain_offset = h->mc3_offset;
   mh_propose_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
                                        h->d_lq.as<double>(), mh_topo(h), P, h->undo_stride, n);
   if (enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st))
@@ -858,8 +858,9 @@ int mc3_configure(mcd_handle* h, int n_global, int chain_offset, int C, const do
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
   CU_TRY(h, cudaSetDevice(h->device));
-  if (C == 0) {  // back to cold chains
+  if (C == 0) {  // back to cold chains (the global chain offset of the random streams stays)
     h->mc3_C = 0;
+    if (chain_offset >= 0) h->mc3_offset = chain_offset;
     return 0;
   }
   if (C < 0 || n_global <= 0 || n_global % C != 0 || chain_offset < 0 || chain_offset > n_global || !ladder_prior || !ladder_lik)
@@ -1256,6 +1257,16 @@ int mcd_mc3_swap(mcd_handle* h, int32_t pair, uint64_t seed, uint32_t iteration,
 }
 int mcd_mc3_slots(mcd_handle* h, int32_t* slots) { return mc3_slots(h, slots); }
 void* mcd_chains_out_device(mcd_handle* h) { return h ? h->d_chain_out.p : nullptr; }
+int mcd_chains_stats_device(mcd_handle* h, double* d_stats) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (h->n_resident <= 0 || !d_stats) return fail(h, "mcd_chains_stats_device: no resident chains or null buffer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaMemcpy2DAsync(d_stats, 16, h->d_chain_out.as<double>() + MCD_OUT_LNPRIOR, MCD_OUT_COLS * 8, 16, h->n_resident,
+                              cudaMemcpyDeviceToDevice, h->streams[0]));
+  CU_TRY(h, cudaStreamSynchronize(h->streams[0]));
+  return 0;
+}
 int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double sd, double tune, int32_t use_root_jacobian, uint64_t seed,
                 uint32_t iteration, int32_t* accepted) {
   return mh_step(h, kind, node, sd, tune, use_root_jacobian, seed, iteration, accepted);

@@ -71,6 +71,8 @@ struct MhParams {
   double param, tune;  // standard deviation (truncated-normal moves) or shape k (multiplier moves); tuning parameter
   uint64_t seed;
   uint32_t iteration;
+  int chain_offset;    // global index of this handle's first chain: the Philox counter uses the global chain index, so the
+                       // draws do not depend on how the chains are split over handles / GPUs
 };
 
 __device__ __forceinline__ void mh_uniform2(uint64_t seed, uint32_t chain, uint32_t iteration, uint32_t draw, double* u0, double* u1) {
@@ -158,12 +160,13 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
       ++nops;
     };
     const double s = P.param * P.tune;  // sd' = t * s (Internal.hs:117)
-    const double p = mh_uniform(P.seed, (uint32_t)b, P.iteration, 0u);
+    const uint32_t gb = (uint32_t)(P.chain_offset + b);
+    const double p = mh_uniform(P.seed, gb, P.iteration, 0u);
     const int kind = P.kind;
     const bool node_kind = kind == MH_SLIDE_NODE || kind == MH_SCALE_SUBTREE || kind == MH_SCALE_RATE_SUBTREE ||
                            kind == MH_SLIDE_NODE_CONTRA || kind == MH_SCALE_SUBTREE_CONTRA;
     if (node < 0) {
-      const double un = mh_uniform(P.seed, (uint32_t)b, P.iteration, 2u);
+      const double un = mh_uniform(P.seed, gb, P.iteration, 2u);
       if (node_kind) {
         int pick = (int)(un * (double)T.n_inner_nonroot);
         if (pick >= T.n_inner_nonroot) pick = T.n_inner_nonroot - 1;
@@ -186,7 +189,7 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
                            kind == MH_SCALE_SCALAR || kind == MH_SCALE_H_M_CONTRA;
     if (mult_kind) {
       const double kk = P.param / P.tune, th = P.tune / P.param;
-      ok = mh_gamma(kk, th, P.seed, (uint32_t)b, P.iteration, &u);
+      ok = mh_gamma(kk, th, P.seed, gb, P.iteration, &u);
       if (ok) lnq = -2.0 * (kk - 1.0) * log(u) - (1.0 / u - u) / th;
     }
     if (ok) switch (kind) {
@@ -391,7 +394,7 @@ mh_accept_kernel(double* __restrict__ states, const double* __restrict__ undo, c
       }
       double lr = bp * (o1[3] - o0[3]) + bl * (o1[4] - o0[4]) + lq[b];
       if (use_root_jacobian) lr += o1[5] - o0[5];
-      const double u = mh_uniform(seed, (uint32_t)b, iteration, 1u);
+      const double u = mh_uniform(seed, (uint32_t)(chain_offset + b), iteration, 1u);
       acc = log(u) < lr;  // false for NaN and for -inf
     }
     sh_acc = acc;

@@ -630,6 +630,50 @@ def test_heated_chains_and_mc3_swaps():
     ev.close()
 
 
+def test_mh_and_mc3_do_not_depend_on_the_split_over_handles():
+    """the multi-GPU layout on one GPU: one handle holding all chains vs two handles holding half each (global chain offsets,
+    all-gathered swap statistics): bit-identical chains and slot tables -- what tools/mc3_bench.py relies on over NCCL"""
+    import torch
+    import mh_ref as R
+    C, G = 8, 6
+    n = C * G
+    md, h = synth.synthetic_model(24, seed=77, clock_model=3, n_cal=3, n_con=2, n_brace=0)
+    X = synth.synthetic_states(md, h, n)
+    ladder = 1.0 / (1.0 + 0.3 * np.arange(C))
+    whole = binding.Evaluator(md)
+    halves = [binding.Evaluator(md), binding.Evaluator(md)]
+    whole.chains_set(X)
+    whole.mc3_configure(n, 0, C, ladder, ladder)
+    for r, ev in enumerate(halves):
+        ev.chains_set(X[r * n // 2:(r + 1) * n // 2])
+        ev.mc3_configure(n, r * n // 2, C, ladder, ladder)
+    props = [(R.SLIDE_NODE, -1, 0.05, 1.0, 0, 2), (R.SCALE_BRANCH, -1, 50.0, 1.0, 0, 2), (R.SLIDE_NODE_CONTRA, -1, 0.1, 0.3, 0, 1),
+             (R.SCALE_SCALAR, 4, 10.0, 1.0, 0, 1)]
+    gathered = torch.empty((n, 2), dtype=torch.float64, device="cuda")
+    k = 0
+    for it in range(4):
+        _, _, k2 = whole.mh_cycle(props, 1, seed=3, iteration0=k)
+        for ev in halves:
+            ev.mh_cycle(props, 1, seed=3, iteration0=k)
+        k = k2
+        for r, ev in enumerate(halves):                       # the "all-gather"
+            ev.chains_stats_device(gathered[r * n // 2:(r + 1) * n // 2].data_ptr())
+        torch.cuda.synchronize()
+        a = whole.mc3_swap(-1, seed=4, iteration=it)
+        bs = [ev.mc3_swap(-1, seed=4, iteration=it, d_stats_global=gathered.data_ptr()) for ev in halves]
+        assert np.array_equal(a, bs[0]) and np.array_equal(a, bs[1])
+    Xw, ow, sw = whole.chains_get()
+    parts = [ev.chains_get() for ev in halves]
+    assert np.array_equal(Xw, np.concatenate([p[0] for p in parts])) and np.array_equal(ow, np.concatenate([p[1] for p in parts]))
+    sl = whole.mc3_slots()
+    assert np.array_equal(sl, halves[0].mc3_slots()) and np.array_equal(sl, halves[1].mc3_slots())
+    assert (sl != np.arange(n) % C).any() and (np.abs(Xw - X).max(axis=1) > 0).all()
+    with pytest.raises(RuntimeError):
+        halves[1].mc3_swap(-1, seed=4, iteration=99)          # groups span handles: the gathered table is required
+    for ev in [whole] + halves:
+        ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
