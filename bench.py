@@ -40,6 +40,7 @@ METRIC = "log-posterior+gradient evals/sec (batched chains)"
 UNIT = "evals/s"
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 FP64 FMA/clk/SM x 1965 MHz = 37.2
 INT8_NOMINAL_TOPS = 4500.0                           # dense int8 tensor peak (2x the 2.25 PFLOP/s bf16 figure)
+INT8_LIBRARY_GEMM_TOPS = 3079.7                      # cuBLASLt int8 GEMM measured on this pool (profiles/r01_int8_peak_measured.json)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the contraction kernel at this shape, from one
 # `ncu --set full` capture of this command (profiles/r01_ncu_summary.md):
 #   gemm_f64_dmma_kernel      237.9 MB + 113.7 MB (algorithmic: P 32 MB + DX 131 MB + Y 134 MB = 297 MB)
@@ -195,6 +196,12 @@ def roofline(oz_s, K, B, gemm_ms, kms, ncalls, args):
             "unit": "TOP/s (int8)", "frac": achieved / INT8_NOMINAL_TOPS, "traffic": traffic,
             "peak_source": "nominal dense INT8 tensor peak (4.5 POP/s); MEASURED_PEAKS.json has no int8 entry -- twice its "
                            f"measured bf16 burst figure would be {2 * peaks.get('bf16_tflops', 1662.5):.0f} TOP/s",
+            "frac_of_measured": {
+                "vs_2x_bf16_burst_of_MEASURED_PEAKS": achieved / (2 * peaks.get("bf16_tflops", 1662.5)),
+                "vs_library_int8_gemm_measured": achieved / INT8_LIBRARY_GEMM_TOPS,
+                "library_int8_gemm_tops": INT8_LIBRARY_GEMM_TOPS,
+                "note": "cuBLASLt int8 GEMM (torch._int_mm, 8192^3, best of 10) measured on this pool's B200 with "
+                        "tools/int8_peak.py -> profiles/r01_int8_peak_measured.json"},
             "kernel_ms": gemm_ms, "algorithmic_int8_ops_per_launch": ops, "int8_products": pairs,
             "algorithmic_flops_per_launch": flops_alg,
             "fp64_equivalent": {"achieved_tflops": fp64_equiv, "fp64_nominal_peak_tflops": FP64_NOMINAL_TFLOPS,

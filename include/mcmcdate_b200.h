@@ -203,6 +203,18 @@ typedef struct mcd_mh_proposal {
 int mcd_mh_cycle(mcd_handle* h, int32_t n_props, const mcd_mh_proposal* props, int32_t n_iterations, uint64_t seed,
                  uint32_t iteration0, uint64_t* accepted, uint64_t* invalid, uint32_t* iteration_next);
 
+/* Incremental evaluation of small moves (default: on).  On large trees with a dense precision matrix the library keeps
+ * y = Sigma^-1 (d - mu) of every resident chain's current state in HBM.  Proposals that touch a few branches only
+ * (slide node, slide braced nodes, their contrary forms, scale branch, sub-tree moves on sub trees of <= 32 (heights) /
+ * <= 64 (rates) nodes with a given node) are then scored from the change alone -- quad' = quad + 2 delta.y +
+ * delta^T Sigma^-1 delta, prior terms of the touched nodes -- instead of 2 K^2 flops per chain; all other proposals are
+ * evaluated from scratch.  The values differ from a fresh evaluation by accumulated rounding only; every
+ * `refresh_every` incremental steps (default 512; 0 = keep) the resident chains are re-evaluated from scratch.  The mode
+ * needs every chain's state to be valid at mcd_chains_set (else that set of chains runs with full evaluations).
+ * mcd_mh_get_incremental: 1 if the resident chains are currently evaluated incrementally. */
+int mcd_mh_set_incremental(mcd_handle* h, int32_t on, int32_t refresh_every);
+int mcd_mh_get_incremental(const mcd_handle* h);
+
 /* Heated chains: Metropolis-coupled MCMC (`mc3`, app/Main.hs:476-479) and the stepping-stone / thermodynamic-integration
  * points of `marginalLikelihood` (app/Main.hs:511-543); both live in the un-vendored `mcmc` package and are restated
  * from their published definitions.  n_global chains (over all ranks; this handle's resident chains are

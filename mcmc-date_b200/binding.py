@@ -21,7 +21,7 @@ EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
     "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_leapfrog", "mcd_nuts",
     "mcd_chains_set", "mcd_chains_get", "mcd_mh_step", "mcd_mh_cycle", "mcd_mc3_configure", "mcd_mc3_swap", "mcd_mc3_slots",
-    "mcd_chains_out_device", "mcd_chains_stats_device",
+    "mcd_chains_out_device", "mcd_chains_stats_device", "mcd_mh_set_incremental", "mcd_mh_get_incremental",
     "mcd_eval_device", "mcd_set_contraction", "mcd_get_contraction",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
     "mcd_kernel_times",
@@ -99,6 +99,8 @@ def load_library():
     L.mcd_chains_out_device.argtypes = [vp]
     L.mcd_chains_out_device.restype = vp
     L.mcd_chains_stats_device.argtypes = [vp, vp]
+    L.mcd_mh_set_incremental.argtypes = [vp, i32, i32]
+    L.mcd_mh_get_incremental.argtypes = [vp]
     L.mcd_eval_device.argtypes = [vp, i32, vp, vp, vp, vp]
     L.mcd_eval_grad_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mcd_set_contraction.argtypes = [vp, i32]
@@ -320,6 +322,13 @@ class Evaluator:
         sl = np.empty(self._mc3[0], np.int32)
         self._check(self._L.mcd_mc3_slots(self.h, _ip(sl)))
         return sl
+
+    def mh_set_incremental(self, on: bool, refresh_every: int = 0):
+        """incremental evaluation of small moves (call before chains_set)"""
+        self._check(self._L.mcd_mh_set_incremental(self.h, int(on), int(refresh_every)))
+
+    def mh_incremental_active(self) -> bool:
+        return self._L.mcd_mh_get_incremental(self.h) == 1
 
     def chains_stats_device(self, d_stats: int):
         """(ln prior, ln lik) of the resident chains -> device buffer [n][2] (send buffer of the MC3 all-gather)"""

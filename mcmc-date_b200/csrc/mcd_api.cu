@@ -75,9 +75,15 @@ struct mcd_handle {
   DevBuf d_chain, d_chain_out, d_chain_status, d_new_out, d_new_status, d_undo, d_rng, d_meta, d_lq, d_accepted, d_counters;
   DevBuf d_mh_child1, d_mh_size, d_mh_inner_cnt, d_mh_inner_list;
   int n_resident = 0, chain_cap = 0, n_inner_nonroot = 0, undo_stride = 0;
-  std::vector<int32_t> br_off_h, br_node_h;  // host copies of the brace table (argument checks of the brace proposals)
+  std::vector<int32_t> br_off_h, br_node_h, sub_size_h;  // host copies of the brace table (argument checks of the brace proposals)
   // heated chains (MC3 / stepping stone): temperature ladders, slot of every chain of every rank, inverse table
   DevBuf d_slot, d_chain_of_slot, d_ladder_p, d_ladder_l, d_swap_acc;
+  // incremental evaluation of small moves (mh_delta_kernel): cached y = Sigma^-1 dx of every resident chain + delta lists
+  DevBuf d_chain_y, d_dl_n, d_dl_k, d_dl_d;
+  bool inc_enabled = true;        // mcd_mh_set_incremental
+  bool inc_ok = false;            // this resident set qualifies (large dense model, every chain's state valid)
+  bool force_sym = false;         // value-only evaluations use the symmetric contraction (they must produce y, not L^T dx)
+  int inc_steps = 0, refresh_every = 512;
   int mc3_C = 0, mc3_n_global = 0, mc3_offset = 0;
   DevBuf d_nuts;                  // batched NUTS: trajectory ends, checkpoints, candidates, per-chain scalars
   size_t nuts_bytes = 0;
@@ -304,7 +310,7 @@ template <bool GRAD>
 int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
             cudaStream_t st) {
   DevModel M = h->dm;
-  const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1 && !h->sparse &&
+  const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1 && !h->sparse && !h->force_sym &&
                    (h->oz_S == 0 || h->oz_U_S == h->oz_S);
   M.quad_from_z = tri ? 1 : 0;
   const bool small = M.N <= SMALL_TREE_MAX_NODES;
@@ -667,6 +673,33 @@ int mh_prepare_value_path(mcd_handle* h, int n) {
   if (h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && (ensure_cholesky(h, nullptr) || ensure_i8(h))) return -1;
   return 0;
 }
+// incremental evaluation applies to the large-tree dense-precision pipeline (small trees are one fused launch anyway)
+bool mh_incremental_capable(const mcd_handle* h) {
+  return h->dm.lik == MCD_LIK_FULL && !h->sparse && h->N > SMALL_TREE_MAX_NODES;
+}
+// evaluate the resident chains from scratch (symmetric contraction) and cache y = Sigma^-1 dx of every chain
+int mh_refresh(mcd_handle* h) {
+  const int n = h->n_resident;
+  cudaStream_t st = h->streams[0];
+  h->force_sym = true;
+  const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_chain_out.as<double>(), nullptr, h->d_chain_status.as<int32_t>(), st);
+  h->force_sym = false;
+  if (rc) return -1;
+  CU_TRY(h, cudaMemcpyAsync(h->d_chain_y.p, h->d_y.p, (size_t)n * h->ldy * 8, cudaMemcpyDeviceToDevice, st));
+  h->inc_steps = 0;
+  return 0;
+}
+bool mh_kind_incremental(const mcd_handle* h, int kind, int node) {
+  switch (kind) {
+    case MH_SLIDE_NODE: case MH_SLIDE_NODE_CONTRA: case MH_SCALE_BRANCH: case MH_SLIDE_BRACE: case MH_SLIDE_BRACE_CONTRA:
+      return true;
+    case MH_SCALE_SUBTREE: case MH_SCALE_SUBTREE_CONTRA:
+      return node > 0 && h->sub_size_h[node] <= DL_SUBTREE_H;
+    case MH_SCALE_RATE_SUBTREE:
+      return node > 0 && h->sub_size_h[node] <= DL_SUBTREE_R;
+    default: return false;  // moves that touch lambda, mu, H, m, v or most of the tree: evaluated from scratch
+  }
+}
 int chains_set(mcd_handle* h, int n, const double* states) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
@@ -678,7 +711,7 @@ int chains_set(mcd_handle* h, int n, const double* states) {
   if (n > h->chain_cap) {
     CU_TRY(h, cudaDeviceSynchronize());
     for (DevBuf* b : {&h->d_chain, &h->d_chain_out, &h->d_chain_status, &h->d_new_out, &h->d_new_status, &h->d_undo, &h->d_meta,
-                      &h->d_lq, &h->d_accepted, &h->d_rng}) {
+                      &h->d_lq, &h->d_accepted, &h->d_rng, &h->d_chain_y, &h->d_dl_n, &h->d_dl_k, &h->d_dl_d}) {
       if (b->p) cudaFree(b->p);
       b->p = nullptr;
     }
@@ -693,6 +726,12 @@ int chains_set(mcd_handle* h, int n, const double* states) {
     CU_TRY(h, cudaMalloc(&h->d_meta.p, (size_t)cap * sizeof(int4)));
     CU_TRY(h, cudaMalloc(&h->d_lq.p, (size_t)cap * 8));
     CU_TRY(h, cudaMalloc(&h->d_accepted.p, (size_t)cap * 4));
+    if (mh_incremental_capable(h)) {
+      CU_TRY(h, cudaMalloc(&h->d_chain_y.p, (size_t)cap * h->ldy * 8));
+      CU_TRY(h, cudaMalloc(&h->d_dl_n.p, (size_t)cap * 4));
+      CU_TRY(h, cudaMalloc(&h->d_dl_k.p, (size_t)cap * DL_MAX_AB * 4));
+      CU_TRY(h, cudaMalloc(&h->d_dl_d.p, (size_t)cap * DL_MAX_AB * 8));
+    }
     h->chain_cap = cap;
   }
   if (!h->d_mh_child1.p) {  // topology tables of the proposals: second children, sub-tree sizes, inner-node counts
@@ -709,6 +748,7 @@ int chains_set(mcd_handle* h, int n, const double* states) {
     for (int i = 1; i < N; ++i)
       if (child0[i] >= 0) list.push_back(i);
     h->n_inner_nonroot = (int)list.size();
+    h->sub_size_h.assign(size.begin(), size.end());
     if (upload(h, h->d_mh_child1, h->child1.data(), N) || upload(h, h->d_mh_size, size.data(), N) ||
         upload(h, h->d_mh_inner_cnt, inner.data(), N) || upload(h, h->d_mh_inner_list, list.data(), list.size()))
       return -1;
@@ -716,10 +756,22 @@ int chains_set(mcd_handle* h, int n, const double* states) {
   }
   cudaStream_t st = h->streams[0];
   CU_TRY(h, cudaMemcpyAsync(h->d_chain.p, states, (size_t)n * S * 8, cudaMemcpyHostToDevice, st));
+  h->n_resident = n;
+  h->inc_ok = false;
+  if (mh_incremental_capable(h) && h->inc_enabled) {
+    // symmetric contraction: y of every chain is kept; incremental moves need every chain's current state to be valid
+    if (mh_refresh(h)) return -1;
+    std::vector<int32_t> stv(n);
+    CU_TRY(h, cudaMemcpyAsync(stv.data(), h->d_chain_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    bool ok = true;
+    for (int b = 0; b < n; ++b) ok = ok && ((stv[b] & ~MCD_ST_NEARCRIT) == 0);
+    h->inc_ok = ok;
+    return 0;
+  }
   if (enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_chain_out.as<double>(), nullptr, h->d_chain_status.as<int32_t>(), st))
     return -1;
   CU_TRY(h, cudaStreamSynchronize(st));
-  h->n_resident = n;
   return 0;
 }
 int chains_get(mcd_handle* h, int n, double* states, double* out, int32_t* status) {
@@ -780,25 +832,54 @@ MhTopo mh_topo(mcd_handle* h) {
   T.br_off = h->dm.br_off; T.br_node = h->dm.br_node;
   return T;
 }
-// enqueue propose -> value-only evaluation -> accept on stream 0 (no synchronisation)
+// enqueue propose -> evaluation of the proposed states -> accept on stream 0 (no synchronisation).  Small moves are
+// evaluated incrementally from the cached y (mh_delta_kernel); everything else by the batched value-only evaluation.
 int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int use_root_jacobian, uint64_t seed,
                uint32_t iteration, unsigned long long* d_counters) {
   const int n = h->n_resident, S = h->S;
   cudaStream_t st = h->streams[0];
+  const bool inc_mode = h->inc_enabled && h->inc_ok;
+  const bool inc = inc_mode && mh_kind_incremental(h, kind, node);
+  if (inc && ++h->inc_steps > h->refresh_every && mh_refresh(h)) return -1;  // bound the accumulated rounding
   MhParams P;
   P.kind = kind; P.node = node; P.use_root_jacobian = use_root_jacobian; P.pad = 0; P.param = param; P.tune = tune;
   P.seed = seed; P.iteration = iteration; P.chain_offset = h->mc3_offset;
+  const MhTopo T = mh_topo(h);
   mh_propose_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
-                                       h->d_lq.as<double>(), mh_topo(h), P, h->undo_stride, n);
-  if (enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st))
-    return -1;
+                                       h->d_lq.as<double>(), T, P, h->undo_stride, n);
+  MhYUpdate Y{};
+  Y.mode = 0; Y.K = h->K; Y.ldk = h->ldk; Y.ldy = h->ldy; Y.y_cur = h->d_chain_y.as<double>(); Y.y_new = h->d_y.as<double>();
+  Y.P = h->d_P.as<double>(); Y.dl_n = h->d_dl_n.as<int>(); Y.dl_k = h->d_dl_k.as<int>(); Y.dl_d = h->d_dl_d.as<double>();
+  if (inc) {
+    const size_t smem = (size_t)8 * ((h->N + 31) / 32) * 4;
+#define MCD_LAUNCH_DELTA(CC)                                                                                                 \
+  mh_delta_kernel<CC><<<(n + 7) / 8, 256, smem, st>>>(h->dm, T, h->d_P.as<double>(), h->d_chain.as<double>(),              \
+      h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(), h->d_chain_y.as<double>(),                         \
+      h->d_chain_out.as<double>(), h->d_chain_status.as<int32_t>(), h->d_new_out.as<double>(), h->d_new_status.as<int32_t>(), \
+      h->d_dl_n.as<int>(), h->d_dl_k.as<int>(), h->d_dl_d.as<double>(), h->undo_stride, n)
+    switch (h->dm.clock) {
+      case 0: MCD_LAUNCH_DELTA(0); break;
+      case 1: MCD_LAUNCH_DELTA(1); break;
+      case 2: MCD_LAUNCH_DELTA(2); break;
+      default: MCD_LAUNCH_DELTA(3); break;
+    }
+#undef MCD_LAUNCH_DELTA
+    h->launches += 1;
+    Y.mode = 1;
+  } else {
+    h->force_sym = inc_mode;  // keep producing y while the incremental mode is on
+    const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st);
+    h->force_sym = false;
+    if (rc) return -1;
+    Y.mode = inc_mode ? 2 : 0;
+  }
   const bool heated = h->mc3_C > 0;
   mh_accept_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
                                       h->d_lq.as<double>(), h->d_chain_out.as<double>(), h->d_new_out.as<double>(),
                                       h->d_chain_status.as<int32_t>(), h->d_new_status.as<int32_t>(), h->d_accepted.as<int32_t>(),
                                       d_counters, heated ? h->d_slot.as<int>() : nullptr, h->d_ladder_p.as<double>(),
                                       h->d_ladder_l.as<double>(), h->mc3_offset, use_root_jacobian, seed, iteration, S,
-                                      h->undo_stride, n);
+                                      h->undo_stride, n, Y);
   h->launches += 2;
   CU_TRY(h, cudaGetLastError());
   return 0;
@@ -1257,6 +1338,17 @@ int mcd_mc3_swap(mcd_handle* h, int32_t pair, uint64_t seed, uint32_t iteration,
 }
 int mcd_mc3_slots(mcd_handle* h, int32_t* slots) { return mc3_slots(h, slots); }
 void* mcd_chains_out_device(mcd_handle* h) { return h ? h->d_chain_out.p : nullptr; }
+int mcd_mh_set_incremental(mcd_handle* h, int32_t on, int32_t refresh_every) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (refresh_every < 0) return fail(h, "mcd_mh_set_incremental: refresh_every must be >= 0 (0 keeps the current value)");
+  if (on && !h->inc_enabled && h->n_resident > 0)
+    return fail(h, "mcd_mh_set_incremental: switch the mode on before mcd_chains_set (the cached contraction results are built there)");
+  h->inc_enabled = on != 0;
+  if (refresh_every > 0) h->refresh_every = refresh_every;
+  return 0;
+}
+int mcd_mh_get_incremental(const mcd_handle* h) { return h ? (h->inc_enabled && h->inc_ok ? 1 : 0) : -1; }
 int mcd_chains_stats_device(mcd_handle* h, double* d_stats) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);

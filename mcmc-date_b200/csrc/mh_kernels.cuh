@@ -40,6 +40,7 @@
 #include <stdint.h>
 
 #include "hmc_kernels.cuh"
+#include "posterior_kernels.cuh"
 
 namespace mcd {
 
@@ -363,6 +364,276 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
   if (tid < nops) rng[(size_t)b * MH_MAX_OPS + tid] = make_int2(ops[tid].off, ops[tid].cnt);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Incremental evaluation of small moves.  The chains are resident, so the contraction result y = Sigma^-1 (d - mu) of
+// every chain's CURRENT state can be kept in HBM.  A proposal that changes the residual by delta on a few branches then
+// needs no contraction at all:
+//     quad' = quad + 2 delta . y + delta^T Sigma^-1 delta       (|A| values of y, |A|^2 entries of Sigma^-1)
+// and every prior part is a sum over nodes / branches in which only the touched terms change.  mh_delta_kernel turns
+// the undo log of mh_propose_kernel into the ln-posterior parts of the proposed state in O(|A|^2) work per chain instead
+// of 2 K^2 flops; on acceptance mh_accept_kernel updates y with |A| rows of Sigma^-1 (which stay in the 126 MB L2).
+// Values differ from a fresh evaluation by accumulated rounding only (the host re-evaluates from scratch every
+// `refresh` steps); a chain in the near-critical birth-death regime re-runs the literal D/E recursion (lane 0).
+enum { DL_MAX_CHG = 96, DL_MAX_AB = 128, DL_SUBTREE_H = 32, DL_SUBTREE_R = 64 };
+struct MhYUpdate {
+  int mode;  // 0: no cached y; 1: rank-|A| update from the delta list; 2: copy the freshly contracted row
+  int K, ldk, ldy;
+  double* y_cur;
+  const double* y_new;
+  const double* P;
+  const int* dl_n;
+  const int* dl_k;
+  const double* dl_d;
+};
+
+template <int CLOCK>
+__device__ __forceinline__ double mh_clock_term(double r, double t, double v, double lgk_v, double ln_v) {
+  const double lnr = log(r);
+  if (CLOCK == 0) {  // uncorrelatedGamma: k = 1/v, theta = v
+    const double k = 1.0 / v;
+    return lnr * (k - 1.0) - r * k - lgk_v - ln_v * k;
+  } else if (CLOCK == 2) {  // white noise: k = t/v, theta = v/t
+    const double k = t / v;
+    return lnr * (k - 1.0) - r * k - lgamma(k) + log(k) * k;
+  } else {  // logNormal' 1 w r, w = v | v t
+    const double w = CLOCK == 1 ? v : v * t;
+    const double bb = lnr + 0.5 * w;
+    return -(MCD_LN_SQRT_2PI + lnr + 0.5 * (CLOCK == 1 ? ln_v : log(w))) - 0.5 / w * bb * bb;
+  }
+}
+
+// One warp per chain, eight chains per CTA.  Dynamic shared memory per warp: the bitmap of affected branches.
+template <int CLOCK>
+__global__ void __launch_bounds__(256)
+mh_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict__ P, const double* __restrict__ states,
+                const double* __restrict__ undo, const int2* __restrict__ rng, const int4* __restrict__ meta,
+                const double* __restrict__ y_cur, const double* __restrict__ cur_out, const int* __restrict__ cur_status,
+                double* __restrict__ new_out, int* __restrict__ new_status, int* __restrict__ dl_n, int* __restrict__ dl_k,
+                double* __restrict__ dl_d, int undo_stride, int B) {
+  extern __shared__ unsigned dl_bitmaps[];
+  __shared__ int s_off[8][DL_MAX_CHG];
+  __shared__ double s_old[8][DL_MAX_CHG];
+  __shared__ int s_ab[8][DL_MAX_AB], s_k[8][DL_MAX_AB];
+  __shared__ double s_d[8][DL_MAX_AB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chain = blockIdx.x * 8 + warp;
+  if (chain >= B) return;
+  const int4 mt = meta[chain];
+  if (mt.y != MH_ST_OK || mt.x == 0) {  // rejected by the accept kernel whatever new_out says
+    if (lane == 0) dl_n[chain] = 0;
+    return;
+  }
+  const int N = M.N, OH = 3, OR = 5 + N;
+  const int nwords = (N + 31) >> 5;
+  unsigned* bm = dl_bitmaps + (size_t)warp * nwords;
+  int* c_off = s_off[warp];
+  double* c_old = s_old[warp];
+  int* ab = s_ab[warp];
+  int* abk = s_k[warp];
+  double* abd = s_d[warp];
+  const double* row = states + (size_t)chain * M.S;
+  // 1. raw change list from the undo log (an entry touched twice appears twice: the FIRST record holds the old value)
+  int n_raw = 0;
+  {
+    const double* ub = undo + (size_t)chain * undo_stride;
+    for (int o = 0; o < mt.x; ++o) {
+      const int2 r = rng[(size_t)chain * MH_MAX_OPS + o];
+      for (int i = lane; i < r.y && n_raw + i < DL_MAX_CHG; i += 32) {
+        c_off[n_raw + i] = r.x + i;
+        c_old[n_raw + i] = ub[n_raw + i];
+      }
+      n_raw += r.y;
+    }
+    if (n_raw > DL_MAX_CHG) n_raw = DL_MAX_CHG;  // the host only routes small moves here
+  }
+  for (int w = lane; w < nwords; w += 32) bm[w] = 0u;
+  __syncwarp();
+  auto old_val = [&](int off) -> double {
+    for (int e = 0; e < n_raw; ++e)
+      if (c_off[e] == off) return c_old[e];
+    return row[off];
+  };
+  auto changed = [&](int off) -> bool {
+    for (int e = 0; e < n_raw; ++e)
+      if (c_off[e] == off) return true;
+    return false;
+  };
+  // 2. affected branches: a changed height moves the node's own branch and its children's, a changed rate its own
+  for (int e = lane; e < n_raw; e += 32) {
+    const int off = c_off[e];
+    if (off > OH && off < OH + N) {
+      const int x = off - OH;
+      atomicOr(&bm[x >> 5], 1u << (x & 31));
+      if (T.parent[x] >= 0) {  // inner node
+        const int c0 = x + 1, c1 = T.child1[x];
+        atomicOr(&bm[c0 >> 5], 1u << (c0 & 31));
+        atomicOr(&bm[c1 >> 5], 1u << (c1 & 31));
+      }
+    } else if (off > OR && off < OR + N) {
+      const int x = off - OR;
+      atomicOr(&bm[x >> 5], 1u << (x & 31));
+    }
+  }
+  __syncwarp();
+  int n_ab = 0;  // ascending node order: the sums below do not depend on the order of the atomics
+  for (int w0 = 0; w0 < nwords; w0 += 32) {
+    const int w = w0 + lane;
+    unsigned word = w < nwords ? bm[w] : 0u;
+    const int cnt = __popc(word);
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    int at = n_ab + pre - cnt;
+    while (word) {
+      const int bit = __ffs(word) - 1;
+      word &= word - 1;
+      if (at < DL_MAX_AB) ab[at] = (w << 5) + bit;
+      ++at;
+    }
+    n_ab += total;
+  }
+  if (n_ab > DL_MAX_AB) n_ab = DL_MAX_AB;
+  __syncwarp();
+  // 3. per-branch residual and clock-prior changes
+  const double la = row[0], mu = row[1], H = row[2], m = row[3 + N], v = row[4 + N];
+  const double sc = H * m;
+  const double lgk_v = CLOCK == 0 ? lgamma(1.0 / v) : 0.0, ln_v = log(v);
+  bool bad = false;
+  double d_clock = 0.0, q1 = 0.0;
+  const double* y = y_cur + (size_t)chain * M.ldy;
+  for (int a = lane; a < n_ab; a += 32) {
+    const int i = ab[a], p = T.parent[i] & 0x7fffffff;
+    const double hi_n = row[OH + i], hp_n = row[OH + p], r_n = row[OR + i];
+    const double hi_o = old_val(OH + i), hp_o = old_val(OH + p), r_o = old_val(OR + i);
+    const double t_n = hp_n - hi_n, t_o = hp_o - hi_o;
+    const bool ok = (t_n > 0.0) && (r_n > 0.0);
+    bad = bad || !ok;
+    const int k = branch_of(i, M.root_r);
+    const double d = (t_n * r_n) * sc - (t_o * r_o) * sc;
+    abk[a] = k;
+    abd[a] = d;
+    q1 = fma(d, y[k], q1);
+    if (ok) d_clock += mh_clock_term<CLOCK>(r_n, t_n, v, lgk_v, ln_v) - mh_clock_term<CLOCK>(r_o, t_o, v, lgk_v, ln_v);
+  }
+  __syncwarp();
+  // 4. delta^T Sigma^-1 delta
+  double q2 = 0.0;
+  for (int idx = lane; idx < n_ab * n_ab; idx += 32) {
+    const int a = idx / n_ab, bb = idx - a * n_ab;
+    q2 = fma(abd[a] * abd[bb], P[(size_t)abk[a] * M.ldk + abk[bb]], q2);
+  }
+  // 5. birth-death and node priors of the nodes whose height changed
+  const bool nearcrit = 1e-6 > fabs(la - mu);
+  const bool bd_series = fabs(la - mu) * fmax(1.0, fabs(row[OH])) < 0.25;
+  const double* h = row + OH;
+  double d_bd = 0.0, d_A = 0.0;
+  for (int e = lane; e < n_raw; e += 32) {
+    const int off = c_off[e];
+    if (!(off > OH && off < OH + N)) continue;
+    bool first = true;
+    for (int e2 = 0; e2 < e; ++e2) first = first && (c_off[e2] != off);
+    if (!first) continue;
+    const int x = off - OH;
+    const double h_n = row[off], h_o = c_old[e];
+    if (T.parent[x] >= 0 && !nearcrit) d_bd += ln_p1<false>(la, mu, h_n, bd_series).v - ln_p1<false>(la, mu, h_o, bd_series).v;
+    for (int q = M.inc_off[x]; q < M.inc_off[x + 1]; ++q) {
+      const int2 ent = M.inc_ent[q];
+      if (ent.x == INC_CAL) {
+        double dh, dH;
+        int f = 0;
+        d_A += calibration_term(M, ent.y, H, h_n, &dh, &dH, &f) - calibration_term(M, ent.y, H, h_o, &dh, &dH, &f);
+      } else if (ent.x == INC_BRACE) {
+        const int j0 = M.br_off[ent.y], j1 = M.br_off[ent.y + 1];
+        bool owner = true;  // the changed node with the smallest index accounts for the brace
+        for (int j = j0; j < j1; ++j) owner = owner && !(M.br_node[j] < x && changed(OH + M.br_node[j]));
+        if (!owner) continue;
+        const double sd = M.br_sd[ent.y];
+        double vn = 0.0, vo = 0.0, sn = 0.0, so = 0.0;
+        bool eqn = true, eqo = true;
+        const double hn0 = h[M.br_node[j0]], ho0 = old_val(OH + M.br_node[j0]);
+        for (int j = j0; j < j1; ++j) {
+          const double a_n = h[M.br_node[j]], a_o = old_val(OH + M.br_node[j]);
+          eqn = eqn && (a_n == hn0);
+          eqo = eqo && (a_o == ho0);
+          sn += a_n;
+          so += a_o;
+        }
+        const double mn = sn / (double)(j1 - j0), mo = so / (double)(j1 - j0);
+        for (int j = j0; j < j1; ++j) {
+          const double dn = h[M.br_node[j]] - mn, d_o = old_val(OH + M.br_node[j]) - mo;
+          vn += -(dn * dn) / (2.0 * sd * sd);
+          vo += -(d_o * d_o) / (2.0 * sd * sd);
+        }
+        d_A += (eqn ? 0.0 : vn) - (eqo ? 0.0 : vo);
+      } else {  // constraint: the younger-index changed node of the pair accounts for it
+        const int ny = M.con_y[ent.y], no = M.con_o[ent.y], other = ny == x ? no : ny;
+        if (other < x && changed(OH + other)) continue;
+        const double s = M.con_s[ent.y];
+        const double hYn = h[ny], hOn = h[no], hYo = old_val(OH + ny), hOo = old_val(OH + no);
+        const double tn = (hYn < hOn) ? 0.0 : -((hYn - hOn) * (hYn - hOn)) / (2.0 * s * s);
+        const double to = (hYo < hOo) ? 0.0 : -((hYo - hOo) * (hYo - hOo)) / (2.0 * s * s);
+        d_A += tn - to;
+      }
+    }
+  }
+  // fixed shuffle trees: deterministic
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d_clock += __shfl_xor_sync(0xffffffffu, d_clock, o);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+    d_bd += __shfl_xor_sync(0xffffffffu, d_bd, o);
+    d_A += __shfl_xor_sync(0xffffffffu, d_A, o);
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  for (int a = lane; a < n_ab; a += 32) {
+    dl_k[(size_t)chain * DL_MAX_AB + a] = abk[a];
+    dl_d[(size_t)chain * DL_MAX_AB + a] = abd[a];
+  }
+  if (lane == 0) {
+    dl_n[chain] = n_ab;
+    const double* o0 = cur_out + (size_t)chain * 8;
+    double* o1 = new_out + (size_t)chain * 8;
+    const double NINF = -CUDART_INF;
+    int st = cur_status[chain] & ST_NEARCRIT;
+    if (bad) {  // a non-positive branch or rate: probability zero (or NaN) -- rejected either way
+      o1[0] = o0[0]; o1[1] = NINF; o1[2] = NINF; o1[3] = NINF; o1[4] = o0[4]; o1[5] = o0[5]; o1[6] = NINF; o1[7] = 0.0;
+      st |= ST_ZERO;
+    } else {
+      double lnB = o0[1] + d_bd;
+      if (nearcrit) {  // literal D/E recursion on the proposed state (BirthDeath.hs:90-114), as in the posterior kernel
+        const double d = la - mu;
+        double E = 0.0, bd = 0.0;
+        for (int i = N - 1; i >= 1; --i) {
+          const int pe = T.parent[i];
+          const bool inner = pe >= 0;
+          const double ti = h[pe & 0x7fffffff] - h[i];
+          const double c = inner ? E : 0.0;
+          const double yy = (mu - c * la) * ti, den = 1.0 + yy;
+          const double D = (1.0 - d * ti) / den / den;
+          E = (c + yy) / den;
+          bd += log(D * (inner ? la : 1.0));
+        }
+        lnB = (0.0 - la) + (0.0 - mu) + bd;
+      }
+      const double lnA = o0[0] + d_A, lnC = o0[2] + d_clock;
+      const double prior = lnA + lnB + lnC;
+      const double lk = o0[4] + (-0.5) * (2.0 * q1 + q2);
+      const double d0 = ((h[0] - h[1]) * row[OR + 1] + (h[0] - h[M.root_r]) * row[OR + M.root_r]) * sc;
+      const double jac = log(1.0 / d0);
+      const double post = prior + lk + jac;
+      if (post == NINF) st |= ST_ZERO;
+      if (post != post) st |= ST_NAN;
+      o1[0] = lnA; o1[1] = lnB; o1[2] = lnC; o1[3] = prior; o1[4] = lk; o1[5] = jac; o1[6] = post; o1[7] = 0.0;
+    }
+    new_status[chain] = st;
+  }
+}
+
 // ln r = beta_p (ln prior(y) - ln prior(x)) + beta_l (ln lik(y) - ln lik(x)) + ln(q |J|) (+ the change of the root-branch
 // Jacobian for proposals lifted with jacobianRootBranch, app/Definitions.hs:145-150); accept iff ln U < ln r.
 // beta: heat of the chain's current temperature slot (MC3: prior and likelihood; stepping stone: likelihood only);
@@ -374,9 +645,11 @@ mh_accept_kernel(double* __restrict__ states, const double* __restrict__ undo, c
                  const double* __restrict__ new_out, int* __restrict__ cur_status, const int* __restrict__ new_status,
                  int* __restrict__ accepted, unsigned long long* __restrict__ counters, const int* __restrict__ slot,
                  const double* __restrict__ ladder_prior, const double* __restrict__ ladder_lik, int chain_offset,
-                 int use_root_jacobian, uint64_t seed, uint32_t iteration, int S, int undo_stride, int B) {
+                 int use_root_jacobian, uint64_t seed, uint32_t iteration, int S, int undo_stride, int B, const MhYUpdate Y) {
   __shared__ int sh_acc;
   __shared__ int2 sh_rng[MH_MAX_OPS];
+  __shared__ int sh_k[DL_MAX_AB];
+  __shared__ double sh_d[DL_MAX_AB];
   const int b = blockIdx.x, tid = threadIdx.x;
   if (b >= B) return;
   const int4 m = meta[b];
@@ -408,6 +681,25 @@ mh_accept_kernel(double* __restrict__ states, const double* __restrict__ undo, c
   if (sh_acc) {
     if (tid < 8) cur_out[(size_t)b * 8 + tid] = new_out[(size_t)b * 8 + tid];
     if (tid == 8) cur_status[b] = new_status[b];
+    // keep the cached y = Sigma^-1 dx of the accepted state (incremental evaluation, mh_delta_kernel)
+    if (Y.mode == 2) {  // full evaluation: the contraction just produced it
+      const double* yn = Y.y_new + (size_t)b * Y.ldy;
+      double* yc = Y.y_cur + (size_t)b * Y.ldy;
+      for (int k = tid; k < Y.K; k += 256) yc[k] = yn[k];
+    } else if (Y.mode == 1) {  // y += sum_a delta_a P[k_a][:]   (P symmetric: rows, coalesced, L2-resident)
+      const int na = Y.dl_n[b];
+      for (int a = tid; a < na; a += 256) {
+        sh_k[a] = Y.dl_k[(size_t)b * DL_MAX_AB + a];
+        sh_d[a] = Y.dl_d[(size_t)b * DL_MAX_AB + a];
+      }
+      __syncthreads();
+      double* yc = Y.y_cur + (size_t)b * Y.ldy;
+      for (int k = tid; k < Y.K; k += 256) {
+        double acc = yc[k];
+        for (int a = 0; a < na; ++a) acc = fma(sh_d[a], Y.P[(size_t)sh_k[a] * Y.ldk + k], acc);
+        yc[k] = acc;
+      }
+    }
   } else if (m.x > 0) {
     double* row = states + (size_t)b * S;
     const double* ub = undo + (size_t)b * undo_stride;

@@ -674,6 +674,69 @@ def test_mh_and_mc3_do_not_depend_on_the_split_over_handles():
         ev.close()
 
 
+@pytest.mark.parametrize("clock", [0, 1, 2, 3])
+def test_incremental_evaluation_of_small_moves(clock):
+    """small moves scored from the cached y = Sigma^-1 dx (mh_delta_kernel) vs the same run with full evaluations, and vs
+    the oracle-driven host restatement: same decisions, same chains; values within accumulated rounding.  Includes chains in
+    the near-critical birth-death regime, a refresh every 5 steps, and proposals that fall back to the full evaluation."""
+    import mh_ref as R
+    n_leaves, B = 150, 48
+    md, h = synth.synthetic_model(n_leaves, seed=911 + clock, clock_model=clock, n_cal=4, n_con=3, n_brace=2)
+    X = synth.synthetic_states(md, h, B)
+    X[::7, 1] = X[::7, 0] + 3e-7                                # |lambda - mu| < 1e-6: literal D/E recursion
+    parent = [int(p) for p in md.parent]
+    braces = [[int(x) for x in md.brace_node[md.brace_off[b]:md.brace_off[b + 1]]] for b in range(md.n_brace)]
+    child, size, inner, inner_list = R.topology(parent)
+    small = [i for i in inner_list if 4 <= size[i] <= 32]
+    big = max(inner_list, key=lambda i: size[i])
+    orc = O.Oracle(md)
+    inc, full = binding.Evaluator(md), binding.Evaluator(md)
+    inc.mh_set_incremental(True, refresh_every=5)
+    full.mh_set_incremental(False)
+    inc.chains_set(X)
+    full.chains_set(X)
+    assert inc.mh_incremental_active() and not full.mh_incremental_active()
+    Xr = X.copy()
+    out_r, st_r = orc.eval(Xr)
+    assert (st_r[::7] & 8).all()
+    steps = [(R.SLIDE_NODE, -1, 0.01, 1.0, False), (R.SLIDE_NODE, 1, 0.01, 1.0, True), (R.SCALE_BRANCH, -1, 100.0, 10.0, False),
+             (R.SLIDE_NODE_CONTRA, -1, 0.1, 0.1, False), (R.SLIDE_BRACE, 0, 0.01, 0.01, False), (R.SLIDE_BRACE_CONTRA, 1, 0.1, 0.002, False),
+             (R.SCALE_SUBTREE, small[0], 0.01, 1.0, False), (R.SCALE_SUBTREE_CONTRA, small[-1], 0.1, 0.1, False),
+             (R.SCALE_RATE_SUBTREE, small[len(small) // 2], 100.0, 5.0, False),
+             (R.SCALE_SCALAR, 0, 10.0, 0.02, False),            # full path; keeps / moves chains in and out of near-criticality
+             (R.SCALE_SUBTREE, big, 0.01, 0.02, False),         # too large for the incremental path
+             (R.SLIDE_NODE, -1, 0.01, 1.0, False), (R.SCALE_NORM_TREE_CONTRA_M, 0, 100.0, 1.0, True),
+             (R.SLIDE_NODE_CONTRA, 1, 0.1, 0.3, True), (R.SCALE_BRANCH, 1, 100.0, 10.0, True), (R.SLIDE_NODE, -1, 0.01, 3.0, False),
+             (R.SLIDE_BRACE, -1, 0.01, 0.02, False), (R.SCALE_BRANCH, -1, 100.0, 30.0, False), (R.SLIDE_NODE, -1, 0.01, 0.5, False)]
+    n_acc = n_rej = 0
+    for it, (kind, node, param, tune, jac) in enumerate(steps):
+        a_i = inc.mh_step(kind, node, param, tune=tune, use_root_jacobian=jac, seed=31, iteration=it)
+        a_f = full.mh_step(kind, node, param, tune=tune, use_root_jacobian=jac, seed=31, iteration=it)
+        a_r = R.mh_step(orc, parent, Xr, out_r, st_r, kind, node, param, tune, jac, 31, it, braces=braces)
+        assert np.array_equal(a_i, a_f) and np.array_equal(a_i, a_r), (it, kind)
+        Xi, oi, si = inc.chains_get()
+        Xf, of, sf = full.chains_get()
+        assert np.array_equal(Xi, Xf) and np.array_equal(si, sf)
+        assert relerr(oi[:, :7], of[:, :7]).max() < 1e-11, (it, kind, relerr(oi[:, :7], of[:, :7]).max())
+        n_acc += int((a_r == 1).sum())
+        n_rej += int((a_r == 0).sum())
+    assert n_acc > 4 * B and n_rej > 2 * B
+    _mh_compare(inc, Xr, out_r, st_r)
+    # the cached values are those of the resident states
+    Xi, oi, si = inc.chains_get()
+    o2, s2 = inc.eval(Xi)
+    assert relerr(oi[:, :7], o2[:, :7]).max() < 1e-11 and np.array_equal(si, s2)
+    # an invalid chain at upload: that set of chains runs with full evaluations
+    Xbad = X.copy()
+    Xbad[3, 3 + inner_list[5]] = 2.0
+    inc.chains_set(Xbad)
+    assert not inc.mh_incremental_active()
+    inc.chains_set(X)
+    assert inc.mh_incremental_active()
+    inc.close()
+    full.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
