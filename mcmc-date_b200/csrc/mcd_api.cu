@@ -83,7 +83,7 @@ struct mcd_handle {
   bool inc_enabled = true;        // mcd_mh_set_incremental
   bool inc_ok = false;            // this resident set qualifies (large dense model, every chain's state valid)
   bool force_sym = false;         // value-only evaluations use the symmetric contraction (they must produce y, not L^T dx)
-  int inc_steps = 0, refresh_every = 512;
+  int inc_steps = 0, refresh_every = 512, ldyc = 0;
   int mc3_C = 0, mc3_n_global = 0, mc3_offset = 0;
   DevBuf d_nuts;                  // batched NUTS: trajectory ends, checkpoints, candidates, per-chain scalars
   size_t nuts_bytes = 0;
@@ -685,7 +685,8 @@ int mh_refresh(mcd_handle* h) {
   const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_chain_out.as<double>(), nullptr, h->d_chain_status.as<int32_t>(), st);
   h->force_sym = false;
   if (rc) return -1;
-  CU_TRY(h, cudaMemcpyAsync(h->d_chain_y.p, h->d_y.p, (size_t)n * h->ldy * 8, cudaMemcpyDeviceToDevice, st));
+  CU_TRY(h, cudaMemcpy2DAsync(h->d_chain_y.p, (size_t)h->ldyc * 8, h->d_y.p, (size_t)h->ldy * 8, (size_t)h->ldk * 8, n,
+                              cudaMemcpyDeviceToDevice, st));
   h->inc_steps = 0;
   return 0;
 }
@@ -727,7 +728,8 @@ int chains_set(mcd_handle* h, int n, const double* states) {
     CU_TRY(h, cudaMalloc(&h->d_lq.p, (size_t)cap * 8));
     CU_TRY(h, cudaMalloc(&h->d_accepted.p, (size_t)cap * 4));
     if (mh_incremental_capable(h)) {
-      CU_TRY(h, cudaMalloc(&h->d_chain_y.p, (size_t)cap * h->ldy * 8));
+      h->ldyc = h->ldk + 16;
+      CU_TRY(h, cudaMalloc(&h->d_chain_y.p, (size_t)cap * h->ldyc * 8));
       CU_TRY(h, cudaMalloc(&h->d_dl_n.p, (size_t)cap * 4));
       CU_TRY(h, cudaMalloc(&h->d_dl_k.p, (size_t)cap * DL_MAX_AB * 4));
       CU_TRY(h, cudaMalloc(&h->d_dl_d.p, (size_t)cap * DL_MAX_AB * 8));
@@ -826,7 +828,7 @@ int mh_check(mcd_handle* h, int kind, int node, double param, double tune) {
 }
 MhTopo mh_topo(mcd_handle* h) {
   MhTopo T;
-  T.N = h->N; T.S = h->S; T.n_inner_nonroot = h->n_inner_nonroot; T.root_r = h->dm.root_r; T.n_brace = h->dm.n_brace;
+  T.ldyc = h->ldyc; T.N = h->N; T.S = h->S; T.n_inner_nonroot = h->n_inner_nonroot; T.root_r = h->dm.root_r; T.n_brace = h->dm.n_brace;
   T.parent = h->dm.parent; T.child1 = h->d_mh_child1.as<int>(); T.sub_size = h->d_mh_size.as<int>();
   T.sub_inner = h->d_mh_inner_cnt.as<int>(); T.inner_list = h->d_mh_inner_list.as<int>();
   T.br_off = h->dm.br_off; T.br_node = h->dm.br_node;
@@ -845,10 +847,29 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
   P.kind = kind; P.node = node; P.use_root_jacobian = use_root_jacobian; P.pad = 0; P.param = param; P.tune = tune;
   P.seed = seed; P.iteration = iteration; P.chain_offset = h->mc3_offset;
   const MhTopo T = mh_topo(h);
+  const bool heated = h->mc3_C > 0;
+  static const bool unfused = getenv("MCD_MH_UNFUSED") != nullptr;  // A/B switch: three launches instead of one
+  if (inc && !unfused) {
+    const size_t smem = (size_t)8 * ((h->N + 31) / 32) * 4;
+#define MCD_LAUNCH_FUSED(CC)                                                                                               \
+  mh_fused_small_kernel<CC><<<(n + 7) / 8, 256, smem, st>>>(h->dm, T, P, h->d_P.as<double>(), h->d_chain.as<double>(),     \
+      h->d_chain_y.as<double>(), h->d_chain_out.as<double>(), h->d_chain_status.as<int32_t>(), h->d_accepted.as<int32_t>(), \
+      d_counters, heated ? h->d_slot.as<int>() : nullptr, h->d_ladder_p.as<double>(), h->d_ladder_l.as<double>(), n)
+    switch (h->dm.clock) {
+      case 0: MCD_LAUNCH_FUSED(0); break;
+      case 1: MCD_LAUNCH_FUSED(1); break;
+      case 2: MCD_LAUNCH_FUSED(2); break;
+      default: MCD_LAUNCH_FUSED(3); break;
+    }
+#undef MCD_LAUNCH_FUSED
+    h->launches += 1;
+    CU_TRY(h, cudaGetLastError());
+    return 0;
+  }
   mh_propose_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
                                        h->d_lq.as<double>(), T, P, h->undo_stride, n);
   MhYUpdate Y{};
-  Y.mode = 0; Y.K = h->K; Y.ldk = h->ldk; Y.ldy = h->ldy; Y.y_cur = h->d_chain_y.as<double>(); Y.y_new = h->d_y.as<double>();
+  Y.mode = 0; Y.K = h->K; Y.ldk = h->ldk; Y.ldy = h->ldy; Y.ldyc = h->ldyc; Y.y_cur = h->d_chain_y.as<double>(); Y.y_new = h->d_y.as<double>();
   Y.P = h->d_P.as<double>(); Y.dl_n = h->d_dl_n.as<int>(); Y.dl_k = h->d_dl_k.as<int>(); Y.dl_d = h->d_dl_d.as<double>();
   if (inc) {
     const size_t smem = (size_t)8 * ((h->N + 31) / 32) * 4;
@@ -873,7 +894,6 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
     if (rc) return -1;
     Y.mode = inc_mode ? 2 : 0;
   }
-  const bool heated = h->mc3_C > 0;
   mh_accept_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
                                       h->d_lq.as<double>(), h->d_chain_out.as<double>(), h->d_new_out.as<double>(),
                                       h->d_chain_status.as<int32_t>(), h->d_new_status.as<int32_t>(), h->d_accepted.as<int32_t>(),
@@ -1249,6 +1269,11 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
 #define MCD_SET_SMEM(CC)                                                                                          \
   cudaFuncSetAttribute(small_tree_fused_kernel<CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);     \
   cudaFuncSetAttribute(small_tree_fused_kernel<CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    MCD_SET_SMEM(0) MCD_SET_SMEM(1) MCD_SET_SMEM(2) MCD_SET_SMEM(3)
+#undef MCD_SET_SMEM
+#define MCD_SET_SMEM(CC)                                                                                  \
+  cudaFuncSetAttribute(mh_fused_small_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024); \
+  cudaFuncSetAttribute(mh_fused_small_kernel<CC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     MCD_SET_SMEM(0) MCD_SET_SMEM(1) MCD_SET_SMEM(2) MCD_SET_SMEM(3)
 #undef MCD_SET_SMEM
   }

@@ -60,6 +60,7 @@ struct MhOp {
 };
 struct MhTopo {
   int N, S, n_inner_nonroot, root_r, n_brace;
+  int ldyc;               // row stride of the cached y (not a power of two: the chains' rows must not alias in L2 / HBM)
   const int* parent;      // leaf flag in bit 31
   const int* child1;      // second child (the first child of an inner node i is i + 1), -1 on leaves
   const int* sub_size;    // nodes of the sub tree (= its branch labels, `length`)
@@ -126,6 +127,203 @@ __device__ __forceinline__ bool mh_gamma(double shape, double scale, uint64_t se
   return false;
 }
 
+// The scalar part of a proposal for chain b (one thread): draws, bounds, factors, ln(q |J|), and the move as a short list
+// of range operations on the state row.  Returns the number of operations (0 and *ok = false where the reference would
+// call `error`).  rate_sum: sum of the rates without the stem (MH_SCALE_VAR_TREE only).
+__device__ __noinline__ int mh_build_ops(const MhTopo& T, const MhParams& P, const double* row, int b, double rate_sum, MhOp* ops,
+                                         bool* ok_out, int* node_out, double* lq_out) {
+  const int N = T.N;
+  const int OH = 3, OR = 5 + N, OM = 3 + N, OV = 4 + N;  // offsets: heights, rates, rate mean, rate variance
+  const double* h = row + OH;
+  int nops = 0, node = P.node;
+  bool ok = true;
+  double lnq = 0.0, lnj = 0.0;
+  auto push = [&](int off, int cnt, int mode, double a, double bb) {
+    if (cnt <= 0) return;
+    ops[nops].off = off; ops[nops].cnt = cnt; ops[nops].mode = mode; ops[nops].a = a; ops[nops].b = bb;
+    ++nops;
+  };
+  const double s = P.param * P.tune;  // sd' = t * s (Internal.hs:117)
+  const uint32_t gb = (uint32_t)(P.chain_offset + b);
+  const double p = mh_uniform(P.seed, gb, P.iteration, 0u);
+  const int kind = P.kind;
+  const bool node_kind = kind == MH_SLIDE_NODE || kind == MH_SCALE_SUBTREE || kind == MH_SCALE_RATE_SUBTREE ||
+                         kind == MH_SLIDE_NODE_CONTRA || kind == MH_SCALE_SUBTREE_CONTRA;
+  if (node < 0) {
+    const double un = mh_uniform(P.seed, gb, P.iteration, 2u);
+    if (node_kind) {
+      int pick = (int)(un * (double)T.n_inner_nonroot);
+      if (pick >= T.n_inner_nonroot) pick = T.n_inner_nonroot - 1;
+      node = T.inner_list[pick];
+    } else if (kind == MH_SCALE_BRANCH) {
+      int pick = (int)(un * (double)(N - 1));
+      if (pick >= N - 1) pick = N - 2;
+      node = 1 + pick;
+    } else if (kind == MH_SLIDE_BRACE || kind == MH_SLIDE_BRACE_CONTRA) {
+      int pick = (int)(un * (double)T.n_brace);
+      if (pick >= T.n_brace) pick = T.n_brace - 1;
+      node = pick;
+    }
+  }
+  const int j = node;
+  // multiplier u ~ Gamma(k / t, t / k) and its Hastings factor pdf(1/u) / pdf(u)  (genericContinuous)
+  double u = 1.0;
+  const bool mult_kind = kind == MH_SCALE_BRANCH || kind == MH_SCALE_RATE_SUBTREE || kind == MH_SCALE_NORM_TREE_CONTRA_M ||
+                         kind == MH_SCALE_NORM_TREE_CONTRA_H || kind == MH_SCALE_VAR_TREE || kind == MH_SCALE_VAR_TREE_AUTO ||
+                         kind == MH_SCALE_SCALAR || kind == MH_SCALE_H_M_CONTRA;
+  if (mult_kind) {
+    const double kk = P.param / P.tune, th = P.tune / P.param;
+    ok = mh_gamma(kk, th, P.seed, gb, P.iteration, &u);
+    if (ok) lnq = -2.0 * (kk - 1.0) * log(u) - (1.0 / u - u) / th;
+  }
+  if (ok) switch (kind) {
+    case MH_SLIDE_NODE:
+    case MH_SLIDE_NODE_CONTRA: {
+      const int c0 = j + 1, c1 = T.child1[j];
+      const double hj = h[j], hP = h[T.parent[j] & 0x7fffffff], h0 = h[c0], h1 = h[c1];
+      double hn;
+      ok = mh_truncated_normal(hj, s, fmax(h0, h1), hP, p, &hn, &lnq);  // hbdMaximumChildrenHeight .. hbdParentHeight
+      if (!ok) break;
+      push(OH + j, 1, OP_SET, 0.0, hn);
+      if (kind == MH_SLIDE_NODE_CONTRA) {  // rates scale inversely to their branches' lengths
+        const double xiS = (hP - hj) / (hP - hn), xi0 = (hj - h0) / (hn - h0), xi1 = (hj - h1) / (hn - h1);
+        push(OR + j, 1, OP_MUL, xiS, 0.0);
+        push(OR + c0, 1, OP_MUL, xi0, 0.0);
+        push(OR + c1, 1, OP_MUL, xi1, 0.0);
+        lnj = (log(xi0) + log(xi1)) + log(xiS);
+      }
+    } break;
+    case MH_SCALE_SUBTREE:
+    case MH_SCALE_SUBTREE_CONTRA: {
+      const double hj = h[j], hP = h[T.parent[j] & 0x7fffffff];
+      double hn;
+      ok = mh_truncated_normal(hj, s, 0.0, hP, p, &hn, &lnq);
+      if (!ok) break;
+      const double xi = hn / hj;
+      const int cnt = T.sub_size[j];
+      push(OH + j, 1, OP_SET, 0.0, hn);  // the sub tree's root gets the sampled height itself (scaleUltrametricTreeF)
+      push(OH + j + 1, cnt - 1, OP_MUL, xi, 0.0);
+      if (kind == MH_SCALE_SUBTREE) {
+        lnj = (double)(T.sub_inner[j] - 1) * log(xi);
+      } else {
+        const double xiR = 1.0 / xi, xiS = (hP - hj) / (hP - hn);
+        push(OR + j + 1, cnt - 1, OP_MUL, xiR, 0.0);
+        push(OR + j, 1, OP_MUL, xiS, 0.0);
+        lnj = (double)(T.sub_inner[j] - cnt) * log(xi) + log(xiS);
+      }
+    } break;
+    case MH_PULLEY: {
+      const int l = 1, r = T.root_r;
+      const double ht = h[0], hL = h[l], hR = h[r], brL = ht - hL, brR = ht - hR;
+      if (!(brL > 0.0) || !(brR > 0.0)) { ok = false; break; }
+      const double a = -fmin(brL, ht - brR), bb = fmin(brR, ht - brL);
+      double uu;
+      ok = mh_truncated_normal(0.0, s, a, bb, p, &uu, &lnq);
+      if (!ok) break;
+      const double hLn = hL - uu, hRn = hR + uu, xiL = hLn / hL, xiR = hRn / hR;
+      push(OH + l, 1, OP_SET, 0.0, hLn);
+      push(OH + l + 1, T.sub_size[l] - 1, OP_MUL, xiL, 0.0);
+      push(OH + r, 1, OP_SET, 0.0, hRn);
+      push(OH + r + 1, T.sub_size[r] - 1, OP_MUL, xiR, 0.0);
+      lnj = (double)(T.sub_inner[l] - 1) * log(xiL) + (double)(T.sub_inner[r] - 1) * log(xiR);
+    } break;
+    case MH_SLIDE_BRACE:
+    case MH_SLIDE_BRACE_CONTRA: {
+      const int o0 = T.br_off[j], o1 = T.br_off[j + 1];
+      double lo = -CUDART_INF, hi = CUDART_INF;
+      for (int o = o0; o < o1; ++o) {
+        const int x = T.br_node[o];
+        const double hx = h[x];
+        lo = fmax(lo, fmax(h[x + 1], h[T.child1[x]]) - hx);
+        hi = fmin(hi, h[T.parent[x] & 0x7fffffff] - hx);
+      }
+      double dl;
+      ok = mh_truncated_normal(0.0, s, lo, hi, p, &dl, &lnq);
+      if (!ok) break;
+      for (int o = o0; o < o1; ++o) push(OH + T.br_node[o], 1, OP_ADD, 0.0, dl);
+      if (kind == MH_SLIDE_BRACE_CONTRA) {
+        for (int o = o0; o < o1; ++o) {
+          const int x = T.br_node[o], c0 = x + 1, c1 = T.child1[x];
+          const double hx = h[x], hP = h[T.parent[x] & 0x7fffffff];
+          const double xiS = (hP - hx) / (hP - hx - dl), xi0 = (hx - h[c0]) / (hx + dl - h[c0]), xi1 = (hx - h[c1]) / (hx + dl - h[c1]);
+          push(OR + x, 1, OP_MUL, xiS, 0.0);
+          push(OR + c0, 1, OP_MUL, xi0, 0.0);
+          push(OR + c1, 1, OP_MUL, xi1, 0.0);
+          lnj += (log(xi0) + log(xi1)) + log(xiS);
+        }
+      }
+    } break;
+    case MH_SCALE_BRANCH:
+      push(OR + j, 1, OP_MUL, u, 0.0);
+      lnj = -log(u);  // scaleUnbiased: Jacobian 1 / u
+      break;
+    case MH_SCALE_RATE_SUBTREE:
+      push(OR + j, T.sub_size[j], OP_MUL, u, 0.0);  // stem included (scaleUnconstrainedTreeF)
+      lnj = (double)(T.sub_size[j] - 2) * log(u);
+      break;
+    case MH_SCALE_NORM_TREE_CONTRA_M:
+    case MH_SCALE_NORM_TREE_CONTRA_H:
+      push(kind == MH_SCALE_NORM_TREE_CONTRA_M ? OM : 2, 1, OP_DIV, u, 0.0);
+      push(OR + 1, N - 1, OP_MUL, u, 0.0);  // without the stem
+      lnj = (double)(N - 1 - 3) * log(u);
+      break;
+    case MH_SCALE_VAR_TREE: {
+      const double n = (double)(N - 1), n1 = 1.0 / n, mean = rate_sum / n;
+      push(OV, 1, OP_MUL, u * u, 0.0);
+      push(OR + 1, N - 1, OP_AFFINE_POS, u, mean);
+      lnj = n * log(u - n1 * u + n1);
+    } break;
+    case MH_SCALE_VAR_TREE_AUTO:
+      // r' = y_parent + u (r - r_parent) down the tree telescopes to m + u (r - m): closed form of scaleF
+      push(OV, 1, OP_MUL, u * u, 0.0);
+      push(OR + 1, N - 1, OP_AFFINE_POS, u, row[OM]);
+      lnj = (double)(N - 1) * log(u);
+      break;
+    case MH_SLIDE_ROOT_CONTRA: {
+      const int l = 1, r = T.root_r;
+      const double H = row[2], hL = h[l], hR = h[r];
+      if (fabs(h[0] - 1.0) > 1e-14) { ok = false; break; }
+      double Hn;
+      ok = mh_truncated_normal(H, s, H * fmax(hL, hR), CUDART_INF, p, &Hn, &lnq);
+      if (!ok) break;
+      const double uu = Hn / H, xiL = (1.0 - hL) / (uu - hL), xiR = (1.0 - hR) / (uu - hR);
+      push(2, 1, OP_SET, 0.0, Hn);
+      push(OH + 1, N - 1, OP_DIV, uu, 0.0);
+      push(OR + l, 1, OP_MUL, xiL, 0.0);
+      push(OR + r, 1, OP_MUL, xiR, 0.0);
+      lnj = -(double)T.sub_inner[0] * log(uu) + (log(xiL) + log(xiR));
+    } break;
+    case MH_SCALE_RATES_TREE_CONTRA: {
+      const int nn = T.sub_inner[0] - 1;
+      if (nn < 1) { ok = false; break; }
+      const double hc = fmax(h[1], h[T.root_r]);
+      double hn;
+      ok = mh_truncated_normal(hc, s, 0.0, h[0], p, &hn, &lnq);
+      if (!ok) break;
+      const double xi = hn / hc;
+      push(OH + 1, N - 1, OP_MUL, xi, 0.0);
+      push(0, 2, OP_DIV, xi, 0.0);  // lambda, mu
+      lnj = (double)(nn - 1 - 2) * log(xi);
+    } break;
+    case MH_SCALE_SCALAR: {
+      const int off = j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 2 : j == 3 ? OM : OV;
+      push(off, 1, OP_MUL, u, 0.0);
+      lnj = -log(u);
+    } break;
+    case MH_SCALE_H_M_CONTRA:
+      push(2, 1, OP_MUL, u, 0.0);
+      push(OM, 1, OP_DIV, u, 0.0);
+      lnj = -log(u * u);
+      break;
+    default: ok = false; break;
+  }
+  if (!ok) nops = 0;
+  *ok_out = ok;
+  *node_out = node;
+  *lq_out = ok ? lnq + lnj : 0.0;
+  return nops;
+}
+
 // Apply proposal P to every chain IN PLACE.  One CTA per chain: thread 0 draws and turns the move into a short list of
 // range operations on the state row, then all threads save the old values to the undo log and apply them.
 // undo[b][..]: old values, ranges packed in order; rng[b][o] = (offset, count); meta[b] = (ranges, validity, node, -);
@@ -140,7 +338,8 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
   if (b >= B) return;
   const int N = T.N, S = T.S;
   double* row = states + (size_t)b * S;
-  const int OH = 3, OR = 5 + N, OM = 3 + N, OV = 4 + N;  // offsets: heights, rates, rate mean, rate variance
+  const int OR = 5 + N;
+  if (tid == 0) sh_sum = 0.0;
   if (P.kind == MH_SCALE_VAR_TREE) {  // sample mean of the rates without the stem (scaleVarianceAndTreeF)
     double s = 0.0;
     for (int i = 1 + tid; i < N; i += 256) s += row[OR + i];
@@ -151,193 +350,13 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
     __syncthreads();
   }
   if (tid == 0) {
-    const double* h = row + OH;
-    int nops = 0, node = P.node;
-    bool ok = true;
-    double lnq = 0.0, lnj = 0.0;
-    auto push = [&](int off, int cnt, int mode, double a, double bb) {
-      if (cnt <= 0) return;
-      ops[nops].off = off; ops[nops].cnt = cnt; ops[nops].mode = mode; ops[nops].a = a; ops[nops].b = bb;
-      ++nops;
-    };
-    const double s = P.param * P.tune;  // sd' = t * s (Internal.hs:117)
-    const uint32_t gb = (uint32_t)(P.chain_offset + b);
-    const double p = mh_uniform(P.seed, gb, P.iteration, 0u);
-    const int kind = P.kind;
-    const bool node_kind = kind == MH_SLIDE_NODE || kind == MH_SCALE_SUBTREE || kind == MH_SCALE_RATE_SUBTREE ||
-                           kind == MH_SLIDE_NODE_CONTRA || kind == MH_SCALE_SUBTREE_CONTRA;
-    if (node < 0) {
-      const double un = mh_uniform(P.seed, gb, P.iteration, 2u);
-      if (node_kind) {
-        int pick = (int)(un * (double)T.n_inner_nonroot);
-        if (pick >= T.n_inner_nonroot) pick = T.n_inner_nonroot - 1;
-        node = T.inner_list[pick];
-      } else if (kind == MH_SCALE_BRANCH) {
-        int pick = (int)(un * (double)(N - 1));
-        if (pick >= N - 1) pick = N - 2;
-        node = 1 + pick;
-      } else if (kind == MH_SLIDE_BRACE || kind == MH_SLIDE_BRACE_CONTRA) {
-        int pick = (int)(un * (double)T.n_brace);
-        if (pick >= T.n_brace) pick = T.n_brace - 1;
-        node = pick;
-      }
-    }
-    const int j = node;
-    // multiplier u ~ Gamma(k / t, t / k) and its Hastings factor pdf(1/u) / pdf(u)  (genericContinuous)
-    double u = 1.0;
-    const bool mult_kind = kind == MH_SCALE_BRANCH || kind == MH_SCALE_RATE_SUBTREE || kind == MH_SCALE_NORM_TREE_CONTRA_M ||
-                           kind == MH_SCALE_NORM_TREE_CONTRA_H || kind == MH_SCALE_VAR_TREE || kind == MH_SCALE_VAR_TREE_AUTO ||
-                           kind == MH_SCALE_SCALAR || kind == MH_SCALE_H_M_CONTRA;
-    if (mult_kind) {
-      const double kk = P.param / P.tune, th = P.tune / P.param;
-      ok = mh_gamma(kk, th, P.seed, gb, P.iteration, &u);
-      if (ok) lnq = -2.0 * (kk - 1.0) * log(u) - (1.0 / u - u) / th;
-    }
-    if (ok) switch (kind) {
-      case MH_SLIDE_NODE:
-      case MH_SLIDE_NODE_CONTRA: {
-        const int c0 = j + 1, c1 = T.child1[j];
-        const double hj = h[j], hP = h[T.parent[j] & 0x7fffffff], h0 = h[c0], h1 = h[c1];
-        double hn;
-        ok = mh_truncated_normal(hj, s, fmax(h0, h1), hP, p, &hn, &lnq);  // hbdMaximumChildrenHeight .. hbdParentHeight
-        if (!ok) break;
-        push(OH + j, 1, OP_SET, 0.0, hn);
-        if (kind == MH_SLIDE_NODE_CONTRA) {  // rates scale inversely to their branches' lengths
-          const double xiS = (hP - hj) / (hP - hn), xi0 = (hj - h0) / (hn - h0), xi1 = (hj - h1) / (hn - h1);
-          push(OR + j, 1, OP_MUL, xiS, 0.0);
-          push(OR + c0, 1, OP_MUL, xi0, 0.0);
-          push(OR + c1, 1, OP_MUL, xi1, 0.0);
-          lnj = (log(xi0) + log(xi1)) + log(xiS);
-        }
-      } break;
-      case MH_SCALE_SUBTREE:
-      case MH_SCALE_SUBTREE_CONTRA: {
-        const double hj = h[j], hP = h[T.parent[j] & 0x7fffffff];
-        double hn;
-        ok = mh_truncated_normal(hj, s, 0.0, hP, p, &hn, &lnq);
-        if (!ok) break;
-        const double xi = hn / hj;
-        const int cnt = T.sub_size[j];
-        push(OH + j, 1, OP_SET, 0.0, hn);  // the sub tree's root gets the sampled height itself (scaleUltrametricTreeF)
-        push(OH + j + 1, cnt - 1, OP_MUL, xi, 0.0);
-        if (kind == MH_SCALE_SUBTREE) {
-          lnj = (double)(T.sub_inner[j] - 1) * log(xi);
-        } else {
-          const double xiR = 1.0 / xi, xiS = (hP - hj) / (hP - hn);
-          push(OR + j + 1, cnt - 1, OP_MUL, xiR, 0.0);
-          push(OR + j, 1, OP_MUL, xiS, 0.0);
-          lnj = (double)(T.sub_inner[j] - cnt) * log(xi) + log(xiS);
-        }
-      } break;
-      case MH_PULLEY: {
-        const int l = 1, r = T.root_r;
-        const double ht = h[0], hL = h[l], hR = h[r], brL = ht - hL, brR = ht - hR;
-        if (!(brL > 0.0) || !(brR > 0.0)) { ok = false; break; }
-        const double a = -fmin(brL, ht - brR), bb = fmin(brR, ht - brL);
-        double uu;
-        ok = mh_truncated_normal(0.0, s, a, bb, p, &uu, &lnq);
-        if (!ok) break;
-        const double hLn = hL - uu, hRn = hR + uu, xiL = hLn / hL, xiR = hRn / hR;
-        push(OH + l, 1, OP_SET, 0.0, hLn);
-        push(OH + l + 1, T.sub_size[l] - 1, OP_MUL, xiL, 0.0);
-        push(OH + r, 1, OP_SET, 0.0, hRn);
-        push(OH + r + 1, T.sub_size[r] - 1, OP_MUL, xiR, 0.0);
-        lnj = (double)(T.sub_inner[l] - 1) * log(xiL) + (double)(T.sub_inner[r] - 1) * log(xiR);
-      } break;
-      case MH_SLIDE_BRACE:
-      case MH_SLIDE_BRACE_CONTRA: {
-        const int o0 = T.br_off[j], o1 = T.br_off[j + 1];
-        double lo = -CUDART_INF, hi = CUDART_INF;
-        for (int o = o0; o < o1; ++o) {
-          const int x = T.br_node[o];
-          const double hx = h[x];
-          lo = fmax(lo, fmax(h[x + 1], h[T.child1[x]]) - hx);
-          hi = fmin(hi, h[T.parent[x] & 0x7fffffff] - hx);
-        }
-        double dl;
-        ok = mh_truncated_normal(0.0, s, lo, hi, p, &dl, &lnq);
-        if (!ok) break;
-        for (int o = o0; o < o1; ++o) push(OH + T.br_node[o], 1, OP_ADD, 0.0, dl);
-        if (kind == MH_SLIDE_BRACE_CONTRA) {
-          for (int o = o0; o < o1; ++o) {
-            const int x = T.br_node[o], c0 = x + 1, c1 = T.child1[x];
-            const double hx = h[x], hP = h[T.parent[x] & 0x7fffffff];
-            const double xiS = (hP - hx) / (hP - hx - dl), xi0 = (hx - h[c0]) / (hx + dl - h[c0]), xi1 = (hx - h[c1]) / (hx + dl - h[c1]);
-            push(OR + x, 1, OP_MUL, xiS, 0.0);
-            push(OR + c0, 1, OP_MUL, xi0, 0.0);
-            push(OR + c1, 1, OP_MUL, xi1, 0.0);
-            lnj += (log(xi0) + log(xi1)) + log(xiS);
-          }
-        }
-      } break;
-      case MH_SCALE_BRANCH:
-        push(OR + j, 1, OP_MUL, u, 0.0);
-        lnj = -log(u);  // scaleUnbiased: Jacobian 1 / u
-        break;
-      case MH_SCALE_RATE_SUBTREE:
-        push(OR + j, T.sub_size[j], OP_MUL, u, 0.0);  // stem included (scaleUnconstrainedTreeF)
-        lnj = (double)(T.sub_size[j] - 2) * log(u);
-        break;
-      case MH_SCALE_NORM_TREE_CONTRA_M:
-      case MH_SCALE_NORM_TREE_CONTRA_H:
-        push(kind == MH_SCALE_NORM_TREE_CONTRA_M ? OM : 2, 1, OP_DIV, u, 0.0);
-        push(OR + 1, N - 1, OP_MUL, u, 0.0);  // without the stem
-        lnj = (double)(N - 1 - 3) * log(u);
-        break;
-      case MH_SCALE_VAR_TREE: {
-        const double n = (double)(N - 1), n1 = 1.0 / n, mean = sh_sum / n;
-        push(OV, 1, OP_MUL, u * u, 0.0);
-        push(OR + 1, N - 1, OP_AFFINE_POS, u, mean);
-        lnj = n * log(u - n1 * u + n1);
-      } break;
-      case MH_SCALE_VAR_TREE_AUTO:
-        // r' = y_parent + u (r - r_parent) down the tree telescopes to m + u (r - m): closed form of scaleF
-        push(OV, 1, OP_MUL, u * u, 0.0);
-        push(OR + 1, N - 1, OP_AFFINE_POS, u, row[OM]);
-        lnj = (double)(N - 1) * log(u);
-        break;
-      case MH_SLIDE_ROOT_CONTRA: {
-        const int l = 1, r = T.root_r;
-        const double H = row[2], hL = h[l], hR = h[r];
-        if (fabs(h[0] - 1.0) > 1e-14) { ok = false; break; }
-        double Hn;
-        ok = mh_truncated_normal(H, s, H * fmax(hL, hR), CUDART_INF, p, &Hn, &lnq);
-        if (!ok) break;
-        const double uu = Hn / H, xiL = (1.0 - hL) / (uu - hL), xiR = (1.0 - hR) / (uu - hR);
-        push(2, 1, OP_SET, 0.0, Hn);
-        push(OH + 1, N - 1, OP_DIV, uu, 0.0);
-        push(OR + l, 1, OP_MUL, xiL, 0.0);
-        push(OR + r, 1, OP_MUL, xiR, 0.0);
-        lnj = -(double)T.sub_inner[0] * log(uu) + (log(xiL) + log(xiR));
-      } break;
-      case MH_SCALE_RATES_TREE_CONTRA: {
-        const int nn = T.sub_inner[0] - 1;
-        if (nn < 1) { ok = false; break; }
-        const double hc = fmax(h[1], h[T.root_r]);
-        double hn;
-        ok = mh_truncated_normal(hc, s, 0.0, h[0], p, &hn, &lnq);
-        if (!ok) break;
-        const double xi = hn / hc;
-        push(OH + 1, N - 1, OP_MUL, xi, 0.0);
-        push(0, 2, OP_DIV, xi, 0.0);  // lambda, mu
-        lnj = (double)(nn - 1 - 2) * log(xi);
-      } break;
-      case MH_SCALE_SCALAR: {
-        const int off = j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 2 : j == 3 ? OM : OV;
-        push(off, 1, OP_MUL, u, 0.0);
-        lnj = -log(u);
-      } break;
-      case MH_SCALE_H_M_CONTRA:
-        push(2, 1, OP_MUL, u, 0.0);
-        push(OM, 1, OP_DIV, u, 0.0);
-        lnj = -log(u * u);
-        break;
-      default: ok = false; break;
-    }
-    if (!ok) nops = 0;
+    bool ok;
+    int node;
+    double lqv;
+    const int nops = mh_build_ops(T, P, row, b, sh_sum, ops, &ok, &node, &lqv);
     sh_nops = nops;
     meta[b] = make_int4(nops, ok ? MH_ST_OK : MH_ST_INVALID, node, 0);
-    lq[b] = ok ? lnq + lnj : 0.0;
+    lq[b] = lqv;
   }
   __syncthreads();
   const int nops = sh_nops;
@@ -377,7 +396,7 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
 enum { DL_MAX_CHG = 96, DL_MAX_AB = 128, DL_SUBTREE_H = 32, DL_SUBTREE_R = 64 };
 struct MhYUpdate {
   int mode;  // 0: no cached y; 1: rank-|A| update from the delta list; 2: copy the freshly contracted row
-  int K, ldk, ldy;
+  int K, ldk, ldy, ldyc;  // ldy: stride of y_new (contraction output), ldyc: stride of y_cur
   double* y_cur;
   const double* y_new;
   const double* P;
@@ -402,50 +421,49 @@ __device__ __forceinline__ double mh_clock_term(double r, double t, double v, do
   }
 }
 
-// One warp per chain, eight chains per CTA.  Dynamic shared memory per warp: the bitmap of affected branches.
-template <int CLOCK>
-__global__ void __launch_bounds__(256)
-mh_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict__ P, const double* __restrict__ states,
-                const double* __restrict__ undo, const int2* __restrict__ rng, const int4* __restrict__ meta,
-                const double* __restrict__ y_cur, const double* __restrict__ cur_out, const int* __restrict__ cur_status,
-                double* __restrict__ new_out, int* __restrict__ new_status, int* __restrict__ dl_n, int* __restrict__ dl_k,
-                double* __restrict__ dl_d, int undo_stride, int B) {
-  extern __shared__ unsigned dl_bitmaps[];
-  __shared__ int s_off[8][DL_MAX_CHG];
-  __shared__ double s_old[8][DL_MAX_CHG];
-  __shared__ int s_ab[8][DL_MAX_AB], s_k[8][DL_MAX_AB];
-  __shared__ double s_d[8][DL_MAX_AB];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chain = blockIdx.x * 8 + warp;
-  if (chain >= B) return;
-  const int4 mt = meta[chain];
-  if (mt.y != MH_ST_OK || mt.x == 0) {  // rejected by the accept kernel whatever new_out says
-    if (lane == 0) dl_n[chain] = 0;
-    return;
+// y[0..ldk) += sum_a d[a] P[k[a]][0..ldk) by a group of G threads.  Rows of P (ldk a multiple of 16, zero padded) and y are
+// 16-byte aligned: 128-bit accesses, four of them in flight per thread and row.  Measured on the benchmark shape this
+// update is 2/3 of a small-move step (y: HBM read-modify-write, rows of P: L2) -- issuing the loads of four rows together
+// was slower (redundant row traffic when fewer than four branches changed).
+template <int G>
+__device__ __forceinline__ void mh_update_y(double* y, const double* __restrict__ P, int ldk, const int* k, const double* d, int n,
+                                            int lane) {
+  constexpr int U = 4;
+  const int n2 = ldk >> 1;
+  double2* y2 = reinterpret_cast<double2*>(y);
+  for (int c0 = lane; c0 < n2; c0 += G * U) {
+    double2 acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = c0 + u * G < n2 ? y2[c0 + u * G] : make_double2(0.0, 0.0);
+    for (int a = 0; a < n; ++a) {
+      const double2* row = reinterpret_cast<const double2*>(P + (size_t)k[a] * ldk);
+      const double da = d[a];
+      double2 p[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) p[u] = c0 + u * G < n2 ? __ldg(row + c0 + u * G) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[u].x = fma(da, p[u].x, acc[u].x);
+        acc[u].y = fma(da, p[u].y, acc[u].y);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c0 + u * G < n2) y2[c0 + u * G] = acc[u];
   }
+}
+
+// The evaluation proper, shared by mh_delta_kernel and the fused small-move kernel: one warp, the raw change list
+// (offset, old value; first record of an offset = its old value) in shared memory, the state row already modified.
+// Results: ln-posterior parts of the proposed state in o1[0..7] and its status (lane 0), the residual changes
+// (abk, abd)[0..n_ab) for the update of y.
+template <int CLOCK>
+__device__ __forceinline__ void mh_delta_core(const DevModel& M, const MhTopo& T, const double* __restrict__ P, const double* row,
+                                              const int* c_off, const double* c_old, int n_raw, unsigned* bm, int* ab, int* abk,
+                                              double* abd, const double* __restrict__ y, const double* o0, int cur_st, int lane,
+                                              double* o1, int* st_out, int* n_ab_out) {
   const int N = M.N, OH = 3, OR = 5 + N;
   const int nwords = (N + 31) >> 5;
-  unsigned* bm = dl_bitmaps + (size_t)warp * nwords;
-  int* c_off = s_off[warp];
-  double* c_old = s_old[warp];
-  int* ab = s_ab[warp];
-  int* abk = s_k[warp];
-  double* abd = s_d[warp];
-  const double* row = states + (size_t)chain * M.S;
-  // 1. raw change list from the undo log (an entry touched twice appears twice: the FIRST record holds the old value)
-  int n_raw = 0;
-  {
-    const double* ub = undo + (size_t)chain * undo_stride;
-    for (int o = 0; o < mt.x; ++o) {
-      const int2 r = rng[(size_t)chain * MH_MAX_OPS + o];
-      for (int i = lane; i < r.y && n_raw + i < DL_MAX_CHG; i += 32) {
-        c_off[n_raw + i] = r.x + i;
-        c_old[n_raw + i] = ub[n_raw + i];
-      }
-      n_raw += r.y;
-    }
-    if (n_raw > DL_MAX_CHG) n_raw = DL_MAX_CHG;  // the host only routes small moves here
-  }
   for (int w = lane; w < nwords; w += 32) bm[w] = 0u;
   __syncwarp();
   auto old_val = [&](int off) -> double {
@@ -504,7 +522,6 @@ mh_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict__ P, 
   const double lgk_v = CLOCK == 0 ? lgamma(1.0 / v) : 0.0, ln_v = log(v);
   bool bad = false;
   double d_clock = 0.0, q1 = 0.0;
-  const double* y = y_cur + (size_t)chain * M.ldy;
   for (int a = lane; a < n_ab; a += 32) {
     const int i = ab[a], p = T.parent[i] & 0x7fffffff;
     const double hi_n = row[OH + i], hp_n = row[OH + p], r_n = row[OR + i];
@@ -590,16 +607,10 @@ mh_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict__ P, 
     d_A += __shfl_xor_sync(0xffffffffu, d_A, o);
   }
   bad = __any_sync(0xffffffffu, bad);
-  for (int a = lane; a < n_ab; a += 32) {
-    dl_k[(size_t)chain * DL_MAX_AB + a] = abk[a];
-    dl_d[(size_t)chain * DL_MAX_AB + a] = abd[a];
-  }
+  *n_ab_out = n_ab;
   if (lane == 0) {
-    dl_n[chain] = n_ab;
-    const double* o0 = cur_out + (size_t)chain * 8;
-    double* o1 = new_out + (size_t)chain * 8;
     const double NINF = -CUDART_INF;
-    int st = cur_status[chain] & ST_NEARCRIT;
+    int st = cur_st & ST_NEARCRIT;
     if (bad) {  // a non-positive branch or rate: probability zero (or NaN) -- rejected either way
       o1[0] = o0[0]; o1[1] = NINF; o1[2] = NINF; o1[3] = NINF; o1[4] = o0[4]; o1[5] = o0[5]; o1[6] = NINF; o1[7] = 0.0;
       st |= ST_ZERO;
@@ -630,6 +641,64 @@ mh_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict__ P, 
       if (post != post) st |= ST_NAN;
       o1[0] = lnA; o1[1] = lnB; o1[2] = lnC; o1[3] = prior; o1[4] = lk; o1[5] = jac; o1[6] = post; o1[7] = 0.0;
     }
+    *st_out = st;
+  }
+}
+
+// One warp per chain, eight chains per CTA.  Dynamic shared memory per warp: the bitmap of affected branches.
+template <int CLOCK>
+__global__ void __launch_bounds__(256)
+mh_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict__ P, const double* __restrict__ states,
+                const double* __restrict__ undo, const int2* __restrict__ rng, const int4* __restrict__ meta,
+                const double* __restrict__ y_cur, const double* __restrict__ cur_out, const int* __restrict__ cur_status,
+                double* __restrict__ new_out, int* __restrict__ new_status, int* __restrict__ dl_n, int* __restrict__ dl_k,
+                double* __restrict__ dl_d, int undo_stride, int B) {
+  extern __shared__ unsigned dl_bitmaps[];
+  __shared__ int s_off[8][DL_MAX_CHG];
+  __shared__ double s_old[8][DL_MAX_CHG];
+  __shared__ int s_ab[8][DL_MAX_AB], s_k[8][DL_MAX_AB];
+  __shared__ double s_d[8][DL_MAX_AB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chain = blockIdx.x * 8 + warp;
+  if (chain >= B) return;
+  const int4 mt = meta[chain];
+  if (mt.y != MH_ST_OK || mt.x == 0) {  // rejected by the accept kernel whatever new_out says
+    if (lane == 0) dl_n[chain] = 0;
+    return;
+  }
+  const int nwords = (M.N + 31) >> 5;
+  unsigned* bm = dl_bitmaps + (size_t)warp * nwords;
+  int* c_off = s_off[warp];
+  double* c_old = s_old[warp];
+  int* ab = s_ab[warp];
+  int* abk = s_k[warp];
+  double* abd = s_d[warp];
+  const double* row = states + (size_t)chain * M.S;
+  // 1. raw change list from the undo log (an entry touched twice appears twice: the FIRST record holds the old value)
+  int n_raw = 0;
+  {
+    const double* ub = undo + (size_t)chain * undo_stride;
+    for (int o = 0; o < mt.x; ++o) {
+      const int2 r = rng[(size_t)chain * MH_MAX_OPS + o];
+      for (int i = lane; i < r.y && n_raw + i < DL_MAX_CHG; i += 32) {
+        c_off[n_raw + i] = r.x + i;
+        c_old[n_raw + i] = ub[n_raw + i];
+      }
+      n_raw += r.y;
+    }
+    if (n_raw > DL_MAX_CHG) n_raw = DL_MAX_CHG;  // the host only routes small moves here
+  }
+  double o1[8];
+  int st = 0, n_ab = 0;
+  mh_delta_core<CLOCK>(M, T, P, row, c_off, c_old, n_raw, bm, ab, abk, abd, y_cur + (size_t)chain * T.ldyc,
+                       cur_out + (size_t)chain * 8, cur_status[chain], lane, o1, &st, &n_ab);
+  for (int a = lane; a < n_ab; a += 32) {
+    dl_k[(size_t)chain * DL_MAX_AB + a] = abk[a];
+    dl_d[(size_t)chain * DL_MAX_AB + a] = abd[a];
+  }
+  if (lane == 0) {
+    dl_n[chain] = n_ab;
+    for (int j = 0; j < 8; ++j) new_out[(size_t)chain * 8 + j] = o1[j];
     new_status[chain] = st;
   }
 }
@@ -684,7 +753,7 @@ mh_accept_kernel(double* __restrict__ states, const double* __restrict__ undo, c
     // keep the cached y = Sigma^-1 dx of the accepted state (incremental evaluation, mh_delta_kernel)
     if (Y.mode == 2) {  // full evaluation: the contraction just produced it
       const double* yn = Y.y_new + (size_t)b * Y.ldy;
-      double* yc = Y.y_cur + (size_t)b * Y.ldy;
+      double* yc = Y.y_cur + (size_t)b * Y.ldyc;
       for (int k = tid; k < Y.K; k += 256) yc[k] = yn[k];
     } else if (Y.mode == 1) {  // y += sum_a delta_a P[k_a][:]   (P symmetric: rows, coalesced, L2-resident)
       const int na = Y.dl_n[b];
@@ -693,12 +762,7 @@ mh_accept_kernel(double* __restrict__ states, const double* __restrict__ undo, c
         sh_d[a] = Y.dl_d[(size_t)b * DL_MAX_AB + a];
       }
       __syncthreads();
-      double* yc = Y.y_cur + (size_t)b * Y.ldy;
-      for (int k = tid; k < Y.K; k += 256) {
-        double acc = yc[k];
-        for (int a = 0; a < na; ++a) acc = fma(sh_d[a], Y.P[(size_t)sh_k[a] * Y.ldk + k], acc);
-        yc[k] = acc;
-      }
+      mh_update_y<256>(Y.y_cur + (size_t)b * Y.ldyc, Y.P, Y.ldk, sh_k, sh_d, na, tid);
     }
   } else if (m.x > 0) {
     double* row = states + (size_t)b * S;
@@ -710,6 +774,115 @@ mh_accept_kernel(double* __restrict__ states, const double* __restrict__ undo, c
       pos -= r.y;
       for (int i = tid; i < r.y; i += 256) row[r.x + i] = ub[pos + i];
       __syncthreads();
+    }
+  }
+}
+
+// Small moves in ONE launch: propose, evaluate incrementally, accept / restore and update the cached y, one warp per chain
+// (eight chains per CTA).  Same draws, same arithmetic and therefore the same decisions as mh_propose_kernel ->
+// mh_delta_kernel -> mh_accept_kernel, without the undo log's round trip through HBM and with a whole batch of 8192
+// chains resident on the 148 SMs at once (the serial part of a proposal -- Philox, erf / erfinv, logs -- is latency, not
+// throughput).  Dynamic shared memory: per warp the operation list and the bitmap of affected branches.
+template <int CLOCK>
+__global__ void __launch_bounds__(256, 4)
+mh_fused_small_kernel(const DevModel M, const MhTopo T, const MhParams P, const double* __restrict__ Pm, double* states,
+                      double* y_cur, double* cur_out, int* cur_status, int* __restrict__ accepted,
+                      unsigned long long* __restrict__ counters, const int* __restrict__ slot,
+                      const double* __restrict__ ladder_prior, const double* __restrict__ ladder_lik, int B) {
+  extern __shared__ __align__(16) unsigned char fs_smem[];
+  __shared__ int s_off[8][DL_MAX_CHG];
+  __shared__ double s_old[8][DL_MAX_CHG];
+  // per warp 2 KB: first the operation list (<= 64 operations for the moves routed here), then the affected branches
+  __shared__ __align__(16) unsigned char s_u[8][DL_MAX_AB * 16];
+  static_assert(sizeof(MhOp) * 4 * MH_MAX_BRACE_NODES <= DL_MAX_AB * 16, "operation list must fit the per-warp scratch");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chain = blockIdx.x * 8 + warp;
+  if (chain >= B) return;
+  const int nwords = (M.N + 31) >> 5;
+  MhOp* ops = reinterpret_cast<MhOp*>(s_u[warp]);
+  int* s_ab_w = reinterpret_cast<int*>(s_u[warp]);
+  int* s_k_w = s_ab_w + DL_MAX_AB;
+  double* s_d_w = reinterpret_cast<double*>(s_u[warp] + DL_MAX_AB * 8);
+  unsigned* bm = reinterpret_cast<unsigned*>(fs_smem) + (size_t)warp * nwords;
+  int* c_off = s_off[warp];
+  double* c_old = s_old[warp];
+  double* row = states + (size_t)chain * M.S;
+  int nops = 0, okv = 0;
+  double lqv = 0.0;
+  if (lane == 0) {
+    bool ok;
+    int node;
+    nops = mh_build_ops(T, P, row, chain, 0.0, ops, &ok, &node, &lqv);
+    okv = ok ? 1 : 0;
+  }
+  nops = __shfl_sync(0xffffffffu, nops, 0);
+  okv = __shfl_sync(0xffffffffu, okv, 0);
+  __syncwarp();
+  if (!okv || nops == 0) {  // the reference would call `error`: the chain stays where it is
+    if (lane == 0) {
+      if (accepted) accepted[chain] = okv ? 0 : -1;
+      if (counters && !okv) atomicAdd(counters + 1, 1ull);
+    }
+    return;
+  }
+  // apply the operations in order, keeping (offset, old value) of every touched entry
+  int n_raw = 0;
+  for (int o = 0; o < nops; ++o) {
+    const MhOp op = ops[o];
+    for (int i = lane; i < op.cnt && n_raw + i < DL_MAX_CHG; i += 32) {
+      const double old = row[op.off + i];
+      c_off[n_raw + i] = op.off + i;
+      c_old[n_raw + i] = old;
+      double y;
+      switch (op.mode) {
+        case OP_SET: y = op.b; break;
+        case OP_MUL: y = old * op.a; break;
+        case OP_DIV: y = old / op.a; break;
+        case OP_ADD: y = old + op.b; break;
+        default: y = (old - op.b) * op.a + op.b; if (!(y > 0.0)) y = CUDART_NAN; break;
+      }
+      row[op.off + i] = y;
+    }
+    n_raw += op.cnt;
+    __syncwarp();
+  }
+  if (n_raw > DL_MAX_CHG) n_raw = DL_MAX_CHG;  // the host only routes small moves here
+  double o1[8];
+  int st = 0, n_ab = 0;
+  double* y = y_cur + (size_t)chain * T.ldyc;
+  mh_delta_core<CLOCK>(M, T, Pm, row, c_off, c_old, n_raw, bm, s_ab_w, s_k_w, s_d_w, y, cur_out + (size_t)chain * 8,
+                       cur_status[chain], lane, o1, &st, &n_ab);
+  int acc = 0;
+  if (lane == 0) {
+    const double* o0 = cur_out + (size_t)chain * 8;
+    double bp = 1.0, bl = 1.0;
+    if (slot) {
+      const int sl = slot[P.chain_offset + chain];
+      bp = ladder_prior[sl];
+      bl = ladder_lik[sl];
+    }
+    double lr = bp * (o1[3] - o0[3]) + bl * (o1[4] - o0[4]) + lqv;
+    if (P.use_root_jacobian) lr += o1[5] - o0[5];
+    const double u = mh_uniform(P.seed, (uint32_t)(P.chain_offset + chain), P.iteration, 1u);
+    acc = log(u) < lr;
+    if (accepted) accepted[chain] = acc;
+    if (counters && acc) atomicAdd(counters, 1ull);
+  }
+  acc = __shfl_sync(0xffffffffu, acc, 0);
+  if (acc) {
+    if (lane == 0) {
+      for (int j = 0; j < 8; ++j) cur_out[(size_t)chain * 8 + j] = o1[j];
+      cur_status[chain] = st;
+    }
+    __syncwarp();
+    mh_update_y<32>(y, Pm, M.ldk, s_k_w, s_d_w, n_ab, lane);
+  } else {
+    // restore: the FIRST record of an offset holds its old value (the operation list has been overwritten by now)
+    for (int e = lane; e < n_raw; e += 32) {
+      const int off = c_off[e];
+      bool first = true;
+      for (int e2 = 0; e2 < e; ++e2) first = first && (c_off[e2] != off);
+      if (first) row[off] = c_old[e];
     }
   }
 }
