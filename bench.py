@@ -349,6 +349,21 @@ def run_gpu(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # Metropolis-Hastings steps on chains resident in HBM: one proposal + evaluation + accept per step
+    ev.chains_set(X)
+    mh = {}
+    for name, kind, par in (("slide_node_incremental", binding.MH_SLIDE_NODE, 0.002),
+                            ("scale_rate_mean_and_tree_full_evaluation", binding.MH_SCALE_NORM_TREE_CONTRA_M, 3000.0)):
+        ev.mh_cycle([(kind, -1, par, 1.0, 0, 3)], 1, seed=3, iteration0=0)
+        ev.synchronize()
+        n_mh = 10 * args.steps
+        t0 = time.perf_counter()
+        acc, _, _ = ev.mh_cycle([(kind, -1, par, 1.0, 0, n_mh)], 1, seed=3, iteration0=10)
+        dt = time.perf_counter() - t0
+        mh[name] = {"value": B * world * n_mh / dt, "unit": "proposals/s", "us_per_step": 1e6 * dt / n_mh,
+                    "acceptance": float(acc[0]) / (n_mh * B)}
+    mh["note"] = ("mcd_mh_cycle on this rank's chains x world (per-rank wall time incl. the final synchronisation); small moves "
+                  "are scored from the cached contraction result, global moves by the full value-only evaluation")
     clocks = sampler.stop() if rank == 0 else None
     # parity guard: the timed outputs are the real thing (finite, and equal through both entry points)
     ok = bool(torch.isfinite(d_out[:, 6]).all().item()) and bool(
@@ -389,6 +404,7 @@ def run_gpu(args):
             "value_only": {"value": B * world / (value_only_ms * 1e-3), "unit": "evals/s", "ms_per_step": value_only_ms,
                            "note": "mcd_eval_device (no gradient), per-rank time of this rank x world; quadratic form from the "
                                    "triangular Cholesky-factor contraction"},
+            "mh": mh,
             "roofline": roofline(oz_s, K, B, gemm_ms, kms, ncalls, args),
             "clocks": clocks, "outputs_ok": ok,
         }
