@@ -48,6 +48,10 @@ def phi2(x):
     return 0.5 * (1.0 + erf(x * 0.70710678118654752440))
 
 
+LAST = (0.0, 0.0)  # (ln q, ln |J|) of the last proposal, for the property tests
+FORCED = None      # tests only: the sampled value (new height / shift / multiplier) instead of a draw
+
+
 def truncated_normal_sample(m, s, a, b, p):
     """truncatedNormalSample (Internal.hs:100-137) -> (value, ln(qYX / qXY)) or None where the reference calls `error`"""
     if not s > 0 or not a < b or a > m or b < m or m != m:
@@ -55,6 +59,8 @@ def truncated_normal_sample(m, s, a, b, p):
     phiA = phi2((a - m) / s)
     z = phi2((b - m) / s) - phiA
     u = erfinv(2.0 * (p * z + phiA) - 1.0) * 1.41421356237309504880 * s + m
+    if FORCED is not None:
+        u = FORCED
     if a > u or b < u or u != u or not z > 0:
         return None
     z2 = phi2((b - u) / s) - phi2((a - u) / s)
@@ -65,6 +71,8 @@ def gamma_sample(shape, scale, seed, chain, iteration):
     """Marsaglia & Tsang with the device's draw numbering"""
     if not shape > 0 or not scale > 0:
         return None
+    if FORCED is not None:
+        return FORCED
     boost, a = 1.0, shape
     if a < 1.0:
         boost = uniform(seed, chain, iteration, 7) ** (1.0 / a)
@@ -255,6 +263,8 @@ def propose(x, parent, topo, braces, kind, node, param, tune, seed, chain, itera
         lnj = math.log(1.0 / (u * u))
     else:
         raise ValueError(kind)
+    global LAST
+    LAST = (lnq, lnj)
     return y, lnq + lnj, node
 
 
