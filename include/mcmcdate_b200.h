@@ -190,6 +190,14 @@ int mcd_chains_get(mcd_handle* h, int32_t n_chains, double* states /*[B][S] or N
                    int32_t* status /*[B] or NULL*/);
 int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double param, double tune, int32_t use_root_jacobian, uint64_t seed,
                 uint32_t iteration, int32_t* accepted /*[B] or NULL*/);
+/* The Hamiltonian proposal of the reference's cycle (`maybeHamiltonianProposal`, app/Definitions.hs:281-283) on the
+ * RESIDENT chains: one mcd_nuts transition per chain, positions packed from and written back to the chains' state rows on
+ * the device, then the chains' ln-posterior parts (and the cached contraction results) are re-evaluated.  Momenta are
+ * drawn on the device.  The fixed entries (root / leaf heights, rate stem, H without calibrations) must agree across the
+ * resident chains (they do for chains started from the reference's `initWith`).  Cold chains only. */
+int mcd_chains_nuts(mcd_handle* h, const double* inv_mass /*[D]*/, const double* step_size /*[B]*/, int32_t max_depth,
+                    uint64_t seed, uint32_t iteration, double* accept_stat /*[B]*/, int32_t* info /*[B][4]*/,
+                    int32_t* status /*[B]*/);
 /* One entry of a proposal cycle (the reference's `Cycle`, app/Definitions.hs:262-285): `repeat` = the proposal's weight. */
 typedef struct mcd_mh_proposal {
   int32_t kind, node;

@@ -20,7 +20,7 @@ _LIB = None
 EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
     "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_leapfrog", "mcd_nuts",
-    "mcd_chains_set", "mcd_chains_get", "mcd_mh_step", "mcd_mh_cycle", "mcd_mc3_configure", "mcd_mc3_swap", "mcd_mc3_slots",
+    "mcd_chains_set", "mcd_chains_get", "mcd_chains_nuts", "mcd_mh_step", "mcd_mh_cycle", "mcd_mc3_configure", "mcd_mc3_swap", "mcd_mc3_slots",
     "mcd_chains_out_device", "mcd_chains_stats_device", "mcd_mh_set_incremental", "mcd_mh_get_incremental",
     "mcd_eval_device", "mcd_set_contraction", "mcd_get_contraction",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
@@ -90,6 +90,7 @@ def load_library():
     L.mcd_nuts.argtypes = [vp, i32, dp, dp, dp, dp, dp, i32, C.c_uint64, C.c_uint32, dp, dp, dp, ip, ip]
     L.mcd_chains_set.argtypes = [vp, i32, dp]
     L.mcd_chains_get.argtypes = [vp, i32, dp, dp, ip]
+    L.mcd_chains_nuts.argtypes = [vp, dp, dp, i32, C.c_uint64, C.c_uint32, dp, ip, ip]
     L.mcd_mh_step.argtypes = [vp, i32, i32, C.c_double, C.c_double, i32, C.c_uint64, C.c_uint32, ip]
     u64p = C.POINTER(C.c_uint64)
     L.mcd_mh_cycle.argtypes = [vp, i32, C.POINTER(MhProposalC), i32, C.c_uint64, C.c_uint32, u64p, u64p, C.POINTER(C.c_uint32)]
@@ -272,6 +273,16 @@ class Evaluator:
         X, out, st = np.empty((B, self.S)), np.empty((B, _m.OUT_COLS)), np.empty(B, np.int32)
         self._check(self._L.mcd_chains_get(self.h, B, _dp(X), _dp(out), _ip(st)))
         return X, out, st
+
+    def chains_nuts(self, inv_mass, step_size, max_depth: int = 10, seed: int = 0, iteration: int = 0):
+        """one NUTS transition of every resident chain -> (accept_stat[B], info[B, 4], status[B])"""
+        B = self._n_resident
+        im = np.ascontiguousarray(inv_mass, dtype=np.float64)
+        eps = np.ascontiguousarray(np.broadcast_to(np.asarray(step_size, dtype=np.float64), (B,)))
+        acc, info, st = np.empty(B), np.empty((B, 4), np.int32), np.empty(B, np.int32)
+        self._check(self._L.mcd_chains_nuts(self.h, _dp(im), _dp(eps), int(max_depth), int(seed), int(iteration), _dp(acc),
+                                            _ip(info), _ip(st)))
+        return acc, info, st
 
     def mh_step(self, kind: int, node: int, sd: float, tune: float = 1.0, use_root_jacobian: bool = False, seed: int = 0,
                 iteration: int = 0, want_accepted: bool = True):

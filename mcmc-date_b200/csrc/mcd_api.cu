@@ -547,14 +547,20 @@ int leapfrog_host(mcd_handle* h, int n, int L, const double* theta0, const doubl
 // One NUTS transition for n chains (hmc_kernels.cuh): all chains tick in lockstep, one leapfrog step per tick, until
 // every chain has made its U-turn (or reached max_depth / diverged); the host only reads the number of still
 // active chains after each tick.
+int mh_refresh(mcd_handle* h);
+bool mh_incremental_capable(const mcd_handle* h);
+// resident = true: the transition runs on the chains uploaded with mcd_chains_set (positions packed from / scattered back to
+// their state rows on the device; theta0, base, theta_out, out are not used)
 int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, const double* inv_mass, const double* eps,
               const double* mom0, int max_depth, uint64_t seed, uint32_t iteration, double* theta_out, double* out,
-              double* accept_stat, int32_t* info, int32_t* status) {
+              double* accept_stat, int32_t* info, int32_t* status, bool resident = false) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
-  if (n <= 0) return 0;
+  if (resident) n = h->n_resident;
+  if (n <= 0) return resident ? fail(h, "mcd_chains_nuts: no resident chains (call mcd_chains_set first)") : 0;
   if (max_depth < 1 || max_depth > 16) return fail(h, "mcd_nuts: max_depth must be in 1..16");
-  if (!theta0 || !base || !inv_mass || !eps || !theta_out || !out || !accept_stat || !info || !status)
+  if (resident && h->mc3_C > 0) return fail(h, "mcd_chains_nuts: heated chains are not supported (cold chains only)");
+  if (!inv_mass || !eps || !accept_stat || !info || !status || (!resident && (!theta0 || !base || !theta_out || !out)))
     return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, true, true)) return -1;
@@ -589,11 +595,18 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
   double* o = h->d_out.as<double>();
   double* gr = h->d_grad.as<double>();
   int32_t* stp = h->d_status.as<int32_t>();
-  CU_TRY(h, cudaMemcpyAsync(d_theta0, theta0, BD * 8, cudaMemcpyHostToDevice, st));
+  const dim3 gD((D + POST_THREADS - 1) / POST_THREADS, n);
+  if (resident) {  // positions = toVector of the resident states; the fixed entries come from the first chain's row
+    pack_theta_kernel<<<gD, POST_THREADS, 0, st>>>(h->d_chain.as<double>(), h->d_sidx.as<int>(), d_theta0, S, D, n);
+    h->launches += 1;
+  } else {
+    CU_TRY(h, cudaMemcpyAsync(d_theta0, theta0, BD * 8, cudaMemcpyHostToDevice, st));
+  }
   if (mom0) CU_TRY(h, cudaMemcpyAsync(d_mom0, mom0, BD * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemcpyAsync(d_invm, inv_mass, (size_t)D * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemcpyAsync(d_eps, eps, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  if (resident) CU_TRY(h, cudaMemcpyAsync(h->d_base.p, h->d_chain.p, (size_t)S * 8, cudaMemcpyDeviceToDevice, st));
+  else CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemsetAsync(nb.n_active, 0, 4, st));
   const dim3 gS((S + POST_THREADS - 1) / POST_THREADS, n);
   unpack_theta_kernel<<<gS, POST_THREADS, 0, st>>>(d_theta0, h->d_base.as<double>(), h->d_tidx.as<int>(), xs, S, D, n);
@@ -650,8 +663,19 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
   // results
   std::vector<int32_t> ni((size_t)n * NI_COLS);
   std::vector<double> nr((size_t)n * NR_COLS);
-  CU_TRY(h, cudaMemcpyAsync(theta_out, nb.thM, BD * 8, cudaMemcpyDeviceToHost, st));
-  CU_TRY(h, cudaMemcpyAsync(out, nb.outM, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost, st));
+  if (resident) {  // the chosen points become the chains' states; their ln-posterior parts (and cached y) are re-evaluated
+    scatter_theta_kernel<<<gD, POST_THREADS, 0, st>>>(nb.thM, h->d_sidx.as<int>(), h->d_chain.as<double>(), S, D, n);
+    h->launches += 1;
+    if (mh_incremental_capable(h) && h->inc_enabled && h->inc_ok) {
+      if (mh_refresh(h)) return -1;
+    } else if (enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_chain_out.as<double>(), nullptr,
+                              h->d_chain_status.as<int32_t>(), st)) {
+      return -1;
+    }
+  } else {
+    CU_TRY(h, cudaMemcpyAsync(theta_out, nb.thM, BD * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(out, nb.outM, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost, st));
+  }
   CU_TRY(h, cudaMemcpyAsync(ni.data(), nb.ni, ni.size() * 4, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaMemcpyAsync(nr.data(), nb.nr, nr.size() * 8, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaStreamSynchronize(st));
@@ -1347,6 +1371,11 @@ int mcd_nuts(mcd_handle* h, int32_t n, const double* theta0, const double* base_
                    accept_stat, info, status);
 }
 int mcd_chains_set(mcd_handle* h, int32_t n, const double* states) { return chains_set(h, n, states); }
+int mcd_chains_nuts(mcd_handle* h, const double* inv_mass, const double* step_size, int32_t max_depth, uint64_t seed,
+                    uint32_t iteration, double* accept_stat, int32_t* info, int32_t* status) {
+  return nuts_host(h, 0, nullptr, nullptr, inv_mass, step_size, nullptr, max_depth, seed, iteration, nullptr, nullptr, accept_stat,
+                   info, status, true);
+}
 int mcd_chains_get(mcd_handle* h, int32_t n, double* states, double* out, int32_t* status) {
   return chains_get(h, n, states, out, status);
 }

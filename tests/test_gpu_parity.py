@@ -737,6 +737,38 @@ def test_incremental_evaluation_of_small_moves(clock):
     full.close()
 
 
+def test_nuts_on_resident_chains_equals_the_host_buffer_call():
+    """mcd_chains_nuts = mcd_nuts on the chains' own HMC vectors, written back to their state rows (the Hamiltonian proposal
+    of the reference's cycle, app/Definitions.hs:281-283), followed by ordinary proposals on the moved chains"""
+    import mh_ref as R
+    md, h = synth.synthetic_model(150, seed=77, n_cal=3, n_con=2, n_brace=1)
+    B = 40
+    X = synth.synthetic_states(md, h, B)
+    X[:, 2] = X[0, 2]                                           # with calibrations H is free; nothing else is shared
+    ev = binding.Evaluator(md)
+    orc = O.Oracle(md)
+    theta = np.array([orc.to_vector(x) for x in X])
+    inv_mass = np.full(ev.D, 1e-4)
+    th1, out1, acc1, info1, st1 = ev.nuts(theta, X[0], inv_mass, 0.01, max_depth=4, seed=5, iteration=2)
+    ev.chains_set(X)
+    acc2, info2, st2 = ev.chains_nuts(inv_mass, 0.01, max_depth=4, seed=5, iteration=2)
+    assert np.array_equal(info1, info2) and np.array_equal(acc1, acc2) and np.array_equal(st1, st2)
+    Xd, out_d, st_d = ev.chains_get()
+    Xexp = np.array([orc.from_vector(X[b], th1[b]) for b in range(B)])
+    assert np.array_equal(Xd, Xexp) and (np.abs(Xd - X).max(axis=1) > 0).mean() > 0.5
+    assert relerr(out_d[:, :7], out1[:, :7]).max() < 1e-10
+    # the cached contraction results follow: incremental moves after the transition agree with the oracle-driven restatement
+    parent = [int(p) for p in md.parent]
+    Xr = Xd.copy()
+    out_r, st_r = orc.eval(Xr)
+    for it in range(3):
+        a_d = ev.mh_step(R.SLIDE_NODE, -1, 0.01, seed=8, iteration=it)
+        a_r = R.mh_step(orc, parent, Xr, out_r, st_r, R.SLIDE_NODE, -1, 0.01, 1.0, False, 8, it)
+        assert np.array_equal(a_d, a_r)
+    _mh_compare(ev, Xr, out_r, st_r)
+    ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
