@@ -769,6 +769,50 @@ def test_nuts_on_resident_chains_equals_the_host_buffer_call():
     ev.close()
 
 
+@pytest.mark.parametrize("clock", [0, 1])
+def test_mh_sampler_draws_from_the_prior(clock):
+    """End-to-end statistical check of proposals + Hastings factors + Jacobians + acceptance: without data (likelihood NoData)
+    the chains must converge to the prior, whose hyper-parameter marginals are known in closed form -- m ~ Exponential(ht),
+    v ~ Gamma(3/2, 1/6) (every branch-rate density is normalised given v), E[r_i] = 1.  The chains start far away
+    (v = 1, m = 4 / ht, rates 2).  Only proposals whose stated Jacobian is exact are used (see the two reference quirks
+    pinned in tests/test_host_logic.py), none lifted with the root-branch Jacobian, so the target is the prior itself."""
+    import mh_ref as R
+    B = 4096
+    md, h = synth.synthetic_model(12, seed=5 + clock, clock_model=clock, likelihood=model.LIK_NONE, n_cal=0)
+    X = synth.synthetic_states(md, h, B)
+    N = md.n_nodes
+    X[:, 3 + N] = 4.0 / md.ht
+    X[:, 4 + N] = 1.0
+    X[:, 5 + N + 1:5 + 2 * N] = 2.0
+    ev = binding.Evaluator(md)
+    ev.chains_set(X)
+    props = [(R.SCALE_SCALAR, 0, 10.0, 3.0, 0, 1), (R.SCALE_SCALAR, 1, 10.0, 3.0, 0, 1), (R.SCALE_SCALAR, 3, 10.0, 5.0, 0, 2),
+             (R.SCALE_SCALAR, 4, 10.0, 5.0, 0, 2), (R.SCALE_BRANCH, -1, 10.0, 5.0, 0, 2 * N), (R.SLIDE_NODE, -1, 0.1, 1.0, 0, 8),
+             (R.SCALE_SUBTREE, -1, 0.1, 1.0, 0, 4), (R.SCALE_RATE_SUBTREE, -1, 20.0, 2.0, 0, 4),
+             (R.SLIDE_NODE_CONTRA, -1, 0.1, 1.0, 0, 4), (R.SCALE_NORM_TREE_CONTRA_M, 0, 50.0, 1.0, 0, 1),
+             (R.SCALE_VAR_TREE_AUTO, 0, 50.0, 1.0, 0, 1)]
+    k = 0
+    _, _, k = ev.mh_cycle(props, 150, seed=21, iteration0=k)       # burn-in
+    ms, vs, rs = [], [], []
+    for _ in range(6):                                            # thinned samples (chains are independent of each other)
+        _, _, k = ev.mh_cycle(props, 25, seed=21, iteration0=k)
+        Xd, out, st = ev.chains_get()
+        assert np.isfinite(out[:, 6]).all() and (st == 0).all()
+        ms.append(Xd[:, 3 + N]); vs.append(Xd[:, 4 + N]); rs.append(Xd[:, 5 + N + 1:5 + 2 * N].mean(axis=1))
+    m_all, v_all, r_all = np.concatenate(ms), np.concatenate(vs), np.concatenate(rs)
+    # tolerances: 6 standard errors of a mean over >= 4096 independent chains (thinned repeats only help)
+    se = lambda sd: 6.0 * sd / np.sqrt(B)
+    assert abs(m_all.mean() - 1.0 / md.ht) < se(1.0 / md.ht), (m_all.mean(), 1.0 / md.ht)
+    assert abs(v_all.mean() - 0.25) < se(np.sqrt(1.5) / 6.0), v_all.mean()
+    assert abs(v_all.var() - 1.5 / 36.0) < 0.15 * 1.5 / 36.0, v_all.var()
+    assert abs(r_all.mean() - 1.0) < 0.02, r_all.mean()
+    # Kolmogorov distance of v to Gamma(3/2, 1/6) and of m to Exponential(ht) on the last sample
+    from scipy import stats
+    assert stats.kstest(vs[-1], stats.gamma(1.5, scale=1.0 / 6.0).cdf).statistic < 0.04
+    assert stats.kstest(ms[-1], stats.expon(scale=1.0 / md.ht).cdf).statistic < 0.04
+    ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
