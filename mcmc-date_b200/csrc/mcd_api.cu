@@ -873,6 +873,28 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
   const MhTopo T = mh_topo(h);
   const bool heated = h->mc3_C > 0;
   static const bool unfused = getenv("MCD_MH_UNFUSED") != nullptr;  // A/B switch: three launches instead of one
+  if (h->N <= SMALL_TREE_MAX_NODES && !unfused) {  // small trees: the whole step in one launch
+    DevModel M = h->dm;
+    M.quad_from_z = 0;
+    const size_t fsmem = POST_SMEM_FIXED + ((size_t)M.K * M.K + (size_t)(POST_THREADS / 32) * (M.S + M.N + M.K)) * 8 +
+                         (size_t)(POST_THREADS / 32) * (sizeof(MhOp) * MH_MAX_OPS + (size_t)(2 * M.N + 8) * 16);
+    const int fgrid = std::min((n + POST_THREADS / 32 - 1) / (POST_THREADS / 32), 2 * h->n_sms);
+#define MCD_LAUNCH_MH_SMALL(CC)                                                                                              \
+  mh_small_tree_kernel<CC><<<fgrid, POST_THREADS, fsmem, st>>>(M, T, P, h->d_P.as<double>(), h->d_chain.as<double>(),        \
+      h->d_chain_out.as<double>(), h->d_chain_status.as<int32_t>(), h->d_new_out.as<double>(), h->d_new_status.as<int32_t>(), \
+      h->d_accepted.as<int32_t>(), d_counters, heated ? h->d_slot.as<int>() : nullptr, h->d_ladder_p.as<double>(),            \
+      h->d_ladder_l.as<double>(), n)
+    switch (M.clock) {
+      case 0: MCD_LAUNCH_MH_SMALL(0); break;
+      case 1: MCD_LAUNCH_MH_SMALL(1); break;
+      case 2: MCD_LAUNCH_MH_SMALL(2); break;
+      default: MCD_LAUNCH_MH_SMALL(3); break;
+    }
+#undef MCD_LAUNCH_MH_SMALL
+    h->launches += 1;
+    CU_TRY(h, cudaGetLastError());
+    return 0;
+  }
   if (inc && !unfused) {
     const size_t smem = (size_t)8 * ((h->N + 31) / 32) * 4;
 #define MCD_LAUNCH_FUSED(CC)                                                                                               \
@@ -1293,6 +1315,9 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
 #define MCD_SET_SMEM(CC)                                                                                          \
   cudaFuncSetAttribute(small_tree_fused_kernel<CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);     \
   cudaFuncSetAttribute(small_tree_fused_kernel<CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    MCD_SET_SMEM(0) MCD_SET_SMEM(1) MCD_SET_SMEM(2) MCD_SET_SMEM(3)
+#undef MCD_SET_SMEM
+#define MCD_SET_SMEM(CC) cudaFuncSetAttribute(mh_small_tree_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     MCD_SET_SMEM(0) MCD_SET_SMEM(1) MCD_SET_SMEM(2) MCD_SET_SMEM(3)
 #undef MCD_SET_SMEM
 #define MCD_SET_SMEM(CC)                                                                                  \

@@ -887,6 +887,151 @@ mh_fused_small_kernel(const DevModel M, const MhTopo T, const MhParams P, const 
   }
 }
 
+// Small trees (N <= 96 nodes, all reference data sets): a whole Metropolis-Hastings step in ONE launch -- these
+// configurations are launch-latency bound (three launches of ~7 us each for a few hundred chains).  Structure of
+// small_tree_fused_kernel (precision matrix in shared memory, one warp per chain: stage the row, residuals, y = P dx as a
+// shared-memory mat-vec, the posterior passes), with the proposal in front of it and the decision behind it.  Same draws
+// and arithmetic as mh_propose_kernel -> small_tree_fused_kernel -> mh_accept_kernel.
+// Dynamic shared memory: reduction scratch | P [K][K] | per warp: state row, y, residuals | per warp: operation list,
+// undo list (offset, old value) of up to 2N + 8 entries.
+template <int CLOCK>
+__global__ void __launch_bounds__(POST_THREADS, 2)
+mh_small_tree_kernel(DevModel M, const MhTopo T, const MhParams P, const double* __restrict__ Pm /*[Mp][ldk] padded*/, double* states,
+                     double* cur_out, int* cur_status, double* new_out, int* new_status, int* __restrict__ accepted,
+                     unsigned long long* __restrict__ counters, const int* __restrict__ slot,
+                     const double* __restrict__ ladder_prior, const double* __restrict__ ladder_lik, int B) {
+  extern __shared__ __align__(16) unsigned char smem_p[];
+  double* scratch = reinterpret_cast<double*>(smem_p);
+  int* iscratch = reinterpret_cast<int*>(smem_p + 8 * NRED * 8);
+  double* sP = reinterpret_cast<double*>(smem_p + POST_SMEM_FIXED);   // [K][K]
+  const int K = M.K, N = M.N, S = M.S;
+  double* stage = sP + (size_t)K * K;
+  const int n_undo = 2 * N + 8;
+  unsigned char* mh_base = reinterpret_cast<unsigned char*>(stage + (size_t)(POST_THREADS / 32) * (S + N + K));
+  const size_t mh_per_warp = sizeof(MhOp) * MH_MAX_OPS + (size_t)n_undo * 16;
+  const Topo Tp{M.parent, M.mu, M.var, M.inner};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (M.lik == 0) {
+    for (int e = threadIdx.x; e < K * K; e += POST_THREADS) sP[e] = Pm[(size_t)(e / K) * M.ldk + (e % K)];
+  }
+  __syncthreads();
+  double* sx = stage + (size_t)warp * (S + N + K);
+  double* sy = sx + S;
+  double* sdx = sy + N;
+  MhOp* ops = reinterpret_cast<MhOp*>(mh_base + (size_t)warp * mh_per_warp);
+  double* c_old = reinterpret_cast<double*>(mh_base + (size_t)warp * mh_per_warp + sizeof(MhOp) * MH_MAX_OPS);
+  int* c_off = reinterpret_cast<int*>(c_old + n_undo);
+  for (int chain = blockIdx.x * (POST_THREADS / 32) + warp; chain < B; chain += gridDim.x * (POST_THREADS / 32)) {
+    double* row = states + (size_t)chain * S;
+    double rate_sum = 0.0;
+    if (P.kind == MH_SCALE_VAR_TREE) {
+      for (int i = 1 + lane; i < N; i += 32) rate_sum += row[5 + N + i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rate_sum += __shfl_xor_sync(0xffffffffu, rate_sum, o);
+    }
+    int nops = 0, okv = 0;
+    double lqv = 0.0;
+    if (lane == 0) {
+      bool ok;
+      int node;
+      nops = mh_build_ops(T, P, row, chain, rate_sum, ops, &ok, &node, &lqv);
+      okv = ok ? 1 : 0;
+    }
+    nops = __shfl_sync(0xffffffffu, nops, 0);
+    okv = __shfl_sync(0xffffffffu, okv, 0);
+    __syncwarp();
+    if (!okv || nops == 0) {
+      if (lane == 0) {
+        if (accepted) accepted[chain] = okv ? 0 : -1;
+        if (counters && !okv) atomicAdd(counters + 1, 1ull);
+      }
+      continue;
+    }
+    int n_raw = 0;
+    for (int o = 0; o < nops; ++o) {
+      const MhOp op = ops[o];
+      for (int i = lane; i < op.cnt && n_raw + i < n_undo; i += 32) {
+        const double old = row[op.off + i];
+        c_off[n_raw + i] = op.off + i;
+        c_old[n_raw + i] = old;
+        double y;
+        switch (op.mode) {
+          case OP_SET: y = op.b; break;
+          case OP_MUL: y = old * op.a; break;
+          case OP_DIV: y = old / op.a; break;
+          case OP_ADD: y = old + op.b; break;
+          default: y = (old - op.b) * op.a + op.b; if (!(y > 0.0)) y = CUDART_NAN; break;
+        }
+        row[op.off + i] = y;
+      }
+      n_raw += op.cnt;
+      __syncwarp();
+    }
+    if (n_raw > n_undo) n_raw = n_undo;
+    __threadfence_block();
+    // evaluate the proposed state: small_tree_fused_kernel's body
+    stage_chain<32>(M, chain, lane, sx, sy, states, nullptr);
+    if (M.lik == 0) {
+      const double* h = sx + 3;
+      const double* r = sx + 5 + N;
+      const double sc = sx[2] * sx[3 + N];
+      for (int i = 1 + lane; i < N; i += 32) {
+        if (i == M.root_r) continue;
+        double e = (h[M.parent[i] & ~LEAF_BIT] - h[i]) * r[i];
+        if (i == 1) e = e + (h[0] - h[M.root_r]) * r[M.root_r];
+        const int kk = i < M.root_r ? i - 1 : i - 2;
+        sdx[kk] = e * sc - M.mu[kk];
+      }
+      __syncwarp();
+      for (int kk = lane; kk < K; kk += 32) {
+        const double* prow = sP + (size_t)kk * K;
+        double a0 = 0.0, a1 = 0.0;
+        int j = 0;
+        for (; j + 2 <= K; j += 2) {
+          a0 = fma(prow[j], sdx[j], a0);
+          a1 = fma(prow[j + 1], sdx[j + 1], a1);
+        }
+        if (j < K) a0 = fma(prow[j], sdx[j], a0);
+        sy[kk] = a0 + a1;
+      }
+      __syncwarp();
+    }
+    process_chain<32, CLOCK, false>(M, Tp, chain, lane, sx, sy, scratch, iscratch, new_out, nullptr, new_status);
+    __syncwarp();
+    int acc = 0;
+    if (lane == 0) {  // lane 0 wrote new_out[chain] / new_status[chain] itself
+      const double* o1 = new_out + (size_t)chain * 8;
+      const double* o0 = cur_out + (size_t)chain * 8;
+      double bp = 1.0, bl = 1.0;
+      if (slot) {
+        const int sl = slot[P.chain_offset + chain];
+        bp = ladder_prior[sl];
+        bl = ladder_lik[sl];
+      }
+      double lr = bp * (o1[3] - o0[3]) + bl * (o1[4] - o0[4]) + lqv;
+      if (P.use_root_jacobian) lr += o1[5] - o0[5];
+      const double u = mh_uniform(P.seed, (uint32_t)(P.chain_offset + chain), P.iteration, 1u);
+      acc = log(u) < lr;
+      if (accepted) accepted[chain] = acc;
+      if (counters && acc) atomicAdd(counters, 1ull);
+      if (acc) {
+        for (int j = 0; j < 8; ++j) cur_out[(size_t)chain * 8 + j] = o1[j];
+        cur_status[chain] = new_status[chain];
+      }
+    }
+    acc = __shfl_sync(0xffffffffu, acc, 0);
+    if (!acc) {  // restore: the first record of an offset holds its old value
+      for (int e = lane; e < n_raw; e += 32) {
+        const int off = c_off[e];
+        bool first = true;
+        for (int e2 = 0; e2 < e; ++e2) first = first && (c_off[e2] != off);
+        if (first) row[off] = c_old[e];
+      }
+    }
+    __syncwarp();  // the warp's staging buffers are reused by its next chain
+  }
+}
+
 // MC3 state swaps between neighbouring temperatures (the `mcmc` package's MC3 algorithm, called at app/Main.hs:476-479;
 // restated from Altekar et al. 2004 / the package's published source): for the chains x_i, x_j holding slots p, p + 1 of a
 // group, ln r = (beta_p - beta_{p+1}) (ln pi(x_j) - ln pi(x_i)) with prior and likelihood heated by their own ladders;
