@@ -323,14 +323,14 @@ class Evaluator:
 
     def mc3_swap(self, pair: int = -1, seed: int = 0, iteration: int = 0, d_stats_global: int = 0, want_accepted: bool = True):
         """one swap attempt per group between the slots (pair, pair + 1) -> accepted flag per group"""
-        n_global, Cg = self._mc3
-        acc = np.empty(n_global // Cg, np.int32) if want_accepted else None
+        n_global, Cg = getattr(self, "_mc3", (0, 0))
+        acc = np.empty(max(1, n_global // max(1, Cg)), np.int32) if want_accepted else None
         self._check(self._L.mcd_mc3_swap(self.h, int(pair), int(seed), int(iteration), d_stats_global or None,
                                          _ip(acc) if acc is not None else None))
         return acc
 
     def mc3_slots(self):
-        sl = np.empty(self._mc3[0], np.int32)
+        sl = np.empty(max(1, getattr(self, "_mc3", (0, 0))[0]), np.int32)
         self._check(self._L.mcd_mc3_slots(self.h, _ip(sl)))
         return sl
 

@@ -813,6 +813,63 @@ def test_mh_sampler_draws_from_the_prior(clock):
     ev.close()
 
 
+def test_mh_edge_cases():
+    """smallest trees, a leaf child of the root, argument checks that mirror the reference's proposal constructors"""
+    import mh_ref as R
+    # 3 leaves: ((a,b),c) -- one inner node below the root, the root's other child is a leaf
+    parent = np.array([-1, 0, 1, 1, 0], np.int32)
+    md = model.ModelDesc(parent=parent, mean=np.array([0.9, 0.3, 0.35]), precision=np.diag([30.0, 90.0, 80.0]) + 1.0,
+                         logdet_sigma=-11.0, clock_model=model.UNCORRELATED_GAMMA)
+    B = 64
+    rng = np.random.default_rng(1)
+    X = np.zeros((B, md.state_len))
+    X[:, 0], X[:, 1], X[:, 2] = 1.2, 0.7, 1.0
+    X[:, 3] = 1.0
+    X[:, 4] = rng.uniform(0.2, 0.8, B)
+    X[:, 3 + 5], X[:, 4 + 5] = 1.0, 0.3
+    X[:, 5 + 5 + 1:] = rng.lognormal(0, 0.2, (B, 4))
+    ev = binding.Evaluator(md)
+    orc = O.Oracle(md)
+    ev.chains_set(X)
+    Xr = X.copy()
+    out_r, st_r = orc.eval(Xr)
+    par = [int(p) for p in parent]
+    for it, (kind, node, param, jac) in enumerate([(R.SLIDE_NODE, 1, 0.2, True), (R.SCALE_SUBTREE, -1, 0.2, True),
+                                                    (R.SLIDE_NODE_CONTRA, 1, 0.2, True), (R.SCALE_BRANCH, 4, 20.0, True),
+                                                    (R.SCALE_RATES_TREE_CONTRA, 0, 0.2, True), (R.SCALE_VAR_TREE, 0, 20.0, True),
+                                                    (R.SCALE_RATE_SUBTREE, 1, 20.0, True), (R.SCALE_SUBTREE_CONTRA, 1, 0.2, True)]):
+        a_d = ev.mh_step(kind, node, param, use_root_jacobian=jac, seed=2, iteration=it)
+        a_r = R.mh_step(orc, par, Xr, out_r, st_r, kind, node, param, 1.0, jac, 2, it)
+        assert np.array_equal(a_d, a_r), (it, kind)
+    _mh_compare(ev, Xr, out_r, st_r)
+    for bad in [(R.PULLEY, 0, 0.1),               # pulleyUltrametric: a sub tree of the root is a leaf
+                (R.SLIDE_NODE, 4, 0.1),           # path leads to a leaf
+                (R.SLIDE_NODE, 0, 0.1),           # the root
+                (R.SCALE_BRANCH, 0, 10.0),        # the stem
+                (R.SLIDE_BRACE, 0, 0.1),          # no braces in this model
+                (R.SLIDE_NODE, 1, -0.1),          # standard deviation
+                (99, 0, 0.1)]:
+        with pytest.raises(RuntimeError):
+            ev.mh_step(*bad)
+    with pytest.raises(RuntimeError):
+        ev.mc3_swap(0)                                          # no ladder configured
+    with pytest.raises(RuntimeError):
+        ev.mc3_configure(B, 0, 7, np.ones(7), np.ones(7))       # 64 chains do not split into groups of 7
+    ev.close()
+    # a cherry: 2 leaves, no inner node below the root
+    md2 = model.ModelDesc(parent=np.array([-1, 0, 0], np.int32), mean=np.array([1.0]), precision=np.array([[4.0]]), logdet_sigma=-1.4)
+    ev2 = binding.Evaluator(md2)
+    x2 = np.array([[1.0, 0.5, 1.0, 1.0, 0.0, 0.0, 1.0, 0.2, 0.0, 1.1, 0.9]])
+    ev2.chains_set(x2)
+    with pytest.raises(RuntimeError):
+        ev2.mh_step(R.SLIDE_NODE, -1, 0.1)                      # nothing to slide
+    with pytest.raises(RuntimeError):
+        ev2.mh_step(R.SCALE_RATES_TREE_CONTRA, 0, 0.1)          # "no internal nodes to scale"
+    a = ev2.mh_step(R.SCALE_BRANCH, -1, 20.0, seed=1, iteration=0)
+    assert a[0] in (0, 1)
+    ev2.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
