@@ -1304,8 +1304,12 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
     if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
   // posterior kernels may need > 48 KiB dynamic smem on large trees
   {
-    const size_t post_smem = POST_SMEM_FIXED + (size_t)(N <= SMALL_TREE_MAX_NODES ? POST_THREADS / 32 : 1) * (h->S + N + h->K) * 8;
-    if (post_smem > 220 * 1024) return bail("mcd_create: tree too large for the posterior kernel's shared-memory staging (N > 9000)");
+    // large trees stage the state row [S] only (y is read from global memory); small ones P and per-warp rows
+    const size_t post_smem = N <= SMALL_TREE_MAX_NODES
+                                 ? POST_SMEM_FIXED + ((size_t)h->K * h->K + (size_t)(POST_THREADS / 32) * (h->S + N + h->K)) * 8
+                                 : POST_SMEM_FIXED + (size_t)h->S * 8;
+    if (post_smem > 220 * 1024)
+      return bail("mcd_create: tree too large for the posterior kernel's shared-memory staging (more than ~14000 nodes)");
     const int lim = 225 * 1024;
 #define MCD_SET_SMEM(CC)                                                                                               \
   cudaFuncSetAttribute(posterior_kernel<256, CC, true, POST_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
