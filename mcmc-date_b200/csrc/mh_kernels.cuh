@@ -42,6 +42,15 @@
 #include "hmc_kernels.cuh"
 #include "posterior_kernels.cuh"
 
+// compute-sanitizer is not available on the GPU pool: build with `make EXTRA=-DMCD_CHECK` to arm bounds checks of the
+// list / range bookkeeping below (device asserts), then run the MH tests.
+#ifdef MCD_CHECK
+#include <assert.h>
+#define MCD_ASSERT(c) assert(c)
+#else
+#define MCD_ASSERT(c) ((void)0)
+#endif
+
 namespace mcd {
 
 enum {
@@ -140,6 +149,7 @@ __device__ __noinline__ int mh_build_ops(const MhTopo& T, const MhParams& P, con
   double lnq = 0.0, lnj = 0.0;
   auto push = [&](int off, int cnt, int mode, double a, double bb) {
     if (cnt <= 0) return;
+    MCD_ASSERT(nops < MH_MAX_OPS && off >= 0 && off + cnt <= T.S);
     ops[nops].off = off; ops[nops].cnt = cnt; ops[nops].mode = mode; ops[nops].a = a; ops[nops].b = bb;
     ++nops;
   };
@@ -365,6 +375,7 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
   for (int o = 0; o < nops; ++o) {
     const MhOp op = ops[o];
     for (int i = tid; i < op.cnt; i += 256) {
+      MCD_ASSERT(pos + i < undo_stride);
       const double old = row[op.off + i];
       ub[pos + i] = old;
       double y;
@@ -514,6 +525,7 @@ __device__ __forceinline__ void mh_delta_core(const DevModel& M, const MhTopo& T
     }
     n_ab += total;
   }
+  MCD_ASSERT(n_ab <= DL_MAX_AB);
   if (n_ab > DL_MAX_AB) n_ab = DL_MAX_AB;
   __syncwarp();
   // 3. per-branch residual and clock-prior changes
@@ -524,12 +536,14 @@ __device__ __forceinline__ void mh_delta_core(const DevModel& M, const MhTopo& T
   double d_clock = 0.0, q1 = 0.0;
   for (int a = lane; a < n_ab; a += 32) {
     const int i = ab[a], p = T.parent[i] & 0x7fffffff;
+    MCD_ASSERT(i >= 1 && i < N && p >= 0 && p < N);
     const double hi_n = row[OH + i], hp_n = row[OH + p], r_n = row[OR + i];
     const double hi_o = old_val(OH + i), hp_o = old_val(OH + p), r_o = old_val(OR + i);
     const double t_n = hp_n - hi_n, t_o = hp_o - hi_o;
     const bool ok = (t_n > 0.0) && (r_n > 0.0);
     bad = bad || !ok;
     const int k = branch_of(i, M.root_r);
+    MCD_ASSERT(k >= 0 && k < M.K);
     const double d = (t_n * r_n) * sc - (t_o * r_o) * sc;
     abk[a] = k;
     abd[a] = d;
@@ -686,6 +700,7 @@ mh_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict__ P, 
       }
       n_raw += r.y;
     }
+    MCD_ASSERT(n_raw <= DL_MAX_CHG);
     if (n_raw > DL_MAX_CHG) n_raw = DL_MAX_CHG;  // the host only routes small moves here
   }
   double o1[8];
@@ -846,6 +861,7 @@ mh_fused_small_kernel(const DevModel M, const MhTopo T, const MhParams P, const 
     n_raw += op.cnt;
     __syncwarp();
   }
+  MCD_ASSERT(n_raw <= DL_MAX_CHG && nops * (int)sizeof(MhOp) <= DL_MAX_AB * 16);
   if (n_raw > DL_MAX_CHG) n_raw = DL_MAX_CHG;  // the host only routes small moves here
   double o1[8];
   int st = 0, n_ab = 0;
@@ -967,6 +983,7 @@ mh_small_tree_kernel(DevModel M, const MhTopo T, const MhParams P, const double*
       n_raw += op.cnt;
       __syncwarp();
     }
+    MCD_ASSERT(n_raw <= n_undo);
     if (n_raw > n_undo) n_raw = n_undo;
     __threadfence_block();
     // evaluate the proposed state: small_tree_fused_kernel's body
