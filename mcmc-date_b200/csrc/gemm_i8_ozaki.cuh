@@ -141,7 +141,8 @@ template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ Y,
-                     int nkb, int ldy, int Bp, int Mp, int bt_base, int n_pr, int n_tiles, int upper_tri) {
+                     int nkb, int ldy, int Bp, int Mp, int bt_base, int n_pr, int n_tiles, int upper_tri, int kb_lo,
+                     const double* __restrict__ yadd, int ldyadd) {
   static_assert(S >= 2 && S <= OZ_MAX_SLICES && S * OZ_N <= OZ_TMEM_COLS, "digit planes must fit TMEM");
   constexpr int STAGE = oz_stage_bytes<S>();
   constexpr int A_PLANE = OZ_M * OZ_KB, B_PLANE = OZ_N * OZ_KB;
@@ -195,7 +196,9 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int pr0 = (t % n_pr) * OZ_N, bt0 = bt_base + (t / n_pr) * OZ_M;
       // upper-triangular operand (U = L^T of the Cholesky factor, value-only path): row m only has entries at
       // k >= m, so this tile's reduction starts at its own diagonal block
-      for (int kb = upper_tri ? pr0 / OZ_KB : 0; kb < nkb; ++kb, ++g) {
+      // kb_lo .. nkb: the reduction may be restricted to the k-blocks where the chains' operand is non-zero (rank-limited
+      // update Y = yadd + dX P of the MH path: dX is zero outside one sub tree's branches)
+      for (int kb = upper_tri ? pr0 / OZ_KB : kb_lo; kb < nkb; ++kb, ++g) {
         if (g >= OZ_STAGES) mbar_wait(&empty[g % OZ_STAGES], ((g / OZ_STAGES) - 1) & 1);
         if (leader) load_kblock(g, kb, bt0, pr0);
         __syncwarp();
@@ -210,7 +213,7 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(acc_empty, (it - 1) & 1);
         tc_fence_after();
       }
-      const int kb0 = upper_tri ? ((t % n_pr) * OZ_N) / OZ_KB : 0;
+      const int kb0 = upper_tri ? ((t % n_pr) * OZ_N) / OZ_KB : kb_lo;
       for (int kb = kb0; kb < nkb; ++kb, ++g) {
         const int st = g % OZ_STAGES;
 #ifdef MCD_OZ_NO_REFILL
@@ -259,6 +262,7 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int b = bt0 + row;
       const double sa = scaleA[b];
       double* yrow = Y + (size_t)b * ldy + pr0;
+      const double* arow = yadd ? yadd + (size_t)b * ldyadd + pr0 : nullptr;
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
 #ifdef MCD_OZ_NO_EPI
@@ -280,7 +284,13 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             r1 = fma(r1, 0.00390625, oz_i2d(v[d][j + 1]));
           }
           const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
-          *reinterpret_cast<double2*>(yrow + c * 16 + j) = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
+          double2 o = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
+          if (arow) {
+            const double2 ya = *reinterpret_cast<const double2*>(arow + c * 16 + j);
+            o.x += ya.x;
+            o.y += ya.y;
+          }
+          *reinterpret_cast<double2*>(yrow + c * 16 + j) = o;
         }
       }
       // this warp's TMEM reads are complete (tcgen05.wait::ld above): hand the accumulators back
@@ -418,6 +428,89 @@ residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ 
   }
 }
 
+// MH path, sub-tree moves on a given node j: the residual changes on the branches of the sub tree only, k in
+// [k_lo, k_lo + span) (contiguous in pre-order).  This kernel forms delta = dx(proposed state) - dx(current state) there
+// from the state row (already modified in place) and the proposal's undo log, and writes its digit planes for the k-blocks
+// [kb_lo, kb_hi) that cover the range (zero elsewhere in those blocks); the contraction then runs over these k-blocks only
+// and adds the cached y of the current state.  Undo layout (mh_propose_kernel, ranges in order):
+//   heights (scale sub tree / contrary): ub[i - j] = old h_i, i in [j, j + size);
+//   contrary rates: ub[size + (i - j - 1)] = old r_i for i > j, ub[2 size - 1] = old r_j;
+//   rate sub tree: ub[i - j] = old r_i.
+// mode: 0 heights only, 1 heights + rates (contrary), 2 rates only.  One CTA per chain; dynamic smem 8 * span_pad bytes.
+template <int S>
+__global__ void __launch_bounds__(256)
+delta_split_kernel(int N, int SL, int root_r, const int* __restrict__ parent, const double* __restrict__ states,
+                   const double* __restrict__ undo, int undo_stride, const int4* __restrict__ meta, int mode, int j, int size,
+                   int k_lo, int span, int kb_lo, int kb_hi, signed char* __restrict__ planes, int ld8, size_t plane_stride,
+                   double* __restrict__ scale, int B) {
+  extern __shared__ __align__(16) unsigned char smem_ds[];
+  double* sd = reinterpret_cast<double*>(smem_ds);  // [(kb_hi - kb_lo) * OZ_KB]
+  __shared__ double s_amax[8];
+  __shared__ int s_bad[8];
+  const int chain = blockIdx.x;
+  if (chain >= B) return;
+  const int tid = threadIdx.x;
+  const double* x = states + (size_t)chain * SL;
+  const double* h = x + 3;
+  const double* r = x + 5 + N;
+  const double* ub = undo + (size_t)chain * undo_stride;
+  const double sc = x[2] * x[3 + N];
+  const bool moved = meta[chain].x > 0;  // an invalid proposal left the chain unchanged: delta = 0
+  const int k_base = kb_lo * OZ_KB, n_k = (kb_hi - kb_lo) * OZ_KB;
+  double amax = 0.0;
+  int bad = 0;
+  for (int q = tid; q < n_k; q += 256) {
+    const int k = k_base + q;
+    double d = 0.0;
+    if (moved && k >= k_lo && k < k_lo + span) {
+      const int i = k + 1 < root_r ? k + 1 : k + 2;  // k > 0: node of branch k (left side i = k + 1, right side i = k + 2)
+      const int p = parent[i] & 0x7fffffff;
+      const double hi_n = h[i], hp_n = h[p], r_n = r[i];
+      double hi_o = hi_n, hp_o = hp_n, r_o = r_n;
+      if (mode != 2) {
+        hi_o = ub[i - j];
+        if (p >= j) hp_o = ub[p - j];  // the parent of the sub tree's root keeps its height
+      }
+      if (mode == 1) r_o = i > j ? ub[size + (i - j - 1)] : ub[2 * size - 1];
+      if (mode == 2) r_o = ub[i - j];
+      d = ((hp_n - hi_n) * r_n) * sc - ((hp_o - hi_o) * r_o) * sc;
+    }
+    sd[q] = d;
+    const double a = fabs(d);
+    bad |= !(a <= 1.7976931348623157e308);
+    amax = fmax(amax, a);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+  }
+  if ((tid & 31) == 0) { s_amax[tid >> 5] = amax; s_bad[tid >> 5] = bad; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { amax = fmax(amax, s_amax[w]); bad |= s_bad[w]; }
+  const bool finite = bad == 0;
+  double mult;
+  const double scl = oz_row_scale<S>(amax, finite, &mult);
+  if (tid == 0) scale[chain] = scl;
+  signed char* prow = planes + (size_t)chain * ld8 + k_base;
+  for (int q4 = tid; q4 < n_k / 4; q4 += 256) {
+    const double2 x01 = *reinterpret_cast<const double2*>(sd + 4 * q4);
+    const double2 x23 = *reinterpret_cast<const double2*>(sd + 4 * q4 + 2);
+    const unsigned long long j0 = oz_digit_bytes<S>(finite ? x01.x : 0.0, mult), j1 = oz_digit_bytes<S>(finite ? x01.y : 0.0, mult),
+                             j2 = oz_digit_bytes<S>(finite ? x23.x : 0.0, mult), j3 = oz_digit_bytes<S>(finite ? x23.y : 0.0, mult);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int byte = S - 1 - s;
+      const uint32_t a0 = byte < 4 ? (uint32_t)j0 : (uint32_t)(j0 >> 32), a1 = byte < 4 ? (uint32_t)j1 : (uint32_t)(j1 >> 32),
+                     a2 = byte < 4 ? (uint32_t)j2 : (uint32_t)(j2 >> 32), a3 = byte < 4 ? (uint32_t)j3 : (uint32_t)(j3 >> 32);
+      const uint32_t sel = (uint32_t)(byte & 3) | ((uint32_t)(4 + (byte & 3)) << 4);
+      const uint32_t lo = __byte_perm(a0, a1, sel), hi = __byte_perm(a2, a3, sel);
+      *reinterpret_cast<uint32_t*>(prow + (size_t)s * plane_stride + 4 * q4) = __byte_perm(lo, hi, 0x5410);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 // tensor map over digit planes stacked along rows: [total_rows][ld8] int8, box = box_rows x OZ_KB bytes, swizzled over OZ_KB
 inline int oz_make_plane_map(CUtensorMap* tm, const signed char* base, size_t total_rows, int ld8, int box_rows) {
@@ -444,11 +537,13 @@ inline cudaError_t gemm_i8_ozaki_configure() {
 template <int S>
 inline cudaError_t gemm_i8_ozaki_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const double* scaleA,
                                         const double* scaleB, double* Y, int Mp, int n_chains_padded, int ld8, int ldy,
-                                        int Bp_total, cudaStream_t st, int bt_base = 0, int n_sms = 148, int upper_tri = 0) {
+                                        int Bp_total, cudaStream_t st, int bt_base = 0, int n_sms = 148, int upper_tri = 0,
+                                        int kb_lo = 0, int kb_hi = -1, const double* yadd = nullptr, int ldyadd = 0) {
   const int n_pr = Mp / OZ_N, n_tiles = n_pr * (n_chains_padded / OZ_M);
   const int grid = n_tiles < n_sms ? n_tiles : n_sms;
-  gemm_i8_ozaki_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), st>>>(tmA, tmB, scaleA, scaleB, Y, ld8 / OZ_KB, ldy,
-                                                                         Bp_total, Mp, bt_base, n_pr, n_tiles, upper_tri);
+  const int nkb = kb_hi > 0 ? kb_hi : ld8 / OZ_KB;  // [kb_lo, kb_hi): non-empty by the caller's contract
+  gemm_i8_ozaki_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), st>>>(tmA, tmB, scaleA, scaleB, Y, nkb, ldy, Bp_total, Mp,
+                                                                         bt_base, n_pr, n_tiles, upper_tri, kb_lo, yadd, ldyadd);
   return cudaGetLastError();
 }
 

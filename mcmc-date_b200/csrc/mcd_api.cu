@@ -231,6 +231,8 @@ int ensure_i8_planes(mcd_handle* h) {
     CU_TRY(h, gemm_i8_ozaki_configure<S>());
     CU_TRY(h, cudaFuncSetAttribute(residual_split_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)((size_t)h->ld8 * 8)));
+    CU_TRY(h, cudaFuncSetAttribute(delta_split_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((size_t)h->ld8 * 8)));
     h->oz_P_S = S;
   }
   if (h->chol_state == 1 && h->oz_U_S != S) {  // value-only path: digit planes of the upper-triangular factor U = L^T
@@ -308,7 +310,7 @@ std::vector<std::pair<int, int>> chunk_schedule(int n, int S) {
 // enqueue the three kernels for chains [c0, c0 + n) of the given device buffers; c0 % 128 == 0
 template <bool GRAD>
 int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
-            cudaStream_t st) {
+            cudaStream_t st, bool posterior_only = false) {
   DevModel M = h->dm;
   const bool tri = !GRAD && M.lik == MCD_LIK_FULL && h->chol_state == 1 && !h->sparse && !h->force_sym &&
                    (h->oz_S == 0 || h->oz_U_S == h->oz_S);
@@ -352,7 +354,10 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
     CU_TRY(h, cudaGetLastError());
     return 0;
   }
-  if (h->sparse) {
+  if (posterior_only) {
+    // the caller has already put y = Sigma^-1 dx of these states into d_y (rank-limited update of the MH path)
+    if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
+  } else if (h->sparse) {
     sparse_contraction_kernel<<<n, POST_THREADS, (size_t)(M.S + M.K) * 8, st>>>(M, xs, h->d_y.as<double>() + (size_t)c0 * M.ldy, n);
     h->launches += 1;
     if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
@@ -709,8 +714,8 @@ int mh_refresh(mcd_handle* h) {
   const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_chain_out.as<double>(), nullptr, h->d_chain_status.as<int32_t>(), st);
   h->force_sym = false;
   if (rc) return -1;
-  CU_TRY(h, cudaMemcpy2DAsync(h->d_chain_y.p, (size_t)h->ldyc * 8, h->d_y.p, (size_t)h->ldy * 8, (size_t)h->ldk * 8, n,
-                              cudaMemcpyDeviceToDevice, st));
+  CU_TRY(h, cudaMemcpy2DAsync(h->d_chain_y.p, (size_t)h->ldyc * 8, h->d_y.p, (size_t)h->ldy * 8,
+                              (size_t)std::min(h->ldy, h->ldyc) * 8, n, cudaMemcpyDeviceToDevice, st));
   h->inc_steps = 0;
   return 0;
 }
@@ -752,8 +757,9 @@ int chains_set(mcd_handle* h, int n, const double* states) {
     CU_TRY(h, cudaMalloc(&h->d_lq.p, (size_t)cap * 8));
     CU_TRY(h, cudaMalloc(&h->d_accepted.p, (size_t)cap * 4));
     if (mh_incremental_capable(h)) {
-      h->ldyc = h->ldk + 16;
+      h->ldyc = h->Mp8 + 16;  // >= the contraction's padded row count (its epilogue adds whole 64-column tiles of this buffer)
       CU_TRY(h, cudaMalloc(&h->d_chain_y.p, (size_t)cap * h->ldyc * 8));
+      CU_TRY(h, cudaMemset(h->d_chain_y.p, 0, (size_t)cap * h->ldyc * 8));
       CU_TRY(h, cudaMalloc(&h->d_dl_n.p, (size_t)cap * 4));
       CU_TRY(h, cudaMalloc(&h->d_dl_k.p, (size_t)cap * DL_MAX_AB * 4));
       CU_TRY(h, cudaMalloc(&h->d_dl_d.p, (size_t)cap * DL_MAX_AB * 8));
@@ -914,6 +920,34 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
   }
   mh_propose_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
                                        h->d_lq.as<double>(), T, P, h->undo_stride, n);
+  // Sub-tree moves on a given node that are too large for the per-chain incremental path still change the residual on
+  // the sub tree's branches only: y' = y + Sigma^-1[:, A] delta_A is a contraction over the k-blocks covering A (all
+  // chains share the range), on the tensor cores, instead of the full one; the posterior kernel then runs as usual.
+  const bool range = inc_mode && h->oz_S != 0 && h->oz_P_S == h->oz_S && h->oz_X_S == h->oz_S && node > 1 && node != h->dm.root_r &&
+                     (kind == MH_SCALE_SUBTREE || kind == MH_SCALE_SUBTREE_CONTRA || kind == MH_SCALE_RATE_SUBTREE) &&
+                     !getenv("MCD_MH_NO_RANGE");
+  if (range) {
+    const int size = h->sub_size_h[node], k_lo = h->bidx[node];
+    const int kb_lo = k_lo / OZ_KB, kb_hi = (k_lo + size - 1) / OZ_KB + 1;
+    const int mode = kind == MH_SCALE_SUBTREE ? 0 : kind == MH_SCALE_SUBTREE_CONTRA ? 1 : 2;
+    const size_t stride = (size_t)h->cap * h->ld8;
+    const int np = (n + OZ_M - 1) / OZ_M * OZ_M;
+#define MCD_LAUNCH_RANGE(SS)                                                                                               \
+  delta_split_kernel<SS><<<n, 256, (size_t)(kb_hi - kb_lo) * OZ_KB * 8, st>>>(                                            \
+      h->N, h->S, h->dm.root_r, h->dm.parent, h->d_chain.as<double>(), h->d_undo.as<double>(), h->undo_stride,            \
+      h->d_meta.as<int4>(), mode, node, size, k_lo, size, kb_lo, kb_hi, h->d_pX.as<signed char>(), h->ld8, stride,        \
+      h->d_sX.as<double>(), n);                                                                                           \
+  CU_TRY(h, gemm_i8_ozaki_launch<SS>(h->tmA8, h->tmB8, h->d_sX.as<double>(), h->d_sP.as<double>(), h->d_y.as<double>(),   \
+                                     h->Mp8, np, h->ld8, h->dm.ldy, h->cap, st, 0, h->n_sms, 0, kb_lo, kb_hi,             \
+                                     h->d_chain_y.as<double>(), h->ldyc))
+    if (h->oz_S == 6) { MCD_LAUNCH_RANGE(6); } else { MCD_LAUNCH_RANGE(7); }
+#undef MCD_LAUNCH_RANGE
+    h->launches += 2;
+    h->force_sym = true;  // d_y holds y = Sigma^-1 dx (not the Cholesky-form z)
+    const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st, true);
+    h->force_sym = false;
+    if (rc) return -1;
+  }
   MhYUpdate Y{};
   Y.mode = 0; Y.K = h->K; Y.ldk = h->ldk; Y.ldy = h->ldy; Y.ldyc = h->ldyc; Y.y_cur = h->d_chain_y.as<double>(); Y.y_new = h->d_y.as<double>();
   Y.P = h->d_P.as<double>(); Y.dl_n = h->d_dl_n.as<int>(); Y.dl_k = h->d_dl_k.as<int>(); Y.dl_d = h->d_dl_d.as<double>();
@@ -933,6 +967,8 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
 #undef MCD_LAUNCH_DELTA
     h->launches += 1;
     Y.mode = 1;
+  } else if (range) {
+    Y.mode = 2;
   } else {
     h->force_sym = inc_mode;  // keep producing y while the incremental mode is on
     const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st);

@@ -680,7 +680,7 @@ def test_incremental_evaluation_of_small_moves(clock):
     the oracle-driven host restatement: same decisions, same chains; values within accumulated rounding.  Includes chains in
     the near-critical birth-death regime, a refresh every 5 steps, and proposals that fall back to the full evaluation."""
     import mh_ref as R
-    n_leaves, B = 150, 48
+    n_leaves, B = 300, 48
     md, h = synth.synthetic_model(n_leaves, seed=911 + clock, clock_model=clock, n_cal=4, n_con=3, n_brace=2)
     X = synth.synthetic_states(md, h, B)
     X[::7, 1] = X[::7, 0] + 3e-7                                # |lambda - mu| < 1e-6: literal D/E recursion
@@ -689,6 +689,10 @@ def test_incremental_evaluation_of_small_moves(clock):
     child, size, inner, inner_list = R.topology(parent)
     small = [i for i in inner_list if 4 <= size[i] <= 32]
     big = max(inner_list, key=lambda i: size[i])
+    # sub trees too large for the per-chain path but not hanging off the root: rank-limited contraction over their k-blocks
+    mids = sorted([i for i in inner_list if size[i] > 64 and parent[i] != 0], key=lambda i: size[i])
+    assert len(mids) >= 2
+    mid, mid2 = mids[0], mids[-1]
     orc = O.Oracle(md)
     inc, full = binding.Evaluator(md), binding.Evaluator(md)
     inc.mh_set_incremental(True, refresh_every=5)
@@ -704,7 +708,10 @@ def test_incremental_evaluation_of_small_moves(clock):
              (R.SCALE_SUBTREE, small[0], 0.01, 1.0, False), (R.SCALE_SUBTREE_CONTRA, small[-1], 0.1, 0.1, False),
              (R.SCALE_RATE_SUBTREE, small[len(small) // 2], 100.0, 5.0, False),
              (R.SCALE_SCALAR, 0, 10.0, 0.02, False),            # full path; keeps / moves chains in and out of near-criticality
-             (R.SCALE_SUBTREE, big, 0.01, 0.02, False),         # too large for the incremental path
+             (R.SCALE_SUBTREE, big, 0.01, 0.02, False),         # hangs off the root: evaluated from scratch
+             (R.SCALE_SUBTREE, mid, 0.01, 0.1, False), (R.SCALE_SUBTREE_CONTRA, mid2, 0.1, 0.02, False),
+             (R.SCALE_RATE_SUBTREE, mid, 100.0, 3.0, False), (R.SCALE_SUBTREE_CONTRA, mid, 0.1, 0.03, False),
+             (R.SCALE_RATE_SUBTREE, mid2, 100.0, 3.0, False), (R.SCALE_SUBTREE, mid2, 0.01, 0.05, False),
              (R.SLIDE_NODE, -1, 0.01, 1.0, False), (R.SCALE_NORM_TREE_CONTRA_M, 0, 100.0, 1.0, True),
              (R.SLIDE_NODE_CONTRA, 1, 0.1, 0.3, True), (R.SCALE_BRANCH, 1, 100.0, 10.0, True), (R.SLIDE_NODE, -1, 0.01, 3.0, False),
              (R.SLIDE_BRACE, -1, 0.01, 0.02, False), (R.SCALE_BRANCH, -1, 100.0, 30.0, False), (R.SLIDE_NODE, -1, 0.01, 0.5, False)]
