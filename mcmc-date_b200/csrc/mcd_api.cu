@@ -918,7 +918,7 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
     CU_TRY(h, cudaGetLastError());
     return 0;
   }
-  mh_propose_kernel<<<n, 256, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
+  mh_propose_kernel<<<n, 64, 0, st>>>(h->d_chain.as<double>(), h->d_undo.as<double>(), h->d_rng.as<int2>(), h->d_meta.as<int4>(),
                                        h->d_lq.as<double>(), T, P, h->undo_stride, n);
   // Sub-tree moves on a given node that are too large for the per-chain incremental path still change the residual on
   // the sub tree's branches only: y' = y + Sigma^-1[:, A] delta_A is a contraction over the k-blocks covering A (all
@@ -943,10 +943,25 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
     if (h->oz_S == 6) { MCD_LAUNCH_RANGE(6); } else { MCD_LAUNCH_RANGE(7); }
 #undef MCD_LAUNCH_RANGE
     h->launches += 2;
-    h->force_sym = true;  // d_y holds y = Sigma^-1 dx (not the Cholesky-form z)
-    const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st, true);
-    h->force_sym = false;
-    if (rc) return -1;
+    if (!getenv("MCD_MH_RANGE_FULL_POSTERIOR")) {  // score the move from the sub tree alone
+#define MCD_LAUNCH_RDELTA(CC)                                                                                              \
+  mh_range_delta_kernel<CC><<<n, 64, 0, st>>>(h->dm, T, h->d_chain.as<double>(), h->d_undo.as<double>(), h->undo_stride,  \
+      h->d_meta.as<int4>(), h->d_chain_y.as<double>(), h->d_y.as<double>(), h->d_chain_out.as<double>(),                   \
+      h->d_chain_status.as<int32_t>(), h->d_new_out.as<double>(), h->d_new_status.as<int32_t>(), mode, node, size, n)
+      switch (h->dm.clock) {
+        case 0: MCD_LAUNCH_RDELTA(0); break;
+        case 1: MCD_LAUNCH_RDELTA(1); break;
+        case 2: MCD_LAUNCH_RDELTA(2); break;
+        default: MCD_LAUNCH_RDELTA(3); break;
+      }
+#undef MCD_LAUNCH_RDELTA
+      h->launches += 1;
+    } else {  // A/B switch: the full value-only posterior kernel on y'
+      h->force_sym = true;  // d_y holds y = Sigma^-1 dx (not the Cholesky-form z)
+      const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st, true);
+      h->force_sym = false;
+      if (rc) return -1;
+    }
   }
   MhYUpdate Y{};
   Y.mode = 0; Y.K = h->K; Y.ldk = h->ldk; Y.ldy = h->ldy; Y.ldyc = h->ldyc; Y.y_cur = h->d_chain_y.as<double>(); Y.y_new = h->d_y.as<double>();

@@ -350,13 +350,18 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
   double* row = states + (size_t)b * S;
   const int OR = 5 + N;
   if (tid == 0) sh_sum = 0.0;
+  const int nthr = blockDim.x;  // 64: the serial part of a proposal is latency, so many chains per SM beat many threads per chain
   if (P.kind == MH_SCALE_VAR_TREE) {  // sample mean of the rates without the stem (scaleVarianceAndTreeF)
     double s = 0.0;
-    for (int i = 1 + tid; i < N; i += 256) s += row[OR + i];
+    for (int i = 1 + tid; i < N; i += nthr) s += row[OR + i];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((tid & 31) == 0) sh_warp[tid >> 5] = s;
     __syncthreads();
-    if (tid == 0) sh_sum = ((sh_warp[0] + sh_warp[1]) + (sh_warp[2] + sh_warp[3])) + ((sh_warp[4] + sh_warp[5]) + (sh_warp[6] + sh_warp[7]));
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (nthr >> 5); ++w) t += sh_warp[w];
+      sh_sum = t;
+    }
     __syncthreads();
   }
   if (tid == 0) {
@@ -374,7 +379,7 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
   int pos = 0;
   for (int o = 0; o < nops; ++o) {
     const MhOp op = ops[o];
-    for (int i = tid; i < op.cnt; i += 256) {
+    for (int i = tid; i < op.cnt; i += nthr) {
       MCD_ASSERT(pos + i < undo_stride);
       const double old = row[op.off + i];
       ub[pos + i] = old;
@@ -391,7 +396,7 @@ mh_propose_kernel(double* __restrict__ states, double* __restrict__ undo, int2* 
     pos += op.cnt;
     __syncthreads();  // ranges may overlap (a braced node that is the child of another): strictly in order
   }
-  if (tid < nops) rng[(size_t)b * MH_MAX_OPS + tid] = make_int2(ops[tid].off, ops[tid].cnt);
+  for (int o = tid; o < nops; o += nthr) rng[(size_t)b * MH_MAX_OPS + o] = make_int2(ops[o].off, ops[o].cnt);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -790,6 +795,155 @@ mh_accept_kernel(double* __restrict__ states, const double* __restrict__ undo, c
       for (int i = tid; i < r.y; i += 256) row[r.x + i] = ub[pos + i];
       __syncthreads();
     }
+  }
+}
+
+// Large sub-tree moves on a given node j (scale sub tree, its contrary form, scale rate sub tree): the residual and every
+// prior term change inside the sub tree [j, j + size) only, and the rank-limited contraction has already produced
+// y' = y + Sigma^-1[:, A] delta_A in y_new.  One CTA per chain scores the proposed state in O(size):
+//   quad' = quad + delta . (y + y')   (= 2 delta.y + delta^T Sigma^-1 delta),
+// clock terms of the sub tree's branches, ln p1 of its inner nodes, the node priors incident to its nodes (an entry shared
+// by several moved nodes is accounted for by the one with the smallest index).  Old values come from the undo log by
+// direct indexing (layout: see delta_split_kernel).  mode: 0 heights, 1 heights + rates (contrary), 2 rates.
+template <int CLOCK>
+__global__ void __launch_bounds__(256)
+mh_range_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict__ states, const double* __restrict__ undo,
+                      int undo_stride, const int4* __restrict__ meta, const double* __restrict__ y_cur,
+                      const double* __restrict__ y_new, const double* __restrict__ cur_out, const int* __restrict__ cur_status,
+                      double* __restrict__ new_out, int* __restrict__ new_status, int mode, int j, int size, int B) {
+  __shared__ double s_red[8][4];
+  __shared__ int s_bad[8];
+  const int chain = blockIdx.x, tid = threadIdx.x;
+  if (chain >= B) return;
+  if (meta[chain].x == 0) return;  // invalid proposal: the accept kernel leaves the chain where it is
+  const int N = M.N, OH = 3, OR = 5 + N;
+  const double* row = states + (size_t)chain * M.S;
+  const double* h = row + OH;
+  const double* r = row + OR;
+  const double* ub = undo + (size_t)chain * undo_stride;
+  const double* yc = y_cur + (size_t)chain * T.ldyc;
+  const double* yn = y_new + (size_t)chain * M.ldy;
+  const double la = row[0], mu = row[1], H = row[2], m = row[3 + N], v = row[4 + N];
+  const double sc = H * m;
+  const double lgk_v = CLOCK == 0 ? lgamma(1.0 / v) : 0.0, ln_v = log(v);
+  const bool nearcrit = 1e-6 > fabs(la - mu);
+  const bool bd_series = fabs(la - mu) * fmax(1.0, fabs(h[0])) < 0.25;
+  const bool hmove = mode != 2;
+  auto old_h = [&](int x) -> double { return hmove && x >= j && x < j + size ? ub[x - j] : h[x]; };
+  double q = 0.0, d_clock = 0.0, d_bd = 0.0, d_A = 0.0;
+  bool bad = false;
+  for (int i = j + tid; i < j + size; i += blockDim.x) {
+    const int pe = T.parent[i], p = pe & 0x7fffffff;
+    const double hi_n = h[i], hp_n = h[p], r_n = r[i];
+    const double hi_o = old_h(i), hp_o = old_h(p);
+    const double r_o = mode == 0 ? r_n : mode == 2 ? ub[i - j] : (i > j ? ub[size + (i - j - 1)] : ub[2 * size - 1]);
+    const double t_n = hp_n - hi_n, t_o = hp_o - hi_o;
+    const bool ok = (t_n > 0.0) && (r_n > 0.0);
+    bad = bad || !ok;
+    const int k = branch_of(i, M.root_r);
+    const double d = (t_n * r_n) * sc - (t_o * r_o) * sc;
+    q = fma(d, yc[k] + yn[k], q);
+    if (ok) d_clock += mh_clock_term<CLOCK>(r_n, t_n, v, lgk_v, ln_v) - mh_clock_term<CLOCK>(r_o, t_o, v, lgk_v, ln_v);
+    if (hmove) {
+      if (pe >= 0 && !nearcrit) d_bd += ln_p1<false>(la, mu, hi_n, bd_series).v - ln_p1<false>(la, mu, hi_o, bd_series).v;
+      for (int e = M.inc_off[i]; e < M.inc_off[i + 1]; ++e) {
+        const int2 ent = M.inc_ent[e];
+        if (ent.x == INC_CAL) {
+          double dh, dH;
+          int f = 0;
+          d_A += calibration_term(M, ent.y, H, hi_n, &dh, &dH, &f) - calibration_term(M, ent.y, H, hi_o, &dh, &dH, &f);
+        } else if (ent.x == INC_BRACE) {
+          const int j0 = M.br_off[ent.y], j1 = M.br_off[ent.y + 1];
+          bool owner = true;
+          for (int e2 = j0; e2 < j1; ++e2) owner = owner && !(M.br_node[e2] < i && M.br_node[e2] >= j);
+          if (!owner) continue;
+          const double sd = M.br_sd[ent.y];
+          double sn = 0.0, so = 0.0;
+          bool eqn = true, eqo = true;
+          const double hn0 = h[M.br_node[j0]], ho0 = old_h(M.br_node[j0]);
+          for (int e2 = j0; e2 < j1; ++e2) {
+            const double a_n = h[M.br_node[e2]], a_o = old_h(M.br_node[e2]);
+            eqn = eqn && (a_n == hn0);
+            eqo = eqo && (a_o == ho0);
+            sn += a_n;
+            so += a_o;
+          }
+          const double mn = sn / (double)(j1 - j0), mo = so / (double)(j1 - j0);
+          double vn = 0.0, vo = 0.0;
+          for (int e2 = j0; e2 < j1; ++e2) {
+            const double dn = h[M.br_node[e2]] - mn, d_o = old_h(M.br_node[e2]) - mo;
+            vn += -(dn * dn) / (2.0 * sd * sd);
+            vo += -(d_o * d_o) / (2.0 * sd * sd);
+          }
+          d_A += (eqn ? 0.0 : vn) - (eqo ? 0.0 : vo);
+        } else {
+          const int ny = M.con_y[ent.y], no = M.con_o[ent.y], other = ny == i ? no : ny;
+          if (other < i && other >= j) continue;  // the other node moved too and has the smaller index
+          const double s = M.con_s[ent.y];
+          const double hYn = h[ny], hOn = h[no], hYo = old_h(ny), hOo = old_h(no);
+          const double tn = (hYn < hOn) ? 0.0 : -((hYn - hOn) * (hYn - hOn)) / (2.0 * s * s);
+          const double to = (hYo < hOo) ? 0.0 : -((hYo - hOo) * (hYo - hOo)) / (2.0 * s * s);
+          d_A += tn - to;
+        }
+      }
+    }
+  }
+  // block sums: shuffle tree per warp, fixed warp order (deterministic)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+    d_clock += __shfl_xor_sync(0xffffffffu, d_clock, o);
+    d_bd += __shfl_xor_sync(0xffffffffu, d_bd, o);
+    d_A += __shfl_xor_sync(0xffffffffu, d_A, o);
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if ((tid & 31) == 0) {
+    s_red[tid >> 5][0] = q; s_red[tid >> 5][1] = d_clock; s_red[tid >> 5][2] = d_bd; s_red[tid >> 5][3] = d_A;
+    s_bad[tid >> 5] = bad ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    q = d_clock = d_bd = d_A = 0.0;
+    int anybad = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      q += s_red[w][0]; d_clock += s_red[w][1]; d_bd += s_red[w][2]; d_A += s_red[w][3];
+      anybad |= s_bad[w];
+    }
+    const double* o0 = cur_out + (size_t)chain * 8;
+    double* o1 = new_out + (size_t)chain * 8;
+    const double NINF = -CUDART_INF;
+    int st = cur_status[chain] & ST_NEARCRIT;
+    if (anybad) {
+      o1[0] = o0[0]; o1[1] = NINF; o1[2] = NINF; o1[3] = NINF; o1[4] = o0[4]; o1[5] = o0[5]; o1[6] = NINF; o1[7] = 0.0;
+      st |= ST_ZERO;
+    } else {
+      double lnB = o0[1] + d_bd;
+      if (nearcrit) {  // literal D/E recursion on the proposed state (BirthDeath.hs:90-114)
+        const double d = la - mu;
+        double E = 0.0, bd = 0.0;
+        for (int i = N - 1; i >= 1; --i) {
+          const int pe = T.parent[i];
+          const bool inner = pe >= 0;
+          const double ti = h[pe & 0x7fffffff] - h[i];
+          const double c = inner ? E : 0.0;
+          const double yy = (mu - c * la) * ti, den = 1.0 + yy;
+          const double D = (1.0 - d * ti) / den / den;
+          E = (c + yy) / den;
+          bd += log(D * (inner ? la : 1.0));
+        }
+        lnB = (0.0 - la) + (0.0 - mu) + bd;
+      }
+      const double lnA = o0[0] + d_A, lnC = o0[2] + d_clock;
+      const double prior = lnA + lnB + lnC;
+      const double lk = o0[4] + (-0.5) * q;
+      const double d0 = ((h[0] - h[1]) * r[1] + (h[0] - h[M.root_r]) * r[M.root_r]) * sc;
+      const double jac = log(1.0 / d0);
+      const double post = prior + lk + jac;
+      if (post == NINF) st |= ST_ZERO;
+      if (post != post) st |= ST_NAN;
+      o1[0] = lnA; o1[1] = lnB; o1[2] = lnC; o1[3] = prior; o1[4] = lk; o1[5] = jac; o1[6] = post; o1[7] = 0.0;
+    }
+    new_status[chain] = st;
   }
 }
 
