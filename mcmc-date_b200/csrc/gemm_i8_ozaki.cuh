@@ -22,6 +22,9 @@
 // (kind::i8, M128 N64 K32, A operand kept in the collector across the products that share it), warps 2-9 =
 // epilogue (tcgen05.ld, Horner in FP64, row/column scales).
 #pragma once
+#ifdef MCD_CHECK
+#include <assert.h>
+#endif
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -465,6 +468,9 @@ delta_split_kernel(int N, int SL, int root_r, const int* __restrict__ parent, co
     if (moved && k >= k_lo && k < k_lo + span) {
       const int i = k + 1 < root_r ? k + 1 : k + 2;  // k > 0: node of branch k (left side i = k + 1, right side i = k + 2)
       const int p = parent[i] & 0x7fffffff;
+#ifdef MCD_CHECK
+      assert(i >= j && i < j + size && i < N && p < i && (p >= j || i == j) && 2 * size - 1 < undo_stride);
+#endif
       const double hi_n = h[i], hp_n = h[p], r_n = r[i];
       double hi_o = hi_n, hp_o = hp_n, r_o = r_n;
       if (mode != 2) {

@@ -834,6 +834,7 @@ mh_range_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict
   bool bad = false;
   for (int i = j + tid; i < j + size; i += blockDim.x) {
     const int pe = T.parent[i], p = pe & 0x7fffffff;
+    MCD_ASSERT(i < N && p < i && (p >= j || i == j) && 2 * size - 1 < undo_stride);
     const double hi_n = h[i], hp_n = h[p], r_n = r[i];
     const double hi_o = old_h(i), hp_o = old_h(p);
     const double r_o = mode == 0 ? r_n : mode == 2 ? ub[i - j] : (i > j ? ub[size + (i - j - 1)] : ub[2 * size - 1]);
