@@ -589,11 +589,12 @@ def test_mh_cycle_equals_single_steps_and_counts():
     ev.close()
 
 
-def test_heated_chains_and_mc3_swaps():
+@pytest.mark.parametrize("n_leaves", [24, 150])
+def test_heated_chains_and_mc3_swaps(n_leaves):
     """MC3 (app/Main.hs:476-479): heated acceptance ratio and slot swaps against the host restatement; stepping-stone heats
-    (likelihood only, app/Main.hs:511-543)"""
+    (likelihood only, app/Main.hs:511-543).  24 leaves: single-launch small-tree step; 150 leaves: fused incremental step."""
     C, G = 4, 12
-    mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r = _mh_setup(24, C * G, n_brace=0)
+    mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r = _mh_setup(n_leaves, C * G, n_brace=0)
     R = mh_ref
     ladder = np.array([1.0, 0.7, 0.4, 0.1])
     ev.mc3_configure(C * G, 0, C, ladder, ladder)
