@@ -183,7 +183,9 @@ def roofline(oz_s, K, B, gemm_ms, kms, ncalls, args):
                 "unit": "TFLOP/s", "frac": fp64_equiv / FP64_NOMINAL_TFLOPS, "traffic": traffic,
                 "peak_source": "nominal FP64 (148 SMs x 64 FMA/clk x 1965 MHz); MEASURED_PEAKS.json has no FP64 entry; "
                                "cublasDgemm on this shape measured 35.6 TFLOP/s executed (profiles/)",
-                "kernel_ms": gemm_ms, "algorithmic_flops_per_launch": flops_alg, "step_share": share}
+                "kernel_ms": gemm_ms, "algorithmic_flops_per_launch": flops_alg, "step_share": share,
+                "hbm_kernels": hbm_kernels(oz_s, K, B, kms, ncalls)}
+    hbm = hbm_kernels(oz_s, K, B, kms, ncalls)
     pairs = oz_s * (oz_s + 1) // 2
     ops = pairs * flops_alg                                # int8 multiply-adds x 2 the split needs, unpadded K
     achieved = ops / (gemm_ms * 1e-3) / 1e12
@@ -208,7 +210,29 @@ def roofline(oz_s, K, B, gemm_ms, kms, ncalls, args):
                                 "ratio_to_fp64_peak": fp64_equiv / FP64_NOMINAL_TFLOPS,
                                 "note": "2 K^2 FP64 flops per chain delivered by exact int8 products (Ozaki split); "
                                         "the FP64 DMMA kernel it replaces reaches 0.92 of that peak"},
-            "step_share": share}
+            "step_share": share, "hbm_kernels": hbm}
+
+
+def hbm_kernels(oz_s, K, B, kms, ncalls):
+    """The two HBM-side kernels of the step against the measured copy bandwidth (north_star: "achieved HBM GB/s for the
+    gather and prior kernels"): algorithmic bytes per chain x chains / CUDA-event time."""
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        peak, src = 6650.0, "fallback 6.65 TB/s (of fallback)"
+    N = K + 2
+    S = 5 + 2 * N
+    ld8 = (K + 63) // 64 * 64
+    k1_bytes = B * (8 * S + (oz_s * ld8 if oz_s else 8 * K))     # state row in, digit planes (or FP64 residuals) out
+    k3_bytes = B * (8 * S + 8 * K + 8 * S + 64)                  # state row + y in, gradient + ln-posterior parts out
+    out = []
+    for name, nbytes, ms in (("residual_split_kernel (tree gather + residuals + digit planes)", k1_bytes, kms[0] / max(1, ncalls)),
+                             ("posterior_kernel (priors, Jacobian, gradient)", k3_bytes, kms[2] / max(1, ncalls))):
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        out.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                    "algorithmic_bytes_per_launch": nbytes, "kernel_ms": ms, "peak_source": src})
+    return out
 
 
 # --------------------------------------------------------------------------------- GPU arm
