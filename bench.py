@@ -232,6 +232,8 @@ def hbm_kernels(oz_s, K, B, kms, ncalls):
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         out.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                     "algorithmic_bytes_per_launch": nbytes, "kernel_ms": ms, "peak_source": src})
+    out[1]["note"] = ("ncu (profiles/r01_ncu_summary.md): 216 M warp instructions, 60 % of the issue slots, FP64 pipe 37 % -- FP64 "
+                      "transcendentals per node (log, exp, reciprocal) bind this kernel before HBM does")
     return out
 
 
