@@ -878,6 +878,42 @@ def test_mh_edge_cases():
     ev2.close()
 
 
+def test_full_size_mh_cycle_is_consistent_with_fresh_evaluations():
+    """BASELINE's largest shape (1000 leaves, K = 1997): a slice of the reference's proposal cycle -- small moves (fused
+    incremental step), large sub-tree moves (k-block-range contraction), global moves (from scratch) -- then the resident
+    ln-posterior parts, statuses and cached contraction results must be those of a fresh evaluation of the resident states,
+    and a second run from the same start must reproduce the chains bit for bit."""
+    from mcmc_date_b200 import mh_cycle
+    md, h = synth.synthetic_model(1000, seed=synth.BASE_SEED + 4, n_cal=16, n_con=8, n_brace=4)
+    B = 1024
+    X = synth.synthetic_states(md, h, B)
+    props = mh_cycle.reference_cycle(md)
+    rng = np.random.default_rng(0)
+    pick = sorted(rng.choice(len(props), size=260, replace=False))
+    sub = [props[i][:5] + (1,) for i in pick] + [p[:5] + (1,) for p in props if p[0] in (binding.MH_SLIDE_BRACE, binding.MH_PULLEY,
+                                                                                       binding.MH_SCALE_VAR_TREE)]
+    ev = binding.Evaluator(md, max_batch=B)
+    ev.mh_set_incremental(True, refresh_every=100)
+    runs = []
+    for _ in range(2):
+        ev.chains_set(X)
+        assert ev.mh_incremental_active()
+        acc, inv, _ = ev.mh_cycle(sub, 1, seed=77, iteration0=5)
+        runs.append(ev.chains_get())
+        assert (inv == 0).all() and (acc > 0).sum() > 0.9 * len(sub)
+    (X1, o1, s1), (X2, o2, s2) = runs
+    assert np.array_equal(X1, X2) and np.array_equal(o1, o2) and np.array_equal(s1, s2)
+    assert (np.abs(X1 - X).max(axis=1) > 0).all()
+    of, sf = ev.eval(X1)
+    assert relerr(o1[:, :7], of[:, :7]).max() < 1e-10 and np.array_equal(s1, sf)
+    # the cached y still describes the resident states: one more small move per chain, scored incrementally, then checked again
+    ev.mh_step(binding.MH_SLIDE_NODE, -1, 0.001, seed=78, iteration=0)
+    X3, o3, s3 = ev.chains_get()
+    of3, sf3 = ev.eval(X3)
+    assert relerr(o3[:, :7], of3[:, :7]).max() < 1e-10 and np.array_equal(s3, sf3)
+    ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
