@@ -151,29 +151,29 @@ int mcd_nuts(mcd_handle* h, int32_t n_chains, const double* theta0 /*[B][D]*/, c
  * n chains and evaluates them; mcd_mh_step applies ONE proposal to every resident chain in place, evaluates the proposed
  * states (value-only path), and accepts or rejects per chain; mcd_mh_cycle runs sweeps over a whole list of proposals
  * without a host round trip; mcd_chains_get reads states / ln-posterior parts back.
- * Every proposal of the reference's cycle (app/Definitions.hs:145-278) is available; lib/ = lib/Mcmc/Tree/Proposal:
+ * Every proposal of the reference's cycle (app/Definitions.hs:145-279) is available; lib/ = lib/Mcmc/Tree/Proposal:
  *   kind                            reference                                           `node` argument      `param`
- *   MCD_MH_SLIDE_NODE               slideNodeAtUltrametric      lib/Ultrametric.hs:50-62     inner node | -1      sd
- *   MCD_MH_SCALE_SUBTREE            scaleSubTreeAtUltrametric   lib/Ultrametric.hs:126-147   inner node | -1      sd
- *   MCD_MH_PULLEY                   pulleyUltrametric           lib/Ultrametric.hs:219-316   ignored              sd
- *   MCD_MH_SLIDE_BRACE              slideBracedNodesUltrametric lib/Brace.hs:30-82           brace index | -1     sd
- *   MCD_MH_SCALE_BRANCH             scaleBranch (rate tree)     lib/Unconstrained.hs:52-92   node >= 1 | -1       shape k
- *   MCD_MH_SCALE_RATE_SUBTREE       scaleSubTreeAt (rate tree)  lib/Unconstrained.hs:94-170  inner node | -1      shape k
- *   MCD_MH_SCALE_NORM_TREE_CONTRA_M scaleNormAndTreeContrarily  lib/Unconstrained.hs:260-306 on (rateMean, rates)     k
- *   MCD_MH_SCALE_NORM_TREE_CONTRA_H   "                         app/Definitions.hs:249-260   on (timeHeight, rates)   k
- *   MCD_MH_SCALE_VAR_TREE           scaleVarianceAndTree        lib/Unconstrained.hs:308-371 ignored              shape k
- *   MCD_MH_SCALE_VAR_TREE_AUTO      scaleVarianceAndTreeAutocorrelated  lib/Unconstrained.hs:380-439 ignored      shape k
- *   MCD_MH_SLIDE_NODE_CONTRA        slideNodesAtContrarily      lib/Contrary.hs:60-131       inner node | -1      sd
- *   MCD_MH_SCALE_SUBTREE_CONTRA     scaleSubTreesAtContrarily   lib/Contrary.hs:283-377      inner node | -1      sd
- *   MCD_MH_SLIDE_BRACE_CONTRA       slideBracedNodesContrarily  lib/Brace.hs:88-209          brace index | -1     sd
- *   MCD_MH_SLIDE_ROOT_CONTRA        slideRootContrarily         lib/Contrary.hs:172-246      ignored              sd
- *   MCD_MH_SCALE_RATES_TREE_CONTRA  scaleRatesAndTreeContrarily lib/Contrary.hs:425-486      ignored              sd
- *   MCD_MH_SCALE_SCALAR             scaleUnbiased (`mcmc`)      app/Definitions.hs:262-266   0 lambda 1 mu 2 H 3 m 4 v   k
- *   MCD_MH_SCALE_H_M_CONTRA         scaleContrarily (`mcmc`)    app/Definitions.hs:251       ignored              shape k
+ *   MCD_MH_SLIDE_NODE               slideNodeAtUltrametric      lib/Ultrametric.hs:50-96     inner node | -1      sd
+ *   MCD_MH_SCALE_SUBTREE            scaleSubTreeAtUltrametric   lib/Ultrametric.hs:126-186   inner node | -1      sd
+ *   MCD_MH_PULLEY                   pulleyUltrametric           lib/Ultrametric.hs:228-316   ignored              sd
+ *   MCD_MH_SLIDE_BRACE              slideBracedNodesUltrametric lib/Brace.hs:37-90           brace index | -1     sd
+ *   MCD_MH_SCALE_BRANCH             scaleBranch (rate tree)     lib/Unconstrained.hs:45-85   node >= 1 | -1       shape k
+ *   MCD_MH_SCALE_RATE_SUBTREE       scaleSubTreeAt (rate tree)  lib/Unconstrained.hs:87-175  inner node | -1      shape k
+ *   MCD_MH_SCALE_NORM_TREE_CONTRA_M scaleNormAndTreeContrarily  lib/Unconstrained.hs:232-284 on (rateMean, rates)     k
+ *   MCD_MH_SCALE_NORM_TREE_CONTRA_H   "                         app/Definitions.hs:241-253   on (timeHeight, rates)   k
+ *   MCD_MH_SCALE_VAR_TREE           scaleVarianceAndTree        lib/Unconstrained.hs:286-371 ignored              shape k
+ *   MCD_MH_SCALE_VAR_TREE_AUTO      scaleVarianceAndTreeAutocorrelated  lib/Unconstrained.hs:381-439 ignored      shape k
+ *   MCD_MH_SLIDE_NODE_CONTRA        slideNodesAtContrarily      lib/Contrary.hs:35-131       inner node | -1      sd
+ *   MCD_MH_SCALE_SUBTREE_CONTRA     scaleSubTreesAtContrarily   lib/Contrary.hs:269-395      inner node | -1      sd
+ *   MCD_MH_SLIDE_BRACE_CONTRA       slideBracedNodesContrarily  lib/Brace.hs:98-209          brace index | -1     sd
+ *   MCD_MH_SLIDE_ROOT_CONTRA        slideRootContrarily         lib/Contrary.hs:173-267      ignored              sd
+ *   MCD_MH_SCALE_RATES_TREE_CONTRA  scaleRatesAndTreeContrarily lib/Contrary.hs:420-486      ignored              sd
+ *   MCD_MH_SCALE_SCALAR             scaleUnbiased (`mcmc`)      app/Definitions.hs:259-262   0 lambda 1 mu 2 H 3 m 4 v   k
+ *   MCD_MH_SCALE_H_M_CONTRA         scaleContrarily (`mcmc`)    app/Definitions.hs:244       ignored              shape k
  * node = -1: every chain draws its own node / brace uniformly among the eligible ones.  Inner node = inner node below
  * the root (the reference never builds these proposals for the root: HandleNode, app/Definitions.hs:132-138).
  * param, tune: standard deviation sd (truncated-normal moves, sd' = tune * sd, Internal.hs:117) or shape k of the
- * multiplier u ~ Gamma(k / tune, tune / k) (Unconstrained.hs:112, `mcmc` Scale proposals).
+ * multiplier u ~ Gamma(k / tune, tune / k) (Unconstrained.hs:103, `mcmc` Scale proposals).
  * use_root_jacobian: include jacobianRootBranch in the ratio (proposals the reference lifts with liftProposalWith
  * jacobianRootBranch: the [R] ones of app/Definitions.hs).  accepted[b] (nullable) = 1 / 0, or -1 where the reference would
  * call `error` (truncatedNormalDistr: bounds crossed -- the chain's tree is invalid); such chains are left unchanged.
@@ -190,7 +190,7 @@ int mcd_chains_get(mcd_handle* h, int32_t n_chains, double* states /*[B][S] or N
                    int32_t* status /*[B] or NULL*/);
 int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double param, double tune, int32_t use_root_jacobian, uint64_t seed,
                 uint32_t iteration, int32_t* accepted /*[B] or NULL*/);
-/* The Hamiltonian proposal of the reference's cycle (`maybeHamiltonianProposal`, app/Definitions.hs:281-283) on the
+/* The Hamiltonian proposal of the reference's cycle (`maybeHamiltonianProposal`, app/Definitions.hs:276-278) on the
  * RESIDENT chains: one mcd_nuts transition per chain, positions packed from and written back to the chains' state rows on
  * the device, then the chains' ln-posterior parts (and the cached contraction results) are re-evaluated.  Momenta are
  * drawn on the device.  The fixed entries (root / leaf heights, rate stem, H without calibrations) must agree across the
@@ -198,7 +198,7 @@ int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double param, double 
 int mcd_chains_nuts(mcd_handle* h, const double* inv_mass /*[D]*/, const double* step_size /*[B]*/, int32_t max_depth,
                     uint64_t seed, uint32_t iteration, double* accept_stat /*[B]*/, int32_t* info /*[B][4]*/,
                     int32_t* status /*[B]*/);
-/* One entry of a proposal cycle (the reference's `Cycle`, app/Definitions.hs:262-285): `repeat` = the proposal's weight. */
+/* One entry of a proposal cycle (the reference's `Cycle`, app/Definitions.hs:256-279): `repeat` = the proposal's weight. */
 typedef struct mcd_mh_proposal {
   int32_t kind, node;
   double param, tune;

@@ -2,30 +2,30 @@
 // (SURVEY.md 8f rank 4).
 //
 // The reference's default sampler cycles through thousands of small proposals per iteration
-// (app/Definitions.hs:145-278), each followed by a full prior + likelihood evaluation.  Here the chains' states stay
+// (app/Definitions.hs:145-279), each followed by a full prior + likelihood evaluation.  Here the chains' states stay
 // resident on the device: one call applies one proposal to every chain (in place, with an undo log), the batched
 // value-only evaluation scores the proposed states, and an accept kernel keeps or restores them.
 //
 // Every proposal of the reference's cycle is restated (first-party code of the reference unless noted):
 //   kind                         reference                                                              state touched
-//   MH_SLIDE_NODE                slideNodeAtUltrametric          Proposal/Ultrametric.hs:50-62          h_j
-//   MH_SCALE_SUBTREE             scaleSubTreeAtUltrametric       Proposal/Ultrametric.hs:126-147        heights of sub tree j
-//   MH_PULLEY                    pulleyUltrametric               Proposal/Ultrametric.hs:219-316        all heights below the root
-//   MH_SLIDE_BRACE               slideBracedNodesUltrametric     Proposal/Brace.hs:30-51                heights of the braced nodes
-//   MH_SCALE_BRANCH              scaleBranch (rate tree)         Proposal/Unconstrained.hs:52-66        r_i
-//   MH_SCALE_RATE_SUBTREE        scaleTree on a sub tree         Proposal/Unconstrained.hs:105-139      rates of sub tree j (with stem)
-//   MH_SCALE_NORM_TREE_CONTRA_M  scaleNormAndTreeContrarily      Proposal/Unconstrained.hs:260-306      m, all rates
-//   MH_SCALE_NORM_TREE_CONTRA_H  (same, on timeHeight)           app/Definitions.hs:249-260             H, all rates
-//   MH_SCALE_VAR_TREE            scaleVarianceAndTree            Proposal/Unconstrained.hs:308-371      v, all rates
-//   MH_SCALE_VAR_TREE_AUTO       scaleVarianceAndTreeAutocorr.   Proposal/Unconstrained.hs:380-439      v, all rates
-//   MH_SLIDE_NODE_CONTRA         slideNodesAtContrarily          Proposal/Contrary.hs:60-131            h_j, r_j, rates of the children
-//   MH_SCALE_SUBTREE_CONTRA      scaleSubTreesAtContrarily       Proposal/Contrary.hs:283-377           heights + rates of sub tree j
-//   MH_SLIDE_BRACE_CONTRA        slideBracedNodesContrarily      Proposal/Brace.hs:88-143               braced heights + adjacent rates
-//   MH_SLIDE_ROOT_CONTRA         slideRootContrarily             Proposal/Contrary.hs:172-246           H, all heights, root-child rates
-//   MH_SCALE_RATES_TREE_CONTRA   scaleRatesAndTreeContrarily     Proposal/Contrary.hs:425-486           lambda, mu, all heights
-//   MH_SCALE_SCALAR              scaleUnbiased (`mcmc` package)  app/Definitions.hs:262-266             one of lambda, mu, H, m, v
-//   MH_SCALE_H_M_CONTRA          scaleContrarily (`mcmc`)        app/Definitions.hs:251                 H, m
-// Truncated-normal moves use truncatedNormalSample (Proposal/Internal.hs:100-137) on the reference's own truncated normal
+//   MH_SLIDE_NODE                slideNodeAtUltrametric          Proposal/Ultrametric.hs:50-96          h_j
+//   MH_SCALE_SUBTREE             scaleSubTreeAtUltrametric       Proposal/Ultrametric.hs:126-186        heights of sub tree j
+//   MH_PULLEY                    pulleyUltrametric               Proposal/Ultrametric.hs:228-316        all heights below the root
+//   MH_SLIDE_BRACE               slideBracedNodesUltrametric     Proposal/Brace.hs:37-90                heights of the braced nodes
+//   MH_SCALE_BRANCH              scaleBranch (rate tree)         Proposal/Unconstrained.hs:45-85        r_i
+//   MH_SCALE_RATE_SUBTREE        scaleTree on a sub tree         Proposal/Unconstrained.hs:87-175      rates of sub tree j (with stem)
+//   MH_SCALE_NORM_TREE_CONTRA_M  scaleNormAndTreeContrarily      Proposal/Unconstrained.hs:232-284      m, all rates
+//   MH_SCALE_NORM_TREE_CONTRA_H  (same, on timeHeight)           app/Definitions.hs:241-253             H, all rates
+//   MH_SCALE_VAR_TREE            scaleVarianceAndTree            Proposal/Unconstrained.hs:286-371      v, all rates
+//   MH_SCALE_VAR_TREE_AUTO       scaleVarianceAndTreeAutocorr.   Proposal/Unconstrained.hs:381-439      v, all rates
+//   MH_SLIDE_NODE_CONTRA         slideNodesAtContrarily          Proposal/Contrary.hs:35-131            h_j, r_j, rates of the children
+//   MH_SCALE_SUBTREE_CONTRA      scaleSubTreesAtContrarily       Proposal/Contrary.hs:269-395           heights + rates of sub tree j
+//   MH_SLIDE_BRACE_CONTRA        slideBracedNodesContrarily      Proposal/Brace.hs:98-209               braced heights + adjacent rates
+//   MH_SLIDE_ROOT_CONTRA         slideRootContrarily             Proposal/Contrary.hs:173-267           H, all heights, root-child rates
+//   MH_SCALE_RATES_TREE_CONTRA   scaleRatesAndTreeContrarily     Proposal/Contrary.hs:420-486           lambda, mu, all heights
+//   MH_SCALE_SCALAR              scaleUnbiased (`mcmc` package)  app/Definitions.hs:259-262             one of lambda, mu, H, m, v
+//   MH_SCALE_H_M_CONTRA          scaleContrarily (`mcmc`)        app/Definitions.hs:244                 H, m
+// Truncated-normal moves use truncatedNormalSample (Proposal/Internal.hs:107-138) on the reference's own truncated normal
 // (lib/Statistics/Distribution/TruncatedNormal.hs:61-131):
 //   z(m) = Phi((b-m)/s') - Phi((a-m)/s'),  quantile(p) = erfinv(2 (p z + Phi(alpha)) - 1) sqrt(2) s' + m,
 //   Hastings factor q = density_{x'}(x) / density_{x}(x') = z(x) / z(x').
@@ -724,7 +724,7 @@ mh_delta_kernel(const DevModel M, const MhTopo T, const double* __restrict__ P, 
 }
 
 // ln r = beta_p (ln prior(y) - ln prior(x)) + beta_l (ln lik(y) - ln lik(x)) + ln(q |J|) (+ the change of the root-branch
-// Jacobian for proposals lifted with jacobianRootBranch, app/Definitions.hs:145-150); accept iff ln U < ln r.
+// Jacobian for proposals lifted with jacobianRootBranch, app/Definitions.hs:139-150); accept iff ln U < ln r.
 // beta: heat of the chain's current temperature slot (MC3: prior and likelihood; stepping stone: likelihood only);
 // slot == nullptr: cold chains.  Rejected chains get their values back from the undo log, ranges in reverse order.
 // counters[0] += accepted, counters[1] += invalid (nullable).  One CTA per chain.

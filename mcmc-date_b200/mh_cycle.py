@@ -1,4 +1,4 @@
-"""Host-side mirror of the reference's proposal cycle (`proposals`, app/Definitions.hs:125-285): which proposals exist for a
+"""Host-side mirror of the reference's proposal cycle (`proposals`, app/Definitions.hs:125-279): which proposals exist for a
 given tree, on which nodes, with which standard deviations / shapes, weights and root-branch Jacobian lifts.  The device
 executes the list (binding.Evaluator.mh_cycle -> mcd_mh_cycle); order, tuning and monitors stay with the host."""
 from __future__ import annotations
@@ -33,7 +33,7 @@ def weight_n_branches(n: int) -> int:
 
 def reference_cycle(md: _m.ModelDesc, calibrations_available: bool | None = None, tune: float = 1.0):
     """-> list of (kind, node, param, tune, use_root_jacobian, weight) in the order of `proposals`
-    (app/Definitions.hs:262-285; the Hamiltonian proposal is mcd_nuts and not part of this list)"""
+    (app/Definitions.hs:256-279; the Hamiltonian proposal is mcd_nuts and not part of this list)"""
     parent = np.asarray(md.parent)
     N = len(parent)
     child, depth, plen = _topology(parent)
@@ -49,7 +49,7 @@ def reference_cycle(md: _m.ModelDesc, calibrations_available: bool | None = None
     def w_depth(i):           # min (wMin + depth - 2) wMax with wMin 3, wMax 8
         return min(3 + depth[i] - 2, 8)
 
-    # hyper-parameters (:264-268)
+    # hyper-parameters (:259-263)
     for scalar in (0, 1, 3, 4):
         add(_b.MH_SCALE_SCALAR, scalar, 10.0, False, w)
     if len(inner) >= 1:
@@ -66,7 +66,7 @@ def reference_cycle(md: _m.ModelDesc, calibrations_available: bool | None = None
             add(_b.MH_SCALE_SUBTREE, i, 0.01, at_root, w_depth(i))
     for b in braces:
         add(_b.MH_SLIDE_BRACE, b, 0.01, False, 5)
-    # proposalsRateTree (:181-204)
+    # proposalsRateTree (:180-201)
     add(_b.MH_SCALE_NORM_TREE_CONTRA_M, 0, 100.0, True, w)
     add(_b.MH_SCALE_VAR_TREE, 0, 100.0, True, w)
     add(_b.MH_SCALE_VAR_TREE_AUTO, 0, 100.0, True, w)
@@ -77,7 +77,7 @@ def reference_cycle(md: _m.ModelDesc, calibrations_available: bool | None = None
         for i in allnodes:
             if child[i]:
                 add(_b.MH_SCALE_RATE_SUBTREE, i, 100.0, at_root, w_depth(i))
-    # proposalsTimeRateTreeContra (:207-224)
+    # proposalsTimeRateTreeContra (:204-224)
     for at_root in (True, False):
         nodes = [i for i in inner if (plen[i] == 1) == at_root]
         for i in nodes:
@@ -86,7 +86,7 @@ def reference_cycle(md: _m.ModelDesc, calibrations_available: bool | None = None
             add(_b.MH_SCALE_SUBTREE_CONTRA, i, 0.1, at_root, w_depth(i))
     for b in braces:
         add(_b.MH_SLIDE_BRACE_CONTRA, b, 0.1, False, 5)
-    # proposalsChangingTimeHeight (:245-260), only with calibrations
+    # proposalsChangingTimeHeight (:241-253), only with calibrations
     if cal:
         add(_b.MH_SCALE_SCALAR, 2, 3000.0, False, w)
         add(_b.MH_SCALE_H_M_CONTRA, 0, 10.0, False, w)

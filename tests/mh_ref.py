@@ -53,7 +53,7 @@ FORCED = None      # tests only: the sampled value (new height / shift / multipl
 
 
 def truncated_normal_sample(m, s, a, b, p):
-    """truncatedNormalSample (Internal.hs:100-137) -> (value, ln(qYX / qXY)) or None where the reference calls `error`"""
+    """truncatedNormalSample (Internal.hs:107-138) -> (value, ln(qYX / qXY)) or None where the reference calls `error`"""
     if not s > 0 or not a < b or a > m or b < m or m != m:
         return None
     phiA = phi2((a - m) / s)

@@ -524,7 +524,7 @@ def test_device_resident_mh_proposals_match_host_restatement(n_leaves, B):
 
 @pytest.mark.parametrize("n_leaves,B,clock", [(24, 48, 1), (24, 48, 3), (200, 24, 0)])
 def test_every_proposal_of_the_reference_cycle(n_leaves, B, clock):
-    """all 17 proposal kinds of app/Definitions.hs:145-278 (time tree, rate tree, contrary, braces, hyper-parameters),
+    """all 17 proposal kinds of app/Definitions.hs:145-279 (time tree, rate tree, contrary, braces, hyper-parameters),
     each restated literally in tests/mh_ref.py: proposed state, Hastings factor, Jacobian, acceptance -- step by step"""
     mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r = _mh_setup(n_leaves, B, clock=clock, n_brace=2, seed_off=7)
     child, size, inner, inner_list = mh_ref.topology(parent)
@@ -747,7 +747,7 @@ def test_incremental_evaluation_of_small_moves(clock):
 
 def test_nuts_on_resident_chains_equals_the_host_buffer_call():
     """mcd_chains_nuts = mcd_nuts on the chains' own HMC vectors, written back to their state rows (the Hamiltonian proposal
-    of the reference's cycle, app/Definitions.hs:281-283), followed by ordinary proposals on the moved chains"""
+    of the reference's cycle, app/Definitions.hs:276-278), followed by ordinary proposals on the moved chains"""
     import mh_ref as R
     md, h = synth.synthetic_model(150, seed=77, n_cal=3, n_con=2, n_brace=1)
     B = 40

@@ -337,7 +337,7 @@ def test_proposal_jacobians_are_the_determinants_of_the_moves(kind):
     finally:
         R.FORCED = None
     if kind == R.SCALE_VAR_TREE:
-        # Reference quirk, preserved: scaleVarianceAndTree states n ln(u - u/n + 1/n) (Unconstrained.hs:339-347), the product
+        # Reference quirk, preserved: scaleVarianceAndTree states n ln(u - u/n + 1/n) (Unconstrained.hs:308-350), the product
         # of the DIAGONAL of the move's Jacobian matrix (every rate also moves with the sample mean); the determinant is
         # u^(n-1).  Parity is with the reference, so the restatement and the kernel keep the stated factor.
         stated = lqj0 - lnq
@@ -365,14 +365,14 @@ def test_proposal_jacobians_are_the_determinants_of_the_moves(kind):
             R.FORCED = None
         if kind == R.SLIDE_ROOT_CONTRA:
             # Second reference quirk, preserved: slideRootContrarily uses -n ln u with n = nInnerNodes INCLUDING the root
-            # (Contrary.hs:172-183, 241-246) although n - 1 relative heights are divided by u: stated = determinant - ln u.
+            # (Contrary.hs:173-189, 246-267) although n - 1 relative heights are divided by u: stated = determinant - ln u.
             assert abs(R.LAST[1] - (logdet - np.log(forced / cur))) < 1e-6
         else:
             assert abs(R.LAST[1] - logdet) < 1e-6, (kind, R.LAST[1], logdet)  # the stated Jacobian is the determinant
 
 
 def test_reference_cycle_mirrors_definitions():
-    """app/Definitions.hs:125-285 on the 24-leaves-braces data set: which proposals exist, their weights and lifts"""
+    """app/Definitions.hs:125-279 on the 24-leaves-braces data set: which proposals exist, their weights and lifts"""
     from mcmc_date_b200 import binding as B, mh_cycle
     md, z = load_fixture("24-leaves-braces")
     cyc = mh_cycle.reference_cycle(md)

@@ -37,7 +37,7 @@ def main():
             dt = time.perf_counter() - t0
             print(f"{name}: {steps} steps x {B} chains in {dt * 1e3:.1f} ms = {steps * B / dt / 1e6:.2f} M proposals/s "
                   f"({dt * 1e6 / steps:.1f} us per step); acceptance {acc[0] / (steps * B):.2f}, invalid {inv[0] / (steps * B):.4f}")
-        # one sweep of the reference's whole cycle (app/Definitions.hs:262-285)
+        # one sweep of the reference's whole cycle (app/Definitions.hs:256-279)
         props = mh_cycle.reference_cycle(md)
         nsteps = sum(p[5] for p in props)
         ev.synchronize()
