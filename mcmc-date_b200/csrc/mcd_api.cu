@@ -84,6 +84,8 @@ struct mcd_handle {
   bool inc_ok = false;            // this resident set qualifies (large dense model, every chain's state valid)
   bool force_sym = false;         // value-only evaluations use the symmetric contraction (they must produce y, not L^T dx)
   int inc_steps = 0, refresh_every = 512, ldyc = 0;
+  const double* y_override = nullptr;  // see enqueue(posterior_only)
+  int y_override_ld = 0;
   int mc3_C = 0, mc3_n_global = 0, mc3_offset = 0;
   DevBuf d_nuts;                  // batched NUTS: trajectory ends, checkpoints, candidates, per-chain scalars
   size_t nuts_bytes = 0;
@@ -321,6 +323,10 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   const double* xs = d_states + (size_t)c0 * M.S;
   double* dx = h->d_dx.as<double>() + (size_t)c0 * M.ldk;
   const double* y = h->d_y.as<double>() + (size_t)c0 * M.ldy;
+  if (posterior_only && h->y_override) {  // score the states against another y buffer (the cached y of the resident chains)
+    M.ldy = h->y_override_ld;
+    y = h->y_override + (size_t)c0 * M.ldy;
+  }
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (h->timing) {
     for (int i = 0; i < 4; ++i) {
@@ -963,6 +969,23 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
       if (rc) return -1;
     }
   }
+  // Moves that leave every distance d_k = H m t_k r_k where it is -- lambda, mu, v; (H u, m / u); (m / u | H / u, rates u) --
+  // leave y = Sigma^-1 (d - mu) where it is (up to one rounding of H m): the posterior kernel scores the proposed state
+  // against the cached y, no contraction.
+  const bool same_d = inc_mode && !range &&
+                      ((kind == MH_SCALE_SCALAR && (node == 0 || node == 1 || node == 4)) || kind == MH_SCALE_H_M_CONTRA ||
+                       kind == MH_SCALE_NORM_TREE_CONTRA_M || kind == MH_SCALE_NORM_TREE_CONTRA_H) &&
+                      !getenv("MCD_MH_NO_SAME_D");
+  if (same_d) {
+    h->force_sym = true;
+    h->y_override = h->d_chain_y.as<double>();
+    h->y_override_ld = h->ldyc;
+    const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st, true);
+    h->y_override = nullptr;
+    h->force_sym = false;
+    if (rc) return -1;
+    ++h->inc_steps;  // counts towards the periodic refresh (it is taken at the next small move)
+  }
   MhYUpdate Y{};
   Y.mode = 0; Y.K = h->K; Y.ldk = h->ldk; Y.ldy = h->ldy; Y.ldyc = h->ldyc; Y.y_cur = h->d_chain_y.as<double>(); Y.y_new = h->d_y.as<double>();
   Y.P = h->d_P.as<double>(); Y.dl_n = h->d_dl_n.as<int>(); Y.dl_k = h->d_dl_k.as<int>(); Y.dl_d = h->d_dl_d.as<double>();
@@ -984,6 +1007,8 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
     Y.mode = 1;
   } else if (range) {
     Y.mode = 2;
+  } else if (same_d) {
+    Y.mode = 0;  // y unchanged
   } else {
     h->force_sym = inc_mode;  // keep producing y while the incremental mode is on
     const int rc = enqueue<false>(h, 0, n, h->d_chain.as<double>(), h->d_new_out.as<double>(), nullptr, h->d_new_status.as<int32_t>(), st);
