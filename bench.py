@@ -384,7 +384,8 @@ def run_gpu(args):
     ev.chains_set(X)
     mh = {}
     for name, kind, par in (("slide_node_incremental", binding.MH_SLIDE_NODE, 0.002),
-                            ("scale_rate_mean_and_tree_full_evaluation", binding.MH_SCALE_NORM_TREE_CONTRA_M, 3000.0)):
+                            ("scale_rate_mean_and_tree_contrarily_no_contraction", binding.MH_SCALE_NORM_TREE_CONTRA_M, 3000.0),
+                            ("scale_variance_and_tree_from_scratch", binding.MH_SCALE_VAR_TREE, 3000.0)):
         ev.mh_cycle([(kind, -1, par, 1.0, 0, 3)], 1, seed=3, iteration0=0)
         ev.synchronize()
         n_mh = 10 * args.steps
@@ -394,7 +395,8 @@ def run_gpu(args):
         mh[name] = {"value": B * world * n_mh / dt, "unit": "proposals/s", "us_per_step": 1e6 * dt / n_mh,
                     "acceptance": float(acc[0]) / (n_mh * B)}
     mh["note"] = ("mcd_mh_cycle on this rank's chains x world (per-rank wall time incl. the final synchronisation); small moves "
-                  "are scored from the cached contraction result, global moves by the full value-only evaluation")
+                  "are scored from the cached contraction result, moves that leave the distances unchanged by the posterior "
+                  "kernel against it, the remaining global moves by the full value-only evaluation")
     clocks = sampler.stop() if rank == 0 else None
     # parity guard: the timed outputs are the real thing (finite, and equal through both entry points)
     ok = bool(torch.isfinite(d_out[:, 6]).all().item()) and bool(
