@@ -121,6 +121,14 @@ int mcd_eval_grad(mcd_handle* h, int32_t n_chains, const double* states /*[B][S]
 int mcd_eval_grad_theta(mcd_handle* h, int32_t n_chains, const double* theta /*[B][D]*/,
                         const double* base_state /*[S]*/, double* out /*[B][MCD_OUT_COLS]*/,
                         double* grad_theta /*[B][D]*/, int32_t* status /*[B]*/);
+/* The same without the final wait: returns a ticket (>= 0; < 0: error) after enqueueing; the outputs are valid after
+ * mcd_wait(ticket) (or mcd_synchronize); the host buffers must stay alive and untouched until then.  Back-to-back calls
+ * overlap the PCIe fill of one with the drain of the previous one (chunk k of every call runs in order on stream k % 4 on
+ * its own slice of the staging buffers).  A double-buffered host loop: t1 = async(A); t2 = async(B); wait(t1); use A;
+ * t3 = async(A); wait(t2); use B; ...  The last 8 tickets can be waited for. */
+int64_t mcd_eval_grad_theta_async(mcd_handle* h, int32_t n_chains, const double* theta, const double* base_state, double* out,
+                                  double* grad_theta, int32_t* status);
+int mcd_wait(mcd_handle* h, int64_t ticket);
 
 /* Device-resident leapfrog trajectory (first half of SURVEY 8f rank 1): n_steps leapfrog steps of the
  * Hamiltonian H = -ln post(theta) + 1/2 p^T M^-1 p (M diagonal) for every chain, positions / momenta /

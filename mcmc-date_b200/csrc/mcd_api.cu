@@ -84,6 +84,9 @@ struct mcd_handle {
   bool inc_ok = false;            // this resident set qualifies (large dense model, every chain's state valid)
   bool force_sym = false;         // value-only evaluations use the symmetric contraction (they must produce y, not L^T dx)
   int inc_steps = 0, refresh_every = 512, ldyc = 0;
+  std::vector<double> base_host;       // base state currently on the device (theta-packed entry points)
+  cudaEvent_t ticket_ev[8][N_STREAMS] = {};  // completion events of the last 8 asynchronous calls
+  int64_t next_ticket = 0;
   const double* y_override = nullptr;  // see enqueue(posterior_only)
   int y_override_ld = 0;
   int mc3_C = 0, mc3_n_global = 0, mc3_offset = 0;
@@ -449,19 +452,26 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
 }
 
 // theta-packed host API: only the D free parameters cross PCIe in either direction
+// async = true: returns after enqueueing; the outputs are valid after mcd_synchronize.  Consecutive calls then overlap
+// their PCIe fill and drain (chunk k of every call runs on stream k % 4, in order, on its own slice of the staging buffers).
 int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* base, double* out, double* gtheta,
-                    int32_t* status) {
+                    int32_t* status, bool async = false, int64_t* ticket_out = nullptr) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
   if (n <= 0) return 0;
   if (!theta || !base || !out || !gtheta || !status) return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
+  if (n > h->cap || !h->d_states.p || !h->d_grad.p) CU_TRY(h, cudaDeviceSynchronize());  // buffers are about to be (re)allocated
   if (ensure_capacity(h, n, true, true)) return -1;
   const int S = h->S, D = h->D;
   if (!h->d_theta.p) CU_TRY(h, cudaMalloc(&h->d_theta.p, (size_t)h->cap * D * 8));
   if (!h->d_gtheta.p) CU_TRY(h, cudaMalloc(&h->d_gtheta.p, (size_t)h->cap * D * 8));
-  CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, h->streams[0]));
-  CU_TRY(h, cudaStreamSynchronize(h->streams[0]));
+  // the shared base state goes to the device only when it changes (work of an earlier asynchronous call may still read it)
+  if (h->base_host.size() != (size_t)S || memcmp(h->base_host.data(), base, (size_t)S * 8) != 0) {
+    CU_TRY(h, cudaDeviceSynchronize());
+    CU_TRY(h, cudaMemcpy(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice));
+    h->base_host.assign(base, base + S);
+  }
   int ci = 0;
   for (const auto& cm : chunk_schedule(n, S)) {
     const int c0 = cm.first, m = cm.second;
@@ -481,7 +491,26 @@ int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* bas
     CU_TRY(h, cudaMemcpyAsync(status + c0, h->d_status.as<int32_t>() + c0, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaMemcpyAsync(gtheta + (size_t)c0 * D, d_gt, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st));
   }
-  for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
+  if (!async) {
+    for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
+    return 0;
+  }
+  const int64_t ticket = h->next_ticket++;
+  for (int i = 0; i < N_STREAMS; ++i) {
+    cudaEvent_t& ev = h->ticket_ev[ticket % 8][i];
+    if (!ev) CU_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU_TRY(h, cudaEventRecord(ev, h->streams[i]));
+  }
+  if (ticket_out) *ticket_out = ticket;
+  return 0;
+}
+int wait_ticket(mcd_handle* h, int64_t ticket) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (ticket < 0 || ticket >= h->next_ticket) return fail(h, "mcd_wait: unknown ticket");
+  if (ticket + 8 <= h->next_ticket) return 0;  // older than the ring: completed when a later call reused its streams' events
+  CU_TRY(h, cudaSetDevice(h->device));
+  for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaEventSynchronize(h->ticket_ev[ticket % 8][i]));
   return 0;
 }
 
@@ -520,6 +549,7 @@ int leapfrog_host(mcd_handle* h, int n, int L, const double* theta0, const doubl
   CU_TRY(h, cudaMemcpyAsync(pm, mom0, nb, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemcpyAsync(h->d_eps.p, eps, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemcpyAsync(h->d_invmass.p, inv_mass, (size_t)D * 8, cudaMemcpyHostToDevice, st));
+  h->base_host.clear();
   CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemsetAsync(sacc, 0, (size_t)n * 4, st));
   const dim3 gS((S + POST_THREADS - 1) / POST_THREADS, n), gD((D + HMC_THREADS - 1) / HMC_THREADS, n);
@@ -617,7 +647,8 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
   CU_TRY(h, cudaMemcpyAsync(d_invm, inv_mass, (size_t)D * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemcpyAsync(d_eps, eps, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   if (resident) CU_TRY(h, cudaMemcpyAsync(h->d_base.p, h->d_chain.p, (size_t)S * 8, cudaMemcpyDeviceToDevice, st));
-  else CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  else h->base_host.clear();
+  CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemsetAsync(nb.n_active, 0, 4, st));
   const dim3 gS((S + POST_THREADS - 1) / POST_THREADS, n);
   unpack_theta_kernel<<<gS, POST_THREADS, 0, st>>>(d_theta0, h->d_base.as<double>(), h->d_tidx.as<int>(), xs, S, D, n);
@@ -1421,6 +1452,9 @@ void mcd_destroy(mcd_handle* h) {
   if (h->nuts_flags) cudaFreeHost(h->nuts_flags);
   for (int i = 0; i < 2; ++i)
     if (h->nuts_ev[i]) cudaEventDestroy(h->nuts_ev[i]);
+  for (auto& evs : h->ticket_ev)
+    for (cudaEvent_t ev : evs)
+      if (ev) cudaEventDestroy(ev);
   delete h;
 }
 
@@ -1463,6 +1497,13 @@ int mcd_eval_grad_theta(mcd_handle* h, int32_t n, const double* theta, const dou
                         double* grad_theta, int32_t* status) {
   return eval_theta_host(h, n, theta, base_state, out, grad_theta, status);
 }
+int64_t mcd_eval_grad_theta_async(mcd_handle* h, int32_t n, const double* theta, const double* base_state, double* out,
+                                  double* grad_theta, int32_t* status) {
+  int64_t ticket = -1;
+  if (n <= 0) return h ? h->next_ticket - 1 : -1;
+  return eval_theta_host(h, n, theta, base_state, out, grad_theta, status, true, &ticket) == 0 ? ticket : -1;
+}
+int mcd_wait(mcd_handle* h, int64_t ticket) { return wait_ticket(h, ticket); }
 int mcd_leapfrog(mcd_handle* h, int32_t n, int32_t n_steps, const double* theta0, const double* momentum0,
                  const double* base_state, const double* inv_mass, const double* step_size, double* theta_out,
                  double* momentum_out, double* out, double* energy, int32_t* status) {

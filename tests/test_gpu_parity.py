@@ -914,6 +914,47 @@ def test_full_size_mh_cycle_is_consistent_with_fresh_evaluations():
     ev.close()
 
 
+def test_asynchronous_theta_calls_overlap_safely():
+    """mcd_eval_grad_theta_async / mcd_wait: several calls in flight on different host buffers (and different inputs) give
+    exactly what the synchronous call gives; tickets older than the ring and a changed base state are handled"""
+    import torch
+    md, h = synth.synthetic_model(300, seed=12, n_cal=3, n_con=2, n_brace=1)
+    B = 700
+    ev = binding.Evaluator(md)
+    mask = ev.mask().astype(bool)
+    D = ev.D
+    Xs = [synth.synthetic_states(md, h, B, seed=100 + i) for i in range(3)]
+    for X in Xs:
+        X[:, 2] = Xs[0][0, 2]
+    thetas = [torch.from_numpy(np.ascontiguousarray(X[:, mask][:, ::-1])).pin_memory() for X in Xs]
+    base = torch.from_numpy(Xs[0][0].copy()).pin_memory()
+    ref = [ev.eval_grad_theta(t.numpy(), base.numpy()) for t in thetas]
+    outs = [(torch.empty((B, model.OUT_COLS), dtype=torch.float64).pin_memory(), torch.empty((B, D), dtype=torch.float64).pin_memory(),
+             torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(3)]
+    tickets = []
+    for rep in range(4):                                   # 12 calls: the ticket ring (8) wraps
+        for i in range(3):
+            o, g, s_ = outs[i]
+            tickets.append(ev.eval_grad_theta_async_ptr(B, thetas[i].data_ptr(), base.data_ptr(), o.data_ptr(), g.data_ptr(), s_.data_ptr()))
+    assert tickets == list(range(tickets[0], tickets[0] + 12))
+    for t in (tickets[0], tickets[-1], tickets[5]):
+        ev.wait(t)
+    ev.synchronize()
+    for i in range(3):
+        o, g, s_ = outs[i]
+        assert np.array_equal(o.numpy(), ref[i][0]) and np.array_equal(g.numpy(), ref[i][1]) and np.array_equal(s_.numpy(), ref[i][2])
+    # a different base state (other fixed entries) is picked up
+    base2 = base.clone()
+    base2[5 + md.n_nodes] = 0.5                             # the rate stem is fixed: it must come from the base state
+    t = ev.eval_grad_theta_async_ptr(B, thetas[0].data_ptr(), base2.data_ptr(), outs[0][0].data_ptr(), outs[0][1].data_ptr(), outs[0][2].data_ptr())
+    ev.wait(t)
+    ref2 = ev.eval_grad_theta(thetas[0].numpy(), base2.numpy())
+    assert np.array_equal(outs[0][0].numpy(), ref2[0]) and np.array_equal(outs[0][1].numpy(), ref2[1])
+    with pytest.raises(RuntimeError):
+        ev.wait(10 ** 6)
+    ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
