@@ -646,9 +646,9 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
   if (mom0) CU_TRY(h, cudaMemcpyAsync(d_mom0, mom0, BD * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemcpyAsync(d_invm, inv_mass, (size_t)D * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemcpyAsync(d_eps, eps, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  h->base_host.clear();  // the theta-packed host calls re-upload their base state next time
   if (resident) CU_TRY(h, cudaMemcpyAsync(h->d_base.p, h->d_chain.p, (size_t)S * 8, cudaMemcpyDeviceToDevice, st));
-  else h->base_host.clear();
-  CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  else CU_TRY(h, cudaMemcpyAsync(h->d_base.p, base, (size_t)S * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemsetAsync(nb.n_active, 0, 4, st));
   const dim3 gS((S + POST_THREADS - 1) / POST_THREADS, n);
   unpack_theta_kernel<<<gS, POST_THREADS, 0, st>>>(d_theta0, h->d_base.as<double>(), h->d_tidx.as<int>(), xs, S, D, n);
