@@ -129,6 +129,9 @@ int mcd_eval_grad_theta(mcd_handle* h, int32_t n_chains, const double* theta /*[
 int64_t mcd_eval_grad_theta_async(mcd_handle* h, int32_t n_chains, const double* theta, const double* base_state, double* out,
                                   double* grad_theta, int32_t* status);
 int mcd_wait(mcd_handle* h, int64_t ticket);
+/* asynchronous forms of mcd_eval / mcd_eval_grad (same tickets) */
+int64_t mcd_eval_async(mcd_handle* h, int32_t n_chains, const double* states, double* out, int32_t* status);
+int64_t mcd_eval_grad_async(mcd_handle* h, int32_t n_chains, const double* states, double* out, double* grad, int32_t* status);
 
 /* Device-resident leapfrog trajectory (first half of SURVEY 8f rank 1): n_steps leapfrog steps of the
  * Hamiltonian H = -ln post(theta) + 1/2 p^T M^-1 p (M diagonal) for every chain, positions / momenta /

@@ -19,7 +19,7 @@ _LIB = None
 
 EXPORTS = [
     "mcd_create", "mcd_destroy", "mcd_last_error", "mcd_state_len", "mcd_dim", "mcd_branch_index", "mcd_mask",
-    "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_eval_grad_theta_async", "mcd_wait", "mcd_leapfrog", "mcd_nuts",
+    "mcd_hmc_dim", "mcd_to_vector", "mcd_from_vector", "mcd_eval", "mcd_eval_grad", "mcd_eval_grad_theta", "mcd_eval_grad_theta_async", "mcd_wait", "mcd_eval_async", "mcd_eval_grad_async", "mcd_leapfrog", "mcd_nuts",
     "mcd_chains_set", "mcd_chains_get", "mcd_chains_nuts", "mcd_mh_step", "mcd_mh_cycle", "mcd_mc3_configure", "mcd_mc3_swap", "mcd_mc3_slots",
     "mcd_chains_out_device", "mcd_chains_stats_device", "mcd_mh_set_incremental", "mcd_mh_get_incremental",
     "mcd_eval_device", "mcd_set_contraction", "mcd_get_contraction",
@@ -89,6 +89,10 @@ def load_library():
     L.mcd_eval_grad_theta_async.argtypes = [vp, i32, dp, dp, dp, dp, ip]
     L.mcd_eval_grad_theta_async.restype = C.c_int64
     L.mcd_wait.argtypes = [vp, C.c_int64]
+    L.mcd_eval_async.argtypes = [vp, i32, dp, dp, ip]
+    L.mcd_eval_async.restype = C.c_int64
+    L.mcd_eval_grad_async.argtypes = [vp, i32, dp, dp, dp, ip]
+    L.mcd_eval_grad_async.restype = C.c_int64
     L.mcd_leapfrog.argtypes = [vp, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip]
     L.mcd_nuts.argtypes = [vp, i32, dp, dp, dp, dp, dp, i32, C.c_uint64, C.c_uint32, dp, dp, dp, ip, ip]
     L.mcd_chains_set.argtypes = [vp, i32, dp]
@@ -379,6 +383,20 @@ class Evaluator:
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         t = self._L.mcd_eval_grad_theta_async(self.h, B, C.cast(theta_ptr, dp), C.cast(base_ptr, dp), C.cast(out_ptr, dp),
                                               C.cast(gtheta_ptr, dp), C.cast(status_ptr, ip))
+        if t < 0:
+            self._check(-1)
+        return int(t)
+
+    def eval_grad_async_ptr(self, B: int, states_ptr: int, out_ptr: int, grad_ptr: int, status_ptr: int) -> int:
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        t = self._L.mcd_eval_grad_async(self.h, B, C.cast(states_ptr, dp), C.cast(out_ptr, dp), C.cast(grad_ptr, dp), C.cast(status_ptr, ip))
+        if t < 0:
+            self._check(-1)
+        return int(t)
+
+    def eval_async_ptr(self, B: int, states_ptr: int, out_ptr: int, status_ptr: int) -> int:
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        t = self._L.mcd_eval_async(self.h, B, C.cast(states_ptr, dp), C.cast(out_ptr, dp), C.cast(status_ptr, ip))
         if t < 0:
             self._check(-1)
         return int(t)

@@ -421,15 +421,30 @@ int eval_device(mcd_handle* h, int n, const double* d_states, double* d_out, dou
   return enqueue<GRAD>(h, 0, n, d_states, d_out, d_grad, d_status, static_cast<cudaStream_t>(stream));
 }
 
+// completion events of an asynchronous host-buffer call on all pipeline streams -> ticket
+int record_ticket(mcd_handle* h, int64_t* ticket_out) {
+  CU_TRY(h, cudaSetDevice(h->device));
+  const int64_t ticket = h->next_ticket++;
+  for (int i = 0; i < N_STREAMS; ++i) {
+    cudaEvent_t& ev = h->ticket_ev[ticket % 8][i];
+    if (!ev) CU_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU_TRY(h, cudaEventRecord(ev, h->streams[i]));
+  }
+  if (ticket_out) *ticket_out = ticket;
+  return 0;
+}
+
 // host buffers: chunks of chains are copied in, evaluated and copied out on rotating streams so
 // that PCIe transfers in both directions overlap the kernels of neighbouring chunks
 template <bool GRAD>
-int eval_host(mcd_handle* h, int n, const double* states, double* out, double* grad, int32_t* status) {
+int eval_host(mcd_handle* h, int n, const double* states, double* out, double* grad, int32_t* status, bool async = false,
+              int64_t* ticket_out = nullptr) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
-  if (n <= 0) return 0;
+  if (n <= 0) return async ? record_ticket(h, ticket_out) : 0;
   if (!states || !out || !status || (GRAD && !grad)) return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
+  if (n > h->cap || !h->d_states.p || (GRAD && !h->d_grad.p)) CU_TRY(h, cudaDeviceSynchronize());  // (re)allocation ahead
   if (ensure_capacity(h, n, true, GRAD)) return -1;
   if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && (ensure_cholesky(h, nullptr) || ensure_i8(h))) return -1;
   const int S = h->S;
@@ -447,6 +462,7 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
       CU_TRY(h, cudaMemcpyAsync(grad + (size_t)c0 * S, h->d_grad.as<double>() + (size_t)c0 * S, (size_t)m * S * 8,
                                 cudaMemcpyDeviceToHost, st));
   }
+  if (async) return record_ticket(h, ticket_out);
   for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
   return 0;
 }
@@ -458,7 +474,7 @@ int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* bas
                     int32_t* status, bool async = false, int64_t* ticket_out = nullptr) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
-  if (n <= 0) return 0;
+  if (n <= 0) return async ? record_ticket(h, ticket_out) : 0;
   if (!theta || !base || !out || !gtheta || !status) return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   if (n > h->cap || !h->d_states.p || !h->d_grad.p) CU_TRY(h, cudaDeviceSynchronize());  // buffers are about to be (re)allocated
@@ -495,14 +511,7 @@ int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* bas
     for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
     return 0;
   }
-  const int64_t ticket = h->next_ticket++;
-  for (int i = 0; i < N_STREAMS; ++i) {
-    cudaEvent_t& ev = h->ticket_ev[ticket % 8][i];
-    if (!ev) CU_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU_TRY(h, cudaEventRecord(ev, h->streams[i]));
-  }
-  if (ticket_out) *ticket_out = ticket;
-  return 0;
+  return record_ticket(h, ticket_out);
 }
 int wait_ticket(mcd_handle* h, int64_t ticket) {
   if (!h) return -1;
@@ -1500,8 +1509,15 @@ int mcd_eval_grad_theta(mcd_handle* h, int32_t n, const double* theta, const dou
 int64_t mcd_eval_grad_theta_async(mcd_handle* h, int32_t n, const double* theta, const double* base_state, double* out,
                                   double* grad_theta, int32_t* status) {
   int64_t ticket = -1;
-  if (n <= 0) return h ? h->next_ticket - 1 : -1;
   return eval_theta_host(h, n, theta, base_state, out, grad_theta, status, true, &ticket) == 0 ? ticket : -1;
+}
+int64_t mcd_eval_async(mcd_handle* h, int32_t n, const double* states, double* out, int32_t* status) {
+  int64_t ticket = -1;
+  return eval_host<false>(h, n, states, out, nullptr, status, true, &ticket) == 0 ? ticket : -1;
+}
+int64_t mcd_eval_grad_async(mcd_handle* h, int32_t n, const double* states, double* out, double* grad, int32_t* status) {
+  int64_t ticket = -1;
+  return eval_host<true>(h, n, states, out, grad, status, true, &ticket) == 0 ? ticket : -1;
 }
 int mcd_wait(mcd_handle* h, int64_t ticket) { return wait_ticket(h, ticket); }
 int mcd_leapfrog(mcd_handle* h, int32_t n, int32_t n_steps, const double* theta0, const double* momentum0,

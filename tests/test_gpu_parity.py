@@ -952,6 +952,21 @@ def test_asynchronous_theta_calls_overlap_safely():
     assert np.array_equal(outs[0][0].numpy(), ref2[0]) and np.array_equal(outs[0][1].numpy(), ref2[1])
     with pytest.raises(RuntimeError):
         ev.wait(10 ** 6)
+    # full-state forms
+    hx = [torch.from_numpy(X).pin_memory() for X in Xs[:2]]
+    S = md.state_len
+    fo = [(torch.empty((B, model.OUT_COLS), dtype=torch.float64).pin_memory(), torch.empty((B, S), dtype=torch.float64).pin_memory(),
+           torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(2)]
+    tk = [ev.eval_grad_async_ptr(B, hx[i].data_ptr(), fo[i][0].data_ptr(), fo[i][1].data_ptr(), fo[i][2].data_ptr()) for i in range(2)]
+    for t in tk:
+        ev.wait(t)
+    for i in range(2):
+        o, g, s_ = ev.eval_grad(Xs[i])
+        assert np.array_equal(fo[i][0].numpy(), o) and np.array_equal(fo[i][1].numpy(), g) and np.array_equal(fo[i][2].numpy(), s_)
+    t = ev.eval_async_ptr(B, hx[0].data_ptr(), fo[0][0].data_ptr(), fo[0][2].data_ptr())
+    ev.wait(t)
+    o, s_ = ev.eval(Xs[0])
+    assert np.array_equal(fo[0][0].numpy(), o) and np.array_equal(fo[0][2].numpy(), s_)
     ev.close()
 
 
