@@ -270,14 +270,33 @@ def run_gpu(args):
     d_out = torch.empty((B, model.OUT_COLS), dtype=torch.float64, device=dev)
     d_grad = torch.empty((B, S), dtype=torch.float64, device=dev)
     d_status = torch.empty(B, dtype=torch.int32, device=dev)
-    gathered = torch.empty((world * B, 2), dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream()
+    # MC3 swap statistics: (ln prior, ln likelihood) of every chain to every rank, every step.  The exchange is not on the
+    # evaluation's critical path (swaps are decided every SwapPeriod iterations), so it runs on a side stream from a
+    # double-buffered copy of the two columns and overlaps the next step's kernels.
+    if world > 1:
+        side = torch.cuda.Stream(device=dev)
+        stats = [torch.empty((B, 2), dtype=torch.float64, device=dev) for _ in range(2)]
+        gathered = [torch.empty((world * B, 2), dtype=torch.float64, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        for e in done:
+            e.record(stream)
+    step_no = [0]
 
     def step():
         ev.eval_grad_device(B, d_states.data_ptr(), d_out.data_ptr(), d_grad.data_ptr(), d_status.data_ptr(),
                             stream.cuda_stream)
-        if world > 1:  # MC3 swap statistics: (ln prior, ln likelihood) of every chain to every rank
-            dist.all_gather_into_tensor(gathered, d_out[:, 3:5].contiguous())
+        if world > 1:
+            k = step_no[0] & 1
+            step_no[0] += 1
+            stream.wait_event(done[k])               # the exchange that last used this buffer pair has finished
+            stats[k].copy_(d_out[:, 3:5])
+            ready[k].record(stream)
+            side.wait_event(ready[k])
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(gathered[k], stats[k])
+                done[k].record(side)
 
     def barrier():
         torch.cuda.synchronize()
@@ -299,6 +318,9 @@ def run_gpu(args):
     e0.record()
     for _ in range(args.steps):
         step()
+    if world > 1:  # the last exchanges belong to the timed region
+        stream.wait_event(done[0])
+        stream.wait_event(done[1])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
