@@ -65,7 +65,8 @@ typedef struct mcd_model_desc {
   int32_t clock_model;       /* MCD_CLOCK_* */
   int32_t likelihood;        /* MCD_LIK_* */
   const double* mean;        /* [K], K = N-2, branch order of mcd_branch_index */
-  const double* precision;   /* FULL: [K*K] row-major symmetric Sigma^-1; UNIVARIATE: [K] variances */
+  const double* precision;   /* FULL: [K*K] row-major Sigma^-1, symmetric up to rounding (its symmetric part is used: `prepare`
+                              * writes an unsymmetrised LU inverse, app/Main.hs:230); UNIVARIATE: [K] variances */
   double logdet_sigma;       /* ln det Sigma (FULL) / sum ln variances (UNIVARIATE) */
   double ht;                 /* mean root height for the rate-mean prior (app/Main.hs:394), > 0 */
   int32_t n_cal;             /* calibrations (Calibration.hs:55-123) */

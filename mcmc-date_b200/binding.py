@@ -275,6 +275,9 @@ class Evaluator:
         self._n_resident = X.shape[0]
         self._check(self._L.mcd_chains_set(self.h, X.shape[0], _dp(X)))
 
+    def n_resident(self) -> int:
+        return int(getattr(self, "_n_resident", 0))
+
     def chains_get(self):
         B = self._n_resident
         X, out, st = np.empty((B, self.S)), np.empty((B, _m.OUT_COLS)), np.empty(B, np.int32)

@@ -1339,21 +1339,27 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
     }
     M.lik = MCD_LIK_FULL;  // downstream kernels see y = S dx exactly like the dense case
   } else if (d->likelihood == MCD_LIK_FULL) {
-    // P padded to [Mp][ldk]; symmetry is assumed by the reference (L.Herm, app/Probability.hs:166) and
-    // relied on here (gradient = -P dx), so it is checked
+    // P padded to [Mp][ldk].  The reference wraps the matrix as symmetric (L.Herm, app/Probability.hs:166) but `prepare`
+    // writes the LU inverse of the covariance as it comes (L.invlndet, app/Main.hs:230), symmetric only up to rounding.
+    // The kernels rely on symmetry (gradient = -P dx), so the symmetric part (P + P^T)/2 is what is stored: the same
+    // quadratic form and exactly its gradient.  A matrix that is not symmetric beyond rounding is a caller error.
     std::vector<double> P((size_t)h->Mp * h->ldk, 0.0);
+    double pmax = 0.0;
+    for (size_t e = 0; e < (size_t)K * K; ++e) pmax = std::fmax(pmax, std::fabs(d->precision[e]));
     for (int i = 0; i < K; ++i) {
       for (int j = 0; j < K; ++j) {
         const double a = d->precision[(size_t)i * K + j], b = d->precision[(size_t)j * K + i];
-        if (a != b && std::fabs(a - b) > 1e-12 * (std::fabs(a) + std::fabs(b))) return bail("mcd_create: precision matrix is not symmetric");
-        P[(size_t)i * h->ldk + j] = a;
+        if (a != b && std::fabs(a - b) > 1e-6 * (std::fabs(a) + std::fabs(b)) && std::fabs(a - b) > 1e-9 * pmax)
+          return bail("mcd_create: precision matrix is not symmetric");
+        P[(size_t)i * h->ldk + j] = a == b ? a : 0.5 * (a + b);
       }
     }
     if (upload(h, h->d_P, P.data(), P.size())) return bail("upload precision");
     if (d->precision_chol) {
       if (ensure_cholesky(h, d->precision_chol)) return bail("upload Cholesky factor");
     } else {
-      h->hostP.assign(d->precision, d->precision + (size_t)K * K);
+      h->hostP.resize((size_t)K * K);
+      for (int i = 0; i < K; ++i) std::copy(&P[(size_t)i * h->ldk], &P[(size_t)i * h->ldk] + K, &h->hostP[(size_t)i * K]);
     }
     if (make_tile_map(&h->tmP, h->d_P.as<double>(), h->Mp, h->ldk) != 0) return bail("cuTensorMapEncodeTiled failed for the precision matrix");
     if (gemm_f64_dmma_configure() != cudaSuccess) return bail("cudaFuncSetAttribute(gemm smem) failed");

@@ -22,7 +22,7 @@
 //   MH_SCALE_SUBTREE_CONTRA      scaleSubTreesAtContrarily       Proposal/Contrary.hs:269-395           heights + rates of sub tree j
 //   MH_SLIDE_BRACE_CONTRA        slideBracedNodesContrarily      Proposal/Brace.hs:98-209               braced heights + adjacent rates
 //   MH_SLIDE_ROOT_CONTRA         slideRootContrarily             Proposal/Contrary.hs:173-267           H, all heights, root-child rates
-//   MH_SCALE_RATES_TREE_CONTRA   scaleRatesAndTreeContrarily     Proposal/Contrary.hs:420-486           lambda, mu, all heights
+//   MH_SCALE_RATES_TREE_CONTRA   scaleRatesAndTreeContrarily     Proposal/Contrary.hs:420-486           lambda, rate mean m, all heights
 //   MH_SCALE_SCALAR              scaleUnbiased (`mcmc` package)  app/Definitions.hs:259-262             one of lambda, mu, H, m, v
 //   MH_SCALE_H_M_CONTRA          scaleContrarily (`mcmc`)        app/Definitions.hs:244                 H, m
 // Truncated-normal moves use truncatedNormalSample (Proposal/Internal.hs:107-138) on the reference's own truncated normal
@@ -312,7 +312,8 @@ __device__ __noinline__ int mh_build_ops(const MhTopo& T, const MhParams& P, con
       if (!ok) break;
       const double xi = hn / hc;
       push(OH + 1, N - 1, OP_MUL, xi, 0.0);
-      push(0, 2, OP_DIV, xi, 0.0);  // lambda, mu
+      push(0, 1, OP_DIV, xi, 0.0);   // timeBirthRate and rateMean: ratesTimeTreeL = tripleLens timeBirthRate rateMean timeTree
+      push(OM, 1, OP_DIV, xi, 0.0);  // (app/Definitions.hs:236-237, 263); the PFunction's `mu` is the mean rate (Contrary.hs:435-436)
       lnj = (double)(nn - 1 - 2) * log(xi);
     } break;
     case MH_SCALE_SCALAR: {

@@ -93,3 +93,109 @@ def reference_cycle(md: _m.ModelDesc, calibrations_available: bool | None = None
         add(_b.MH_SCALE_NORM_TREE_CONTRA_H, 0, 100.0, True, w)
         add(_b.MH_SLIDE_ROOT_CONTRA, 0, 10.0, True, w)
     return out
+
+
+# ----------------------------------------------------------------------------- order, dimensions, auto tuning (host side)
+def proposal_dimension(md: _m.ModelDesc, entry) -> int:
+    """PDimension of one cycle entry, as the reference's proposal constructors state it (the auto tuner's target acceptance
+    rate depends on it): lib/Mcmc/Tree/Proposal/Ultrametric.hs:97,185,311; Unconstrained.hs:50,115,280,366,435;
+    Contrary.hs:133,262,382,482; Brace.hs:90,200; `scaleUnbiased` 1 and `scaleContrarily` 2 (`mcmc` package)."""
+    kind, node = entry[0], entry[1]
+    parent = np.asarray(md.parent)
+    N = len(parent)
+    child, _, plen = _topology(parent)
+    size = [1] * N
+    inner = [1 if child[i] else 0 for i in range(N)]
+    for i in range(N - 1, 0, -1):
+        size[int(parent[i])] += size[i]
+        inner[int(parent[i])] += inner[i]
+    brace_nodes = lambda b: [int(x) for x in md.brace_node[md.brace_off[b]:md.brace_off[b + 1]]]
+    if kind in (_b.MH_SLIDE_NODE, _b.MH_SCALE_BRANCH, _b.MH_SCALE_SCALAR):
+        return 1
+    if kind == _b.MH_SCALE_H_M_CONTRA:
+        return 2
+    if kind == _b.MH_SCALE_SUBTREE:
+        return inner[node]
+    if kind == _b.MH_PULLEY:
+        return inner[child[0][0]] + inner[child[0][1]]
+    if kind == _b.MH_SCALE_RATE_SUBTREE:
+        return size[node]                                   # scaleTree: `length tr`, stem included
+    if kind in (_b.MH_SCALE_NORM_TREE_CONTRA_M, _b.MH_SCALE_NORM_TREE_CONTRA_H, _b.MH_SCALE_VAR_TREE, _b.MH_SCALE_VAR_TREE_AUTO):
+        return (N - 1) + 1
+    if kind == _b.MH_SLIDE_NODE_CONTRA:
+        return 1 + 1 + len(child[node])                      # never the root here
+    if kind == _b.MH_SCALE_SUBTREE_CONTRA:
+        return inner[node] + size[node]
+    if kind == _b.MH_SLIDE_ROOT_CONTRA:
+        return 1 + inner[0] + len(child[0])
+    if kind == _b.MH_SCALE_RATES_TREE_CONTRA:
+        return (inner[0] - 1) + 2
+    if kind == _b.MH_SLIDE_BRACE:
+        return len(brace_nodes(node))
+    if kind == _b.MH_SLIDE_BRACE_CONTRA:
+        ns = brace_nodes(node)
+        return len(ns) + sum(1 for i in ns if plen[i] > 0) + sum(len(child[i]) for i in ns)
+    raise ValueError(f"unknown proposal kind {kind}")
+
+
+def optimal_rate(dim: int) -> float:
+    """target acceptance rate of the auto tuner by proposal dimension: 0.44 in one dimension falling linearly (step 0.0515) to
+    0.234 from five dimensions on (Roberts & Rosenthal optimal scaling; the `mcmc` package's `getOptimalRate`, restated from
+    its published definition -- the package is not vendored)."""
+    if dim <= 0:
+        raise ValueError("getOptimalRate: Proposal dimension is zero or negative.")
+    return 0.44 - 0.0515 * (min(dim, 5) - 1)
+
+
+TUNE_MIN, TUNE_MAX = 1e-5, 1e3
+
+
+def auto_tune(md: _m.ModelDesc, cycle, accepted, proposed):
+    """one auto-tuning step after a tuning period: t <- t * exp(2 (rate - optimal rate)) for every entry of the cycle
+    (`mcmc` package: tuningFunction / autoTuneCycle, restated from its published definition); entries that were never
+    proposed keep their parameter.  -> new cycle list"""
+    out = []
+    for e, a, n in zip(cycle, accepted, proposed):
+        kind, node, param, tune, jac, w = e
+        if n > 0:
+            rate = float(a) / float(n)
+            tune = min(TUNE_MAX, max(TUNE_MIN, tune * math.exp(2.0 * (rate - optimal_rate(proposal_dimension(md, e))))))
+        out.append((kind, node, param, tune, jac, w))
+    return out
+
+
+def random_order(cycle, rng: np.random.Generator):
+    """one iteration in the `mcmc` package's default order RandomO: every proposal replicated by its weight, the whole list
+    shuffled anew for each iteration.  -> (list of entries with repeat 1, index of each into `cycle`)"""
+    idx = np.repeat(np.arange(len(cycle)), [e[5] for e in cycle])
+    rng.shuffle(idx)
+    return [cycle[i][:5] + (1,) for i in idx], idx
+
+
+BURN_IN_FAST = [10, 10] + list(range(10, 131, 10))      # burnIn (app/Definitions.hs:417-422)
+BURN_IN_SLOW = list(range(100, 401, 20))
+
+
+def run_iterations(ev, md, cycle, n_iterations: int, rng, seed: int, k0: int):
+    """n_iterations of the cycle in random order on the evaluator's resident chains -> (accepted, proposed per entry, next k).
+    All chains share the order (each chain is still a realisation of the same Markov chain)."""
+    acc = np.zeros(len(cycle))
+    prop = np.zeros(len(cycle))
+    n_chains = ev.n_resident()
+    k = k0
+    for _ in range(n_iterations):
+        lst, idx = random_order(cycle, rng)
+        a, inv, k = ev.mh_cycle(lst, 1, seed=seed, iteration0=k)
+        np.add.at(acc, idx, a.astype(float))
+        np.add.at(prop, idx, float(n_chains))
+    return acc, prop, k
+
+
+def burn_in(ev, md, cycle, rng, seed: int = 0, k0: int = 0, periods=None):
+    """BurnInWithCustomAutoTuning (app/Definitions.hs:417-422): tuning periods of the given lengths, an auto-tuning step after
+    each.  The acceptance rate of an entry is the mean over the resident chains (they share the tuning parameters).
+    -> (tuned cycle, next k)"""
+    for n in (BURN_IN_FAST + BURN_IN_SLOW) if periods is None else periods:
+        acc, prop, k0 = run_iterations(ev, md, cycle, n, rng, seed, k0)
+        cycle = auto_tune(md, cycle, acc, prop)
+    return cycle, k0

@@ -8,10 +8,12 @@ the data formats either side of the hot path.  numpy only.
   mean_root_height        lib/Mcmc/Tree/Prior/Node/Calibration.hs:324-339   getMeanRootHeight
   initial_state           app/Definitions.hs:96-123                         initWith
 
-Restrictions (documented): the trees of the list must already be rooted at the outgroup
-and bifurcating (the reference re-roots with elynx `outgroup`, app/Main.hs:179-180; all of its own
-tests/*/data/test.treelist files already are).  Constraint validation, conflict detection and the pruning of
-duplicate / redundant constraints (Constraint.hs:117-146, 211-253, 306-374) are restated in load_constraints.
+  load_calibrations_from_tree  lib/Mcmc/Tree/Prior/Node/CalibrationFromTree.hs:27-130  MCMCtree-labelled Newick tree -> table
+  outgroup                app/Main.hs:179-180 (elynx-tree `outgroup`, un-vendored: restated from its published algorithm)
+
+Constraint validation, conflict detection and the pruning of duplicate / redundant constraints
+(Constraint.hs:117-146, 211-253, 306-374) are restated in load_constraints.  Not restated: glasso (`SparseMultivariateNormal`,
+app/Main.hs:257-277, a Fortran dependency) -- a sparse `.data` file written by the reference is read as is.
 """
 from __future__ import annotations
 
@@ -33,18 +35,122 @@ def _branches_row(parent, lengths):
     return row
 
 
-def prepare_from_treelist(text: str):
+def _leaf_set(nd):
+    if not nd["children"]:
+        return frozenset([nd["name"]])
+    return frozenset().union(*[_leaf_set(c) for c in nd["children"]])
+
+
+def _with_length(nd, length):
+    return {"name": nd["name"], "length": length, "children": nd["children"]}
+
+
+def _half(x):
+    return None if x is None else 0.5 * x       # elynx `split` on a branch length
+
+
+def _plus(a, b):
+    return None if a is None and b is None else (a or 0.0) + (b or 0.0)   # `<>` on branch lengths
+
+
+def outgroup(og, tree):
+    """Root `tree` (nested dict from tree.parse_newick) at the branch that separates the leaf set `og` from the rest:
+    elynx-tree `outgroup` (ELynx.Tree.Rooted, rev 34fc58b0; the package is not vendored in the reference checkout, so this
+    follows its published algorithm and documentation, as called at app/Main.hs:179-180).
+
+    * a leaf root or a root of degree one is an error;
+    * a multifurcating root first gets a bifurcating root above it by splitting the leftmost branch in two halves:
+      `[leftmost child, (the other children)]`, the old root label moving to the second node;
+    * a tree that is already rooted at the bipartition is returned unchanged (`roots t` starts with `t` itself);
+    * otherwise the root moves down to the branch above the sub tree X whose leaves are `og` or its complement; that branch is
+      split in halves.  `descend` puts the part that hangs "upside down" FIRST and X SECOND; the upside-down node keeps the
+      label of X's former parent and lists [the former up-going part (branch = the two halves / root branches joined),
+      then X's former siblings in their old order].
+    The sub-tree order is observable: the mean tree takes the order of the re-rooted tree list (app/Main.hs:289-291), and
+    every node index follows from it."""
+    og = frozenset(og)
+    if not og:
+        raise ValueError("outgroup: Outgroup is empty.")
+    ch = tree["children"]
+    if len(ch) == 0:
+        raise ValueError("outgroup: Root node is a leaf.")
+    if len(ch) == 1:
+        raise ValueError("outgroup: Root node has degree two.")
+    if len(ch) > 2:
+        o = ch[0]
+        h = _half(o["length"])
+        tree = {"name": "", "length": tree["length"],
+                "children": [_with_length(o, h), {"name": tree["name"], "length": h, "children": ch[1:]}]}
+        ch = tree["children"]
+    allv = _leaf_set(tree)
+    if not og < allv:
+        raise ValueError("outgroup: Outgroup is not a proper subset of the leaves.")
+    target = (og, allv - og)
+    tl, tr = ch
+    if _leaf_set(tl) in target:
+        return tree
+
+    def descend(tc, d):
+        """the root sits above d, tc is everything else (its branch = the other root branch); -> re-rooted tree or None"""
+        if not d["children"]:
+            return None
+        tc2 = _with_length(tc, _plus(tc["length"], d["length"]))
+        kids = d["children"]
+        cfs = [[tc2] + kids[:i] + kids[i + 1:] for i in range(len(kids))]
+        for dd, f in zip(kids, cfs):
+            if _leaf_set(dd) in target:
+                h = _half(dd["length"])
+                return {"name": tree["name"], "length": tree["length"],
+                        "children": [{"name": d["name"], "length": h, "children": f}, _with_length(dd, h)]}
+        for dd, f in zip(kids, cfs):
+            if og <= _leaf_set(dd) or (allv - og) <= _leaf_set(dd):
+                h = _half(dd["length"])
+                return descend({"name": d["name"], "length": h, "children": f}, _with_length(dd, h))
+        return None
+
+    out = descend(tr, tl) or descend(tl, tr)
+    if out is None:
+        raise ValueError("outgroup: No rooted tree has the required bipartition (the outgroup is not monophyletic).")
+    return out
+
+
+def _topology_key(nd, ordered):
+    """T.fromBranchLabelTree: the topology with leaf labels only; ordered = sub-tree order matters (`nub`, app/Main.hs:184),
+    unordered = `T.equal'` (:198)"""
+    if not nd["children"]:
+        return nd["name"]
+    ks = [_topology_key(c, ordered) for c in nd["children"]]
+    return tuple(ks) if ordered else frozenset(ks)
+
+
+def prepare_from_treelist(text: str, rooted_tree_text: str | None = None):
     """-> dict(parent, names, mean, cov, precision, logdet_sigma, mean_lengths).
-    Drops the first len/6 trees (app/Main.hs:166-168), requires identical topology AND sub-tree
-    order (:184-190), mean/covariance like hmatrix meanCov (unbiased, 1/(n-1)), then invlndet (:230)."""
-    lines = [ln for ln in text.splitlines() if ln.strip()]
-    trees = [_tree.flatten_preorder(_tree.parse_newick(ln)) for ln in lines]
-    burn = len(trees) // 6
-    trees = trees[burn:]
+    `prepare` (app/Main.hs:159-307): drop the first len/6 trees (:166-168); no duplicate leaves (:171-173); re-root every tree
+    at the outgroup of the given rooted tree (:176-180; skipped when no rooted tree is given -- the list must then already be
+    rooted); identical topology AND sub-tree order (:184-190); same topology as the rooted tree up to sub-tree order
+    (:195-205); mean / covariance like hmatrix meanCov (unbiased, 1/(n-1)); invlndet (:230) -- the inverse is NOT symmetrised
+    here, as in the reference's `.data` file (mcd_create takes the symmetric part: same quadratic form, and its gradient)."""
+    lines = [ln for ln in text.replace(";", ";\n").splitlines() if ln.strip()]
+    nested_all = [_tree.parse_newick(ln) for ln in lines]
+    for t in nested_all:
+        lv = [n for n in _all_leaves(t)]
+        if len(set(lv)) != len(lv):
+            raise ValueError("prepare: Trees have duplicate leaves.")
+    nested = nested_all[len(nested_all) // 6:]
+    rooted = None
+    if rooted_tree_text is not None:
+        rooted = _tree.parse_newick(rooted_tree_text)
+        if len(rooted["children"]) != 2:
+            raise ValueError("bipartition: Root node is not bifurcating.")
+        og = min((_leaf_set(c) for c in rooted["children"]), key=lambda x: sorted(x))   # fst . fromBipartition
+        nested = [outgroup(og, t) for t in nested]
+    keys = {_topology_key(t, True) for t in nested}
+    if len(keys) != 1:
+        raise ValueError("prepare: A single topology and equal sub tree orders are required.")
+    if rooted is not None and _topology_key(rooted, False) != _topology_key(nested[0], False):
+        raise ValueError("prepare: A single topology is required.")
+    trees = [_tree.flatten_preorder(t) for t in nested]
     parent, c0, c1, names, _ = trees[0]
-    for p, _, _, nm, _ in trees:
-        if not np.array_equal(p, parent) or nm != names:
-            raise ValueError("prepare: A single topology and equal sub tree orders are required.")
     rows = np.array([_branches_row(p, ln) for p, _, _, _, ln in trees])
     mean = rows.mean(axis=0)
     cov = np.cov(rows, rowvar=False, ddof=1).reshape(len(mean), len(mean))
@@ -54,10 +160,16 @@ def prepare_from_treelist(text: str):
     if sign != 1.0:
         raise ValueError("prepare: Determinant of covariance matrix is negative?")
     prec = np.linalg.inv(cov)
-    prec = 0.5 * (prec + prec.T)
     all_len = np.array([ln for _, _, _, _, ln in trees]).mean(axis=0)  # mean tree incl. both root branches
     return {"parent": parent, "names": names, "mean": mean, "cov": cov, "precision": prec,
             "logdet_sigma": float(logdet), "mean_lengths": all_len}
+
+
+def _all_leaves(nd):
+    if not nd["children"]:
+        yield nd["name"]
+    for c in nd["children"]:
+        yield from _all_leaves(c)
 
 
 def _mrca(parent, names, leaf_a: str, leaf_b: str) -> int:
@@ -78,26 +190,116 @@ def _opt(s):
     return float(s) if s else None
 
 
-def load_calibrations(text: str, parent, names):
-    """CSV `Name,LeafA,LeafB,YoungAge,YoungProbabilityMass,OldAge,OldProbabilityMass` -> dict of arrays."""
-    node, lo, lop, hi, hip, nm = [], [], [], [], [], []
+def load_calibrations(text: str, parent, names, on_problem: str = "warn", log=None):
+    """CSV `Name,LeafA,LeafB,YoungAge,YoungProbabilityMass,OldAge,OldProbabilityMass` -> dict of arrays
+    (loadCalibrations, Calibration.hs:283-319)."""
+    rows = []
     for row in csv.reader(io.StringIO(text)):
         if not row or row[0].strip() == "Name":
             continue
-        name, la, lb = row[0], row[1].strip(), row[2].strip()
-        a, pa, b, pb = (_opt(x) for x in row[3:7])
-        if (a is None) != (pa is None) or (b is None) != (pb is None) or (a is None and b is None):
-            raise ValueError(f"calibrationDataToCalibration: {name}: inconsistent boundaries")
+        rows.append((row[0], row[1].strip(), row[2].strip()) + tuple(_opt(x) for x in row[3:7]))
+    if not rows:
+        raise ValueError("loadCalibrations: No calibrations found in file.")
+    return _calibration_table(rows, parent, names, on_problem, log)
+
+
+_MCMCTREE_LABEL = None
+
+
+def _parse_mcmctree_label(label: str):
+    """pABounded (CalibrationFromTree.hs:36-88): `L(l[,p,c[,pL]])`, `U(u[,pU])`, `B(l,u[,pL[,pU]])` at the START of a node label
+    (attoparsec `parseOnly` does not demand the end of the input) -> (lo, lo_p, hi, hi_p) with None for absent bounds, or
+    None when the label is no calibration.  Missing probability masses default to 0.01 (defPM, :93-95); the Cauchy
+    parameters of L are read and ignored."""
+    import re
+    global _MCMCTREE_LABEL
+    if _MCMCTREE_LABEL is None:
+        num = r"[+-]?\d+(?:\.\d+)?(?:[eE][+-]?\d+)?"   # attoparsec `double`: at least one leading digit (".06" does not parse)
+        _MCMCTREE_LABEL = {
+            "L": re.compile(rf"L\(({num})(?:,({num}))?(?:,({num}))?(?:,({num}))?\)"),
+            "U": re.compile(rf"U\(({num})(?:,({num}))?\)"),
+            "B": re.compile(rf"B\(({num}),({num})(?:,({num}))?(?:,({num}))?\)"),
+        }
+    f = lambda x: None if x is None else float(x)
+    d = lambda x: 0.01 if x is None else float(x)
+    m = _MCMCTREE_LABEL["L"].match(label)
+    if m:
+        return float(m.group(1)), d(m.group(4)), None, None
+    m = _MCMCTREE_LABEL["U"].match(label)
+    if m:
+        return None, None, float(m.group(1)), d(m.group(2))
+    m = _MCMCTREE_LABEL["B"].match(label)
+    if m:
+        return float(m.group(1)), d(m.group(3)), float(m.group(2)), d(m.group(4))
+    return None
+
+
+def load_calibrations_from_tree(text: str, parent, names, on_problem: str = "warn", log=None):
+    """loadCalibrationsFromTree (CalibrationFromTree.hs:97-130): every node of the Newick tree whose label parses as an MCMCtree
+    bound becomes a calibration on the MRCA of the node's leftmost and rightmost leaf (filterBoundedNodes, :107-116), named
+    `<leftmost>-<rightmost>`, in pre-order of the labelled tree; then the same checks as the CSV loader
+    (checkAndConvertCalibrationData, Calibration.hs:254-281)."""
+    t = _tree.parse_newick(text)
+    rows = []
+
+    def left(nd):
+        return nd["name"] if not nd["children"] else left(nd["children"][0])
+
+    def right(nd):
+        return nd["name"] if not nd["children"] else right(nd["children"][-1])
+
+    def walk(nd):
+        b = _parse_mcmctree_label(nd["name"])
+        if b is not None:
+            rows.append((left(nd) + "-" + right(nd), left(nd), right(nd)) + b)
+        for c in nd["children"]:
+            walk(c)
+
+    walk(t)
+    if not rows:
+        raise ValueError("loadCalibrationsFromTree: no calibrations found")
+    return _calibration_table(rows, parent, names, on_problem, log)
+
+
+def _calibration_table(rows, parent, names, on_problem="warn", log=None):
+    """calibrationDataToCalibration + checkAndConvertCalibrationData (Calibration.hs:210-281) on rows
+    (name, leafA, leafB, lo, lo_p, hi, hi_p) with None for absent fields"""
+    node, lo, lop, hi, hip, nm = [], [], [], [], [], []
+    for name, la, lb, a, pa, b, pb in rows:
+        err = lambda m: ValueError(f"calibrationDataToCalibration: {name}: {m}")
+        if a is None and pa is not None:
+            raise err("Lower probability mass given but no lower boundary.")
+        if b is None and pb is not None:
+            raise err("Upper probability mass given but no upper boundary.")
+        if a is not None and pa is None:
+            raise err("Lower boundary given but no lower probability mass.")
+        if b is not None and pb is None:
+            raise err("Upper boundary given but no upper probability mass.")
+        if a is None and b is None:
+            raise err("No boundaries provided.")
         if a is not None and b is not None and a >= b:
-            raise ValueError(f"calibrationDataToCalibration: {name}: Lower boundary larger equal upper boundary.")
+            raise err("Lower boundary larger equal upper boundary.")
+        for pm in (pa, pb):
+            if pm is not None and not 0.0 < pm < 1.0:
+                raise err("probabilityMass: out of (0, 1)")
+        if a is not None and a <= 0:
+            raise err("positiveLowerBoundary: Zero or negative value.")
+        if b is not None and b <= 0:
+            raise err("positiveUpperBoundary: Zero or negative value.")
         nm.append(name)
         node.append(_mrca(parent, names, la, lb))
         lo.append(a if a is not None else 0.0)
         lop.append(pa if pa is not None else 0.5)
         hi.append(b if b is not None else np.inf)
         hip.append(pb if pb is not None else 0.5)
-    return {"names": nm, "node": np.array(node, np.int32), "lo": np.array(lo), "lo_p": np.array(lop),
-            "hi": np.array(hi), "hi_p": np.array(hip)}
+    dups = sorted({n for n in node if node.count(n) > 1})
+    if dups:
+        msg = "loadCalibrations: Duplicate/conflicting/redundant calibrations have been detected."
+        if on_problem == "error":
+            raise ValueError(msg)
+        (log or (lambda m: None))("WARNING: " + msg + f" (nodes {dups})")
+    return {"names": nm, "node": np.array(node, np.int32), "lo": np.array(lo, float), "lo_p": np.array(lop, float),
+            "hi": np.array(hi, float), "hi_p": np.array(hip, float)}
 
 
 def _is_ancestor(parent, x: int, y: int) -> bool:

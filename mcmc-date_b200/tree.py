@@ -12,17 +12,17 @@ import numpy as np
 
 # ----------------------------------------------------------------------------- Newick
 def parse_newick(text: str):
-    """Parse one Newick tree -> nested dict {name, length, children}.  Handles quoted-free labels,
+    """Parse one Newick tree -> nested dict {name, length, children}.  Handles plain and quoted labels,
     branch lengths and [comments]; enough for the reference's tests/*/data/*.tree files."""
     s = text.strip()
     if s.endswith(";"):
         s = s[:-1]
     pos = 0
 
-    def skip_comment():
+    def skip_comment():   # white space and [comments]
         nonlocal pos
-        while pos < len(s) and s[pos] == "[":
-            pos = s.index("]", pos) + 1
+        while pos < len(s) and (s[pos] == "[" or s[pos].isspace()):
+            pos = s.index("]", pos) + 1 if s[pos] == "[" else pos + 1
 
     def node():
         nonlocal pos
@@ -41,10 +41,16 @@ def parse_newick(text: str):
                     break
                 raise ValueError(f"newick: unexpected {s[pos]!r} at {pos}")
         skip_comment()
-        start = pos
-        while pos < len(s) and s[pos] not in ",():;[":
-            pos += 1
-        name = s[start:pos].strip()
+        if pos < len(s) and s[pos] in "'\"":   # quoted label (MCMCtree calibrations: 'B(6,8,2.5e-2,2.5e-2)')
+            q = s[pos]
+            end = s.index(q, pos + 1)
+            name = s[pos + 1:end]
+            pos = end + 1
+        else:
+            start = pos
+            while pos < len(s) and s[pos] not in ",():;[":
+                pos += 1
+            name = s[start:pos].strip()
         skip_comment()
         length = None
         if pos < len(s) and s[pos] == ":":

@@ -62,6 +62,20 @@ inline Result<double> eval_grad_double(const Model& M, const double* x, const ui
     std::vector<double> w(M.K, 0.0);
     if (M.lik == LIK_FULL) {
       for (int k = 0; k < M.K; ++k) w[k] = -y[k];
+      // y = dx <# P = P^T dx; the gradient of -1/2 dx^T P dx is -1/2 (P + P^T) dx.  `prepare` writes the LU inverse of the
+      // covariance unsymmetrised (app/Main.hs:230), so P may differ from P^T in the last digits: add the other half then.
+      bool sym = true;
+      for (int i = 0; i < M.K && sym; ++i)
+        for (int j = 0; j < i; ++j)
+          if (M.prec[(size_t)i * M.K + j] != M.prec[(size_t)j * M.K + i]) { sym = false; break; }
+      if (!sym) {
+        std::vector<double> d = distances(M, s, t);
+        for (int i = 0; i < M.K; ++i) {
+          double z = 0;
+          for (int j = 0; j < M.K; ++j) z += M.prec[(size_t)i * M.K + j] * (d[j] - M.mu[j]);
+          w[i] = -0.5 * (y[i] + z);
+        }
+      }
     } else if (M.lik == LIK_UNIVARIATE) {
       std::vector<double> d = distances(M, s, t);
       for (int k = 0; k < M.K; ++k) w[k] = -(d[k] - M.mu[k]) / M.prec[k];

@@ -101,23 +101,28 @@ def dataset(name, d, cal=True, con=False, br=False, seed=0):
 
 
 def mtcdnapri():
-    """7-taxon primate set of bench/comparison_with_mcmctree (BASELINE.json configs[3]): topology and
-    calibrations from the reference (calibrated tree 00_inp_data/tree_display/mtcdnapri_calib_MCMCtree.tree:
-    U(100,.025) root, B(12,16), B(6,8)); this checkout keeps only 10 trees of the tree list (too few for a
-    non-singular 11x11 covariance), so the mean vector comes from those trees and the precision is synthetic."""
+    """7-taxon primate set of bench/comparison_with_mcmctree (BASELINE.json configs[3]).  Topology: the tree list re-rooted
+    at the outgroup of the rooted tree (prepare.outgroup; the list is already rooted there, sub-tree order (apes, gibbon)).
+    Calibrations: parsed from the MCMCtree-labelled tree the reference run used (`calibrations="data/mtCDNApri_MD.trees"`,
+    02_McmcDate/01_McmcDate/analysis.conf) with prepare.load_calibrations_from_tree: U(100,.025) root, B(12,16,.025,.025),
+    B(6,8,.025,.025).  This checkout keeps only 10 trees of the tree list (too few for a non-singular 11x11 covariance), so
+    the mean vector comes from those trees (after the len/6 burn-in) and the precision is synthetic."""
     base = "bench/comparison_with_mcmctree/02_McmcDate/01_McmcDate/data/"
+    rooted = tree.parse_newick(read(base + "pb_rooted_mitCDNApri.tree"))
+    og = min((prepare._leaf_set(c) for c in rooted["children"]), key=lambda x: sorted(x))
     lines = [ln for ln in read(base + "unr_lg_g5_ncat1.treelist").splitlines() if ln.strip()]
-    trees = [tree.flatten_preorder(tree.parse_newick(ln)) for ln in lines]
+    lines = lines[len(lines) // 6:]
+    trees = [tree.flatten_preorder(prepare.outgroup(og, tree.parse_newick(ln))) for ln in lines]
     parent, c0, c1, names, _ = trees[0]
     rows = np.array([prepare._branches_row(p, ln) for p, _, _, _, ln in trees])
     mu = rows.mean(axis=0)
     rng = np.random.default_rng(7)
     prec, logdet = synth.synthetic_precision(mu, rng, band=4)
-    great_apes = prepare._mrca(parent, names, "human", "sumatran")
-    hcb = prepare._mrca(parent, names, "human", "bonobo")
-    md = model.ModelDesc(parent=parent, mean=mu, precision=prec, logdet_sigma=logdet, ht=50.0,
-                         cal_node=[0, great_apes, hcb], cal_lo=[0.0, 12.0, 6.0], cal_lo_p=[0.5, 0.025, 0.025],
-                         cal_hi=[100.0, 16.0, 8.0], cal_hi_p=[0.025, 0.025, 0.025])
+    cal = prepare.load_calibrations_from_tree(read(base + "mtCDNApri_MD.trees"), parent, names)
+    assert cal["node"].tolist() == [0, 1, 3] and cal["names"] == ["human-gibbon", "human-sumatran", "human-bonobo"]
+    md = model.ModelDesc(parent=parent, mean=mu, precision=prec, logdet_sigma=logdet, ht=prepare.mean_root_height(cal),
+                         cal_node=cal["node"], cal_lo=cal["lo"], cal_lo_p=cal["lo_p"], cal_hi=cal["hi"], cal_hi_p=cal["hi_p"])
+    assert md.ht == 50.0
     mean_len = np.array([ln for _, _, _, _, ln in trees]).mean(axis=0)
     init = prepare.initial_state(parent, mean_len)
     make("mtcdnapri-7-leaves", md, {"names": names}, init, seed=3)

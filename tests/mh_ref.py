@@ -251,7 +251,7 @@ def propose(x, parent, topo, braces, kind, node, param, tune, seed, chain, itera
         hn, lnq = res
         xi = hn / hc
         y[OH + 1:OH + N] *= xi
-        y[0], y[1] = x[0] / xi, x[1] / xi
+        y[0], y[OM] = x[0] / xi, x[OM] / xi   # timeBirthRate, rateMean (ratesTimeTreeL, app/Definitions.hs:236-237)
         lnj = (nn - 1 - 2) * math.log(xi)
     elif kind == SCALE_SCALAR:
         o = [0, 1, 2, OM, OV][j]
