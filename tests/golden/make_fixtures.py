@@ -65,7 +65,7 @@ def make(name, md, pr, init_state, n_valid=24, seed=0):
     X = synth.synthetic_states(md, heights, n_valid, seed=synth.BASE_SEED + 100 + seed)
     X = np.vstack([init_state[None, :], X])
     if md.calibrations_available:
-        X[0, 2] = md.ht  # the reference starts H at the mean root calibration (app/Main.hs:394)
+        X[0, 2] = md.ht  # a start inside the calibrations (the reference itself starts at H = 1, app/Definitions.hs:101, and lets the burn-in climb)
     X = edge_states(md, X)
     arrs = dict(
         parent=md.parent, mean=md.mean, precision=md.precision, logdet_sigma=md.logdet_sigma, ht=md.ht,

@@ -11,6 +11,9 @@ iterations (burn-in 4 930 + 8 000, app/Definitions.hs:417-441), the time-tree mo
 
 Written: per run and pooled, for each node: mean, standard deviation and a 201-point quantile grid (0, 0.5 %, ..., 100 %);
 and the figures the reference's own summary table reports (03_compare_estimates/out/compare_divtimes.tsv:2-4, MD_CLK columns).
+The same statistics restricted to the samples whose root age is below 28 (`below_*`): the committed samples stop at a root
+age of about 30-31.5 in all six runs although the committed calibration file says U(100) -- see
+tests/test_reference_samples.py -- so the part of the distribution that does not depend on the root bound is kept as well.
 """
 from __future__ import annotations
 
@@ -19,6 +22,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+BELOW = 28.0
 BASE = "/root/reference/bench/comparison_with_mcmctree/03_compare_estimates/"
 
 
@@ -46,7 +50,14 @@ def main():
         run_quantiles=np.array([np.quantile(r, q, axis=0) for r in runs]),          # [6 runs][201][6 nodes]
         pooled_mean=pooled.mean(0), pooled_sd=pooled.std(0, ddof=1), pooled_quantiles=np.quantile(pooled, q, axis=0),
         table_nodes=np.array(sorted(table), np.int32), table_mean_q025_q975=np.array([table[k] for k in sorted(table)]),
-        samples_per_run=4850)
+        samples_per_run=4850, below=BELOW,
+        below_fraction=np.array([(r[:, 0] < BELOW).mean() for r in runs]),
+        below_run_mean=np.array([r[r[:, 0] < BELOW].mean(0) for r in runs]),
+        below_run_sd=np.array([r[r[:, 0] < BELOW].std(0, ddof=1) for r in runs]),
+        below_run_quantiles=np.array([np.quantile(r[r[:, 0] < BELOW], q, axis=0) for r in runs]),
+        below_pooled_mean=pooled[pooled[:, 0] < BELOW].mean(0), below_pooled_sd=pooled[pooled[:, 0] < BELOW].std(0, ddof=1),
+        below_pooled_quantiles=np.quantile(pooled[pooled[:, 0] < BELOW], q, axis=0),
+        root_age_max_per_run=np.array([r[:, 0].max() for r in runs]))
     print("pooled mean", pooled.mean(0).round(3), "table", table)
 
 

@@ -21,25 +21,43 @@ from mcmc_date_b200 import binding, mh_cycle, model  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def load_model(clock=model.UNCORRELATED_LOGNORMAL):
+def load_model(clock=model.UNCORRELATED_LOGNORMAL, root_upper=None):
+    """the model of the reference's `./run -c ul n r`: calibrations of data/mtCDNApri_MD.trees (parsed into the fixture by
+    prepare.load_calibrations_from_tree), NoLikelihood; root_upper replaces the root's upper bound (U(100,.025) in the file)"""
     z = np.load(os.path.join(GOLDEN, "mtcdnapri-7-leaves.npz"))
     K = len(z["mean"])
+    cal_hi = z["cal_hi"].copy()
+    if root_upper is not None:
+        assert z["cal_node"][0] == 0
+        cal_hi[0] = root_upper
     md = model.ModelDesc(parent=z["parent"], mean=np.zeros(K), precision=np.zeros(0), logdet_sigma=0.0, clock_model=clock,
                          likelihood=model.LIK_NONE, ht=float(z["ht"]), cal_node=z["cal_node"], cal_lo=z["cal_lo"],
-                         cal_lo_p=z["cal_lo_p"], cal_hi=z["cal_hi"], cal_hi_p=z["cal_hi_p"])
-    x0 = z["states"][0].copy()     # initWith (app/Definitions.hs:96-123) with H = ht (app/Main.hs:394)
+                         cal_lo_p=z["cal_lo_p"], cal_hi=cal_hi, cal_hi_p=z["cal_hi_p"])
+    x0 = z["states"][0].copy()     # initWith (app/Definitions.hs:96-123) but H = ht instead of 1: a shorter climb for the burn-in
     return md, x0
 
 
-def sample(n_chains=4096, periods=None, n_sampling=400, thin=50, seed=11, tune_samples=False, log=None):
+def exact_cycle(md):
+    """proposals whose stated Jacobian is the determinant of the move, none lifted with the root-branch Jacobian: the chain
+    then targets the prior itself (used to tell the prior's own marginals from the stationary distribution of the
+    reference's cycle, which mixes kernels with and without the root-branch Jacobian)"""
+    B = binding
+    cyc = [(B.MH_SCALE_SCALAR, s, 10.0, 1.0, 0, 3) for s in (0, 1, 2, 3, 4)]
+    inner = [i for i in range(1, md.n_nodes) if md.child0[i] >= 0]
+    cyc += [(B.MH_SLIDE_NODE, i, 0.01, 1.0, 0, 5) for i in inner]
+    cyc += [(B.MH_SCALE_BRANCH, i, 100.0, 1.0, 0, 1) for i in range(1, md.n_nodes)]
+    return cyc
+
+
+def sample(n_chains=4096, periods=None, n_sampling=400, thin=50, seed=11, cycle=None, log=None, root_upper=None):
     """burn-in with auto tuning, then `n_sampling` iterations with the node ages H h_i of all chains recorded every `thin`-th
     iteration -> (ages [n_records * n_chains][N], tuned cycle, acceptance rates per cycle entry)"""
-    md, x0 = load_model()
+    md, x0 = load_model(root_upper=root_upper)
     N = md.n_nodes
     ev = binding.Evaluator(md)
     ev.chains_set(np.tile(x0, (n_chains, 1)))
     rng = np.random.default_rng(seed)
-    cycle = mh_cycle.reference_cycle(md)
+    cycle = mh_cycle.reference_cycle(md) if cycle is None else cycle(md)
     cycle, k = mh_cycle.burn_in(ev, md, cycle, rng, seed=seed, k0=0, periods=periods)
     ages, acc, prop = [], np.zeros(len(cycle)), np.zeros(len(cycle))
     for _ in range(n_sampling // thin):
@@ -55,7 +73,12 @@ def sample(n_chains=4096, periods=None, n_sampling=400, thin=50, seed=11, tune_s
     return np.concatenate(ages), cycle, acc / np.maximum(prop, 1)
 
 
-def compare(ages, g):
+def compare(ages, g, prefix=""):
+    """our statistics beside the reference's: per node (mean, sd, 2.5 %, 50 %, 97.5 %) of ours, of the pooled reference samples
+    and the range over the six reference runs; prefix "below_" = the statistics conditional on a root age below g["below"]"""
+    if prefix:
+        ages = ages[ages[:, 0] < float(g["below"])]
+        g = {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)} | {"nodes": g["nodes"], "quantile_grid": g["quantile_grid"]}
     nodes = g["nodes"]
     q = g["quantile_grid"]
     iq = [int(np.argmin(np.abs(q - x))) for x in (0.025, 0.5, 0.975)]
@@ -75,8 +98,12 @@ if __name__ == "__main__":
     ns = int(sys.argv[3]) if len(sys.argv) > 3 else 400
     periods = [max(5, int(round(n * scale))) for n in mh_cycle.BURN_IN_FAST + mh_cycle.BURN_IN_SLOW]
     t0 = time.time()
-    ages, cycle, rates = sample(nch, periods, ns, log=print)
+    mode = sys.argv[4] if len(sys.argv) > 4 else "reference"
+    ru = float(sys.argv[6]) if len(sys.argv) > 6 else None
+    ages, cycle, rates = sample(nch, periods, ns, cycle=exact_cycle if mode == "exact" else None, log=print, root_upper=ru)
     print(f"{time.time() - t0:.1f} s, {len(ages)} samples")
+    if len(sys.argv) > 5 and sys.argv[5] != "-":
+        np.save(sys.argv[5], ages.astype(np.float32))
     g = np.load(os.path.join(GOLDEN, "mtcdnapri-prior-samples.npz"))
     print("node  stat: ours  pooled-reference  [run min, run max]")
     for r in compare(ages, g):
