@@ -2,12 +2,15 @@
 """bench.py -- log-posterior + gradient evaluations / second (batched chains).
 
 Workload (BASELINE.json configs[4], the one the north-star target is quoted on): synthetic 1000-leaf
-tree (N = 1999 nodes, K = 1997 MVN dimensions, dense precision matrix), 8192 chains PER GPU
-(weak scaling: chains are independent, the model is replicated, no data-path collective), uncorrelated
-log-normal clock, 16 calibrations / 8 constraints / 4 braces.  One "step" = one batched evaluation of
-ln prior (three parts), ln likelihood, ln Jacobian and the full HMC gradient for every chain.
+tree (N = 1999 nodes, K = 1997 MVN dimensions, dense precision matrix), uncorrelated log-normal clock,
+16 calibrations / 8 constraints / 4 braces.  One "step" = one batched evaluation of ln prior (three parts),
+ln likelihood, ln Jacobian and the full HMC gradient for every chain.  Chains are independent and the model is
+replicated, so there is no data-path collective.
+  --scaling weak   (default) 8192 chains PER GPU;
+  --scaling strong 8192 chains in total, 8192 / N per GPU (the split SURVEY 8e names).
+With N > 1 the default (weak) line also carries a `strong_scaling` object measured in the same run.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--scaling weak|strong] [--impl reference]
 
   value : chains/s with states resident in HBM (mcd_eval_grad_device), CUDA events, max over ranks
   e2e   : chains/s through the host-buffer C-ABI call mcd_eval_grad (pinned host states in, ln-posterior
@@ -41,21 +44,67 @@ UNIT = "evals/s"
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 FP64 FMA/clk/SM x 1965 MHz = 37.2
 INT8_NOMINAL_TOPS = 4500.0                           # dense int8 tensor peak (2x the 2.25 PFLOP/s bf16 figure)
 INT8_LIBRARY_GEMM_TOPS = 3079.7                      # cuBLASLt int8 GEMM measured on this pool (profiles/r01_int8_peak_measured.json)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the contraction kernel at this shape, from one
-# `ncu --set full` capture of this command (profiles/r01_ncu_summary.md):
-#   gemm_f64_dmma_kernel      237.9 MB + 113.7 MB (algorithmic: P 32 MB + DX 131 MB + Y 134 MB = 297 MB)
-#   gemm_i8_ozaki_kernel<7>   see NCU_DRAM_BYTES below (algorithmic: P planes 29 MB + DX planes 117 MB + Y 134 MB)
-NCU_DRAM_BYTES = {0: 351.5e6, 7: 308.1e6}
+GLOBAL_CHAINS_STRONG = 8192
+
+
+def ncu_dram_bytes(oz_s):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the contraction kernel at the benchmark shape, from the
+    tracked summary of the last `ncu --set full` capture of the shipped kernel (profiles/dram_traffic.json)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+        e = t["gemm_f64_dmma_kernel" if oz_s == 0 else f"gemm_i8_ozaki_kernel<{oz_s}>"]
+        return float(e["dram_read_bytes"]) + float(e["dram_write_bytes"])
+    except Exception:
+        return None
 
 
 def workload_config(n_gpus, chains):
+    mb = lambda x: f"{x * chains / 8192:.0f}"
     return {
         "workload": "synthetic 1000-leaf tree (N=1999 nodes, K=1997, dense precision), "
                     f"{chains} chains per GPU, value+gradient, uncorrelated log-normal clock, 16 cal / 8 con / 4 braces",
         "n_leaves": N_LEAVES, "chains_per_gpu": chains, "global_chains": chains * n_gpus,
         "parallelism": f"chains sharded over {n_gpus} GPU(s), model replicated",
-        "l2": "inputs larger than L2 (states 262 MB + residuals 131 MB + gradient 262 MB per step vs 126 MB L2)",
+        "l2": f"inputs larger than L2 (states {mb(262)} MB + residual planes {mb(117)} MB + gradient {mb(262)} MB per step vs 126 MB L2)"
+              if chains >= 4096 else
+              f"states {mb(262)} MB + residual planes {mb(117)} MB + contraction result {mb(134)} MB + gradient {mb(262)} MB per step "
+              "exceed the 126 MB L2 together; every step streams all of them",
     }
+
+
+def chains_per_gpu(args, world):
+    if args.chains is not None:
+        return args.chains
+    if args.scaling == "strong":
+        if GLOBAL_CHAINS_STRONG % world:
+            raise SystemExit(f"--scaling strong: {GLOBAL_CHAINS_STRONG} chains do not divide over {world} GPUs")
+        return GLOBAL_CHAINS_STRONG // world
+    return CHAINS_PER_GPU
+
+
+def bind_to_gpu_numa_node(local):
+    """Rank placement for the host-buffer path: pin this process (and therefore the pinned buffers it allocates afterwards,
+    first touch) to the CPUs of the NUMA node its GPU hangs off.  Best effort: returns a description for the JSON line."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                      text=True, timeout=20).strip().lower()
+        dom, rest = bus.split(":", 1)
+        dev = f"{dom[-4:]}:{rest}"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read())
+        cpus = open(f"/sys/bus/pci/devices/{dev}/local_cpulist").read().strip()
+        if node < 0 or not cpus:
+            return {"numa_node": node, "bound": False}
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if not ids:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "bound": True, "cpus": cpus}
+    except Exception as exc:  # no sysfs / nvidia-smi: run unpinned
+        return {"bound": False, "why": type(exc).__name__}
 
 
 def build_workload(chains, seed_offset=0):
@@ -129,13 +178,32 @@ def cpu_port_rate(md, X, threads, target_seconds=12.0):
     return n * reps / dt, n * reps, dt
 
 
+def cpu_blas_contraction_rate(md, n=2048, reps=3):
+    """Upper bound for ANY CPU implementation of the step: the contraction alone, Y = DX . Sigma^-1, as one batched DGEMM through
+    the BLAS numpy links (OpenBLAS, all host threads) -- chains/s if everything else were free."""
+    try:
+        P = np.ascontiguousarray(md.precision, dtype=np.float64).reshape(md.dim, md.dim)
+        DX = np.random.default_rng(0).normal(size=(n, md.dim))
+        DX @ P
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            DX @ P
+        dt = (time.perf_counter() - t0) / reps
+        return {"value": n / dt, "unit": UNIT, "gflops": 2.0 * n * md.dim * md.dim / dt / 1e9,
+                "note": f"contraction only ({n} chains x K x K DGEMM, numpy/OpenBLAS, all host threads): an upper bound for a CPU "
+                        "implementation, not the reference's algorithm (it does one gemv per state, app/Probability.hs:169)"}
+    except Exception as exc:
+        return {"unavailable": type(exc).__name__}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle as O
     threads = O.max_threads()
-    md, X = build_workload(CHAINS_PER_GPU)
+    chains = chains_per_gpu(args, max(1, args.gpus))
+    md, X = build_workload(max(chains, 4 * threads))
     orc = O.Oracle(md)
     probe = 4 * threads
     t0 = time.perf_counter()
@@ -150,13 +218,13 @@ def run_reference(args):
         orc.eval_grad(X[:n], nthreads=threads)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    cfg = workload_config(args.gpus, CHAINS_PER_GPU)
+    cfg = workload_config(args.gpus, chains)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} of {CHAINS_PER_GPU} chains per step (bounded sample of the same workload); "
+                         "sample": f"{n} of {chains} chains per step (bounded sample of the same workload); "
                                    "oracle CPU port (C++ -O3 -march=native, std::thread over chains); the Haskell "
                                    "reference cannot be built here (no GHC)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -174,9 +242,9 @@ def roofline(oz_s, K, B, gemm_ms, kms, ncalls, args):
     on, and the FP64-equivalent rate against the FP64 peak is given beside it."""
     flops_alg = 2.0 * K * K * B
     share = {"residual_ms": kms[0] / max(1, ncalls), "contraction_ms": gemm_ms, "posterior_ms": kms[2] / max(1, ncalls)}
-    traffic = args.traffic if args.traffic is not None else NCU_DRAM_BYTES.get(oz_s)
+    traffic = args.traffic if args.traffic is not None else ncu_dram_bytes(oz_s)
     if B != CHAINS_PER_GPU:
-        traffic = None
+        traffic = None   # the capture is of the 8192-chain launch
     fp64_equiv = flops_alg / (gemm_ms * 1e-3) / 1e12
     if oz_s == 0:
         return {"kernel": "gemm_f64_dmma_kernel", "bound": "tensor", "achieved": fp64_equiv, "peak": FP64_NOMINAL_TFLOPS,
@@ -196,8 +264,10 @@ def roofline(oz_s, K, B, gemm_ms, kms, ncalls, args):
         pass
     return {"kernel": f"gemm_i8_ozaki_kernel<{oz_s}>", "bound": "tensor", "achieved": achieved, "peak": INT8_NOMINAL_TOPS,
             "unit": "TOP/s (int8)", "frac": achieved / INT8_NOMINAL_TOPS, "traffic": traffic,
-            "peak_source": "nominal dense INT8 tensor peak (4.5 POP/s); MEASURED_PEAKS.json has no int8 entry -- twice its "
-                           f"measured bf16 burst figure would be {2 * peaks.get('bf16_tflops', 1662.5):.0f} TOP/s",
+            "peak_source": "nominal dense INT8 tensor peak (4.5 POP/s); MEASURED_PEAKS.json has no int8 entry -- the figure derived "
+                           f"from it is twice its measured bf16 burst, {2 * peaks.get('bf16_tflops', 1662.5):.0f} TOP/s "
+                           "(frac_derived_from_measured)",
+            "frac_derived_from_measured": achieved / (2 * peaks.get("bf16_tflops", 1662.5)),
             "frac_of_measured": {
                 "vs_2x_bf16_burst_of_MEASURED_PEAKS": achieved / (2 * peaks.get("bf16_tflops", 1662.5)),
                 "vs_library_int8_gemm_measured": achieved / INT8_LIBRARY_GEMM_TOPS,
@@ -256,9 +326,10 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    placement = bind_to_gpu_numa_node(local) if not args.no_numa else {"bound": False, "why": "--no-numa"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.chains
+    B = chains_per_gpu(args, world)
     md, X = build_workload(B, seed_offset=rank)
     S, K = md.state_len, md.dim
     ev = binding.Evaluator(md, device=local, max_batch=B)
@@ -327,6 +398,27 @@ def run_gpu(args):
     kms, ncalls = ev.kernel_times()
     ev.set_kernel_timing(False)
     launches = ev.kernel_launches() - launches0
+    # the same step on the strong-scaling split (8192 chains in total, 8192 / N on this GPU), measured in the same run
+    strong = None
+    if world > 1 and args.scaling == "weak" and args.chains is None and GLOBAL_CHAINS_STRONG % world == 0:
+        Bs = GLOBAL_CHAINS_STRONG // world
+
+        def strong_step():
+            ev.eval_grad_device(Bs, d_states.data_ptr(), d_out.data_ptr(), d_grad.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+
+        for _ in range(3):
+            strong_step()
+        barrier()
+        ev.set_kernel_timing(True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            strong_step()
+        s1.record()
+        barrier()
+        skms, sncalls = ev.kernel_times()
+        ev.set_kernel_timing(False)
+        strong = {"ms": s0.elapsed_time(s1), "chains_per_gpu": Bs, "kernel_ms": [x / max(1, sncalls) for x in skms]}
     # value-only evaluation (what the Metropolis-Hastings proposals need): triangular contraction on the Cholesky factor
     ev.eval_device(B, d_states.data_ptr(), d_out.data_ptr(), d_status.data_ptr(), stream.cuda_stream)  # factorises once
     for _ in range(2):
@@ -452,11 +544,12 @@ def run_gpu(args):
         torch.equal(h_out2, h_out)) and bool(torch.equal(h_gtheta, torch.from_numpy(
             np.ascontiguousarray(h_grad.numpy()[:, mask][:, ::-1]))))
 
-    t = torch.tensor([ms, e2e_s * 1e3, e2e_state_s * 1e3, traj_s * 1e3, e2e_pipe_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, e2e_state_s * 1e3, traj_s * 1e3, e2e_pipe_s * 1e3, strong["ms"] if strong else 0.0],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max, e2e_state_ms_max, traj_ms_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
-    e2e_pipe_ms_max = float(t[4])
+    e2e_pipe_ms_max, strong_ms_max = float(t[4]), float(t[5])
     if rank == 0:
         total = B * world
         value = total * args.steps / (ms_max * 1e-3)
@@ -465,9 +558,12 @@ def run_gpu(args):
         gemm_ms = kms[1] / max(1, ncalls)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak" if args.chains is not None else args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(world, B), contraction=("fp64 dmma" if oz_s == 0 else f"int8 tensor cores, {oz_s} base-256 digit planes per operand (error-free split)")),
+            "config": workload_config(world, B), "global_chains": total,
+            "contraction": "fp64 dmma" if oz_s == 0 else f"int8 tensor cores, {oz_s} base-256 digit planes per operand (error-free split)",
+            "rank_placement": placement,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 8 + S * 8,
                     "d2h_bytes_per_step": B * (D + model.OUT_COLS) * 8 + B * 4,
                     "note": "mcd_eval_grad_theta_async / mcd_wait on two sets of pinned host buffers (HMC position vectors in, packed "
@@ -494,13 +590,23 @@ def run_gpu(args):
             "roofline": roofline(oz_s, K, B, gemm_ms, kms, ncalls, args),
             "clocks": clocks, "outputs_ok": ok and pipe_ok,
         }
+        if strong:
+            line["strong_scaling"] = {
+                "value": GLOBAL_CHAINS_STRONG * args.steps / (strong_ms_max * 1e-3), "unit": UNIT, "scaling": "strong",
+                "global_chains": GLOBAL_CHAINS_STRONG, "chains_per_gpu": strong["chains_per_gpu"],
+                "ms_per_step": strong_ms_max / args.steps,
+                "kernel_ms_rank0": {"residual": strong["kernel_ms"][0], "contraction": strong["kernel_ms"][1], "posterior": strong["kernel_ms"][2]},
+                "contraction_tiles": f"{(strong['chains_per_gpu'] + 127) // 128} x {(K + 63) // 64} tiles of 128 chains x 64 rows on {torch.cuda.get_device_properties(local).multi_processor_count} persistent CTAs",
+                "note": "same step, 8192 chains in total split evenly over the GPUs (SURVEY 8e); device-resident, max over ranks; "
+                        "speed-up over one GPU = value / the one-GPU value of this bench"}
         if world == 1 and not args.no_cpu:
             from oracle import oracle as O
             threads = O.max_threads()
             rate, n, dt = cpu_port_rate(md, X, threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n} chains of the same workload in {dt:.1f} s (oracle CPU port, "
-                                              "std::thread over chains)"}
+                                              "std::thread over chains)",
+                                    "best_case_blas_contraction": cpu_blas_contraction_rate(md)}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -518,7 +624,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU (overrides --scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 8192 chains per GPU; strong: 8192 chains in total, split evenly over the GPUs")
+    ap.add_argument("--no-numa", action="store_true", help="do not pin the ranks to their GPU's NUMA node")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the contraction kernel from ncu (default: the committed capture)")

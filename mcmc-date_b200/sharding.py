@@ -8,14 +8,16 @@ heated chain i targets prior^beta_i * likelihood^beta_i.
 """
 from __future__ import annotations
 
-import numpy as np
-
 
 def shard_range(n_chains: int, world: int, rank: int):
-    """Contiguous block of chains owned by `rank` (first `n_chains % world` ranks get one extra)."""
-    base, rem = divmod(n_chains, world)
-    start = rank * base + min(rank, rem)
-    return start, start + base + (1 if rank < rem else 0)
+    """Contiguous block of chains owned by `rank`.  The chains must divide evenly over the ranks: the all-gather of the swap
+    statistics and the slot tables of mcd_mc3_configure assume the same number of chains on every rank."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("shard_range: rank out of range")
+    if n_chains % world != 0:
+        raise ValueError(f"shard_range: {n_chains} chains do not divide evenly over {world} ranks")
+    per = n_chains // world
+    return rank * per, (rank + 1) * per
 
 
 def allgather_swap_stats(local_stats, world: int, dist=None):
@@ -28,23 +30,3 @@ def allgather_swap_stats(local_stats, world: int, dist=None):
                       device=local_stats.device)
     dist.all_gather_into_tensor(out, local_stats.contiguous())
     return out
-
-
-def mc3_swap_decisions(stats: np.ndarray, betas: np.ndarray, n_swaps: int, seed: int):
-    """Propose `n_swaps` swaps between neighbouring heated chains and accept with the MC3 ratio
-    ((prior*lik)_j / (prior*lik)_i)^(beta_i - beta_j).  Deterministic in (stats, betas, seed), so
-    every rank that holds the gathered statistics reaches the same permutation.
-    Returns the list of accepted (i, j) pairs."""
-    rng = np.random.default_rng(seed)
-    lp = stats[:, 0] + stats[:, 1]
-    n = len(betas)
-    accepted = []
-    for _ in range(n_swaps):
-        i = int(rng.integers(0, n - 1))
-        j = i + 1
-        log_ratio = (betas[i] - betas[j]) * (lp[j] - lp[i])
-        u = rng.random()
-        if np.isfinite(log_ratio) and np.log(u) < log_ratio:
-            accepted.append((i, j))
-            lp[[i, j]] = lp[[j, i]]
-    return accepted

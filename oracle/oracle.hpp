@@ -51,6 +51,7 @@ struct Model {
   int K = 0;                              // N-2
   std::vector<double> mu;                 // [K]
   std::vector<double> prec;               // [K*K] row-major Sigma^-1 (LIK_FULL) or [K] variances
+  bool prec_symmetric = true;             // LIK_FULL: prec == prec^T exactly (`prepare` writes an unsymmetrised LU inverse)
   std::vector<int> sp_row, sp_col;        // LIK_SPARSE: association list ((i, j), v) as stored by the
   std::vector<double> sp_val;             //   reference (SparseS, app/Main.hs:75-81,95-97)
   double logdet = 0;                      // ln det Sigma   (or sum ln var)

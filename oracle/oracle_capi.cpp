@@ -49,6 +49,10 @@ void* orc_model_create(int N, const int* parent, const int* child0, const int* c
   if (lik == LIK_FULL || lik == LIK_UNIVARIATE) {
     size_t np = lik == LIK_FULL ? (size_t)K * K : (size_t)K;
     M->prec.assign(prec_or_var, prec_or_var + np);
+    if (lik == LIK_FULL)
+      for (int i = 0; i < K && M->prec_symmetric; ++i)
+        for (int j = 0; j < i; ++j)
+          if (M->prec[(size_t)i * K + j] != M->prec[(size_t)j * K + i]) { M->prec_symmetric = false; break; }
   }
   if (lik == LIK_SPARSE) {
     M->sp_row.assign(sp_row, sp_row + nnz);

@@ -64,11 +64,7 @@ inline Result<double> eval_grad_double(const Model& M, const double* x, const ui
       for (int k = 0; k < M.K; ++k) w[k] = -y[k];
       // y = dx <# P = P^T dx; the gradient of -1/2 dx^T P dx is -1/2 (P + P^T) dx.  `prepare` writes the LU inverse of the
       // covariance unsymmetrised (app/Main.hs:230), so P may differ from P^T in the last digits: add the other half then.
-      bool sym = true;
-      for (int i = 0; i < M.K && sym; ++i)
-        for (int j = 0; j < i; ++j)
-          if (M.prec[(size_t)i * M.K + j] != M.prec[(size_t)j * M.K + i]) { sym = false; break; }
-      if (!sym) {
+      if (!M.prec_symmetric) {
         std::vector<double> d = distances(M, s, t);
         for (int i = 0; i < M.K; ++i) {
           double z = 0;

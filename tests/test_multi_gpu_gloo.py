@@ -23,8 +23,6 @@ def _worker(rank, world, port, q):
     stats_all = rng.normal(size=(B, 2)) * 10.0          # stands in for (ln prior, ln lik) of every chain
     local = torch.from_numpy(stats_all[a:b].copy())
     gathered = sharding.allgather_swap_stats(local, world, dist).numpy()
-    betas = np.linspace(1.0, 0.3, B)
-    swaps = sharding.mc3_swap_decisions(gathered.copy(), betas, n_swaps=3, seed=42)
     # the device path's decision rule (mcd_mc3_swap, restated in tests/mh_ref.py): every rank updates its replica of the
     # slot table from the gathered statistics and the shared Philox counters
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -34,7 +32,7 @@ def _worker(rank, world, port, q):
     ladder = 1.0 / (1.0 + 0.4 * np.arange(C))
     for it in range(5):
         mh_ref.mc3_swap(gathered, slot, cos, ladder, ladder, C, -1, 99, it)
-    swaps = (swaps, slot.tolist())
+    swaps = slot.tolist()
     q.put((rank, a, b, gathered.tolist(), swaps))
     dist.barrier()
     dist.destroy_process_group()
@@ -58,5 +56,16 @@ def test_two_rank_gloo_allgather_and_swaps():
     full = rng.normal(size=(64, 2)) * 10.0
     assert np.array_equal(np.array(g0), full) and np.array_equal(np.array(g1), full)
     assert s0 == s1
-    slots = np.array(s0[1])
+    slots = np.array(s0)
     assert (np.sort(slots.reshape(-1, 8), axis=1) == np.arange(8)).all() and (slots != np.arange(64) % 8).any()
+
+
+def test_shard_range_needs_an_even_split():
+    sys.path.insert(0, ROOT)
+    import pytest
+    from mcmc_date_b200 import sharding
+    assert [sharding.shard_range(64, 4, r) for r in range(4)] == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    with pytest.raises(ValueError):
+        sharding.shard_range(65, 4, 0)
+    with pytest.raises(ValueError):
+        sharding.shard_range(64, 4, 4)

@@ -15,7 +15,6 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 from mcmc_date_b200 import binding, mh_cycle, model  # noqa: E402
 
 N_CHAINS, SWAP_PERIOD, N_SWAPS = 64, 2, 3
@@ -31,8 +30,10 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    from util import load_fixture
-    md, z = load_fixture("mtcdnapri-7-leaves", clock=model.AUTOCORRELATED_LOGNORMAL)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "mtcdnapri-7-leaves.npz"))    # model + states of the 7-taxon data set
+    md = model.ModelDesc(parent=z["parent"], mean=z["mean"], precision=z["precision"], logdet_sigma=float(z["logdet_sigma"]),
+                         clock_model=model.AUTOCORRELATED_LOGNORMAL, likelihood=int(z["likelihood"]), ht=float(z["ht"]),
+                         cal_node=z["cal_node"], cal_lo=z["cal_lo"], cal_lo_p=z["cal_lo_p"], cal_hi=z["cal_hi"], cal_hi_p=z["cal_hi_p"])
     n_global = groups * N_CHAINS
     assert n_global % world == 0, "chains must divide over the ranks"
     B = n_global // world
@@ -93,6 +94,12 @@ def main():
               f"{iters * steps_per_sweep * n_global / dt / 1e6:.2f} M proposals/s; acceptance "
               f"{tot_acc / (iters * steps_per_sweep * B):.2f}; chains off their initial slot {moved}/{n_global}; "
               f"slots a permutation per group and identical on all ranks: {ok}; finite posteriors {np.isfinite(out[:, 6]).mean():.2f}")
+        import json
+        print(json.dumps({"config": "mtCDNApri 7 leaves, autocorrelated log-normal clock, MC3", "groups": groups, "heated_chains_per_group": N_CHAINS,
+                          "n_gpus": world, "chains_per_gpu": B, "iterations": iters, "proposal_steps_per_iteration": steps_per_sweep,
+                          "swap_period": SWAP_PERIOD, "n_swaps": N_SWAPS, "iterations_per_s": iters / dt,
+                          "proposals_per_s": iters * steps_per_sweep * n_global / dt, "acceptance": tot_acc / (iters * steps_per_sweep * B),
+                          "chains_off_initial_slot": moved, "slot_tables_identical_on_all_ranks": ok}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
