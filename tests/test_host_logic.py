@@ -161,11 +161,14 @@ def test_synthetic_generators_are_seeded_and_valid():
 
 
 def test_shard_ranges_partition_chains():
-    for B, W in [(8192, 8), (64, 8), (10, 4), (7, 3)]:
+    for B, W in [(8192, 8), (64, 8), (8192, 1), (12, 4)]:
         spans = [sharding.shard_range(B, W, r) for r in range(W)]
         assert spans[0][0] == 0 and spans[-1][1] == B
         assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
-        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+        assert len({b - a for a, b in spans}) == 1          # the all-gather and the MC3 slot tables need equal shards
+    for B, W in [(10, 4), (7, 3)]:
+        with pytest.raises(ValueError):
+            sharding.shard_range(B, W, 0)
 
 
 def test_library_loads_and_exports_every_declared_symbol():
@@ -417,3 +420,182 @@ def test_mc3_swap_restatement_keeps_permutations():
         assert (np.sort(slot.reshape(G, C), axis=1) == np.arange(C)).all()
         assert all(slot[cos[g * C + p]] == p for g in range(G) for p in range(C))
     assert 0 < tot < 30 * G
+
+
+@pytest.mark.parametrize("kind", range(17))
+def test_proposals_touch_the_state_entries_their_lenses_name(kind):
+    """Which entries of the state a proposal may change is fixed by the lens it is lifted through in app/Definitions.hs:145-279
+    (e.g. `ratesTimeTreeL = tripleLens timeBirthRate rateMean timeTree`, :236-237, for scaleRatesAndTreeContrarily -- the
+    PFunction's local name `mu` is the MEAN RATE, lib/Mcmc/Tree/Proposal/Contrary.hs:435-436, not the death rate).  The host
+    restatement the CUDA kernels are compared with step by step must change exactly entries inside that set, and must change the
+    scalars the lens names."""
+    R, md, x, parent, braces = _small_mh_model()
+    topo = R.topology(parent)
+    child, size, inner, inner_list = topo
+    N = len(parent)
+    LA, MU, H, OH, OM, OV, OR = 0, 1, 2, 3, 3 + N, 4 + N, 5 + N
+    heights = set(range(OH + 1, OH + N))       # the root's relative height is never touched
+    rates = set(range(OR + 1, OR + N))         # the stem of the rate tree is never touched
+    table = {   # kind: (lens of app/Definitions.hs, entries it may change, scalars it must change)
+        R.SLIDE_NODE: ("timeTree", heights, set()), R.SCALE_SUBTREE: ("timeTree", heights, set()),
+        R.PULLEY: ("timeTree", heights, set()), R.SLIDE_BRACE: ("timeTree", heights, set()),
+        R.SCALE_BRANCH: ("rateTree", rates, set()), R.SCALE_RATE_SUBTREE: ("rateTree", rates, set()),
+        R.SCALE_NORM_TREE_CONTRA_M: ("rateMeanRateTreeL", rates | {OM}, {OM}),
+        R.SCALE_NORM_TREE_CONTRA_H: ("timeHeightRateTreeL", rates | {H}, {H}),
+        R.SCALE_VAR_TREE: ("rateVarianceRateTreeL", rates | {OV}, {OV}),
+        R.SCALE_VAR_TREE_AUTO: ("rateMeanVarianceTreeL", rates | {OV}, {OV}),          # the mean is used but unchanged
+        R.SLIDE_NODE_CONTRA: ("timeRateTreesL", heights | rates, set()),
+        R.SCALE_SUBTREE_CONTRA: ("timeRateTreesL", heights | rates, set()),
+        R.SLIDE_BRACE_CONTRA: ("timeRateTreesL", heights | rates, set()),
+        R.SLIDE_ROOT_CONTRA: ("heightTimeRateTreesLens", heights | rates | {H}, {H}),
+        R.SCALE_RATES_TREE_CONTRA: ("ratesTimeTreeL", heights | {LA, OM}, {LA, OM}),
+        R.SCALE_H_M_CONTRA: ("timeHeightRateMeanL", {H, OM}, {H, OM}),
+    }
+    cases = [(kind, inner_list[1])] if kind != R.SCALE_SCALAR else [(kind, j) for j in range(5)]
+    for kd, node in cases:
+        if kd == R.SCALE_SCALAR:
+            off = [LA, MU, H, OM, OV][node]
+            may, must = {off}, {off}
+        else:
+            _, may, must = table[kd]
+            node = {R.SCALE_BRANCH: 3, R.SLIDE_BRACE: 0, R.SLIDE_BRACE_CONTRA: 0}.get(kd, node)
+        y, lqj, _ = R.propose(x.copy(), parent, topo, braces, kd, node, 0.5 if kd not in R.MULT_KINDS else 20.0, 1.0, 5, 0, 3)
+        assert y is not None
+        changed = set(np.nonzero(y != x)[0].tolist())
+        assert changed and changed <= may, (kd, sorted(changed - may))
+        assert must <= changed, (kd, sorted(must - changed))
+
+
+def _leafdist(nd, acc=None, path=0.0):
+    """leaf -> distance from the root of a nested-dict tree"""
+    acc = {} if acc is None else acc
+    if not nd["children"]:
+        acc[nd["name"]] = path
+    for c in nd["children"]:
+        _leafdist(c, acc, path + (c["length"] or 0.0))
+    return acc
+
+
+def _pairwise(nd):
+    """all leaf-to-leaf path lengths (an invariant of the unrooted tree)"""
+    out = {}
+
+    def rec(n):
+        if not n["children"]:
+            return {n["name"]: 0.0}
+        sides = []
+        for c in n["children"]:
+            sides.append({k: v + (c["length"] or 0.0) for k, v in rec(c).items()})
+        for i in range(len(sides)):
+            for j in range(i + 1, len(sides)):
+                for a, da in sides[i].items():
+                    for b, db in sides[j].items():
+                        out[frozenset((a, b))] = da + db
+        merged = {}
+        for s_ in sides:
+            merged.update(s_)
+        return merged
+
+    rec(nd)
+    return out
+
+
+def test_outgroup_rerooting():
+    """prepare.outgroup (elynx `outgroup`, app/Main.hs:179-180): the root moves to the branch that separates the outgroup, the
+    unrooted tree (all leaf-to-leaf distances) is unchanged, the split branch is halved, and the sub-tree order follows the
+    documented `descend` rule"""
+    t = tree.parse_newick("((a:1,b:2)x:1,(c:3,(d:4,e:5)y:2)z:1)r;")
+    same = prepare.outgroup({"a", "b"}, t)
+    assert same is t                                              # already rooted there: unchanged (`roots t` starts with t)
+    assert prepare.outgroup({"c", "d", "e"}, t) is t              # either side of the bipartition
+    r = prepare.outgroup({"d", "e"}, t)
+    assert [prepare._leaf_set(c) for c in r["children"]] == [frozenset("abc"), frozenset("de")]
+    assert r["children"][0]["length"] == 1.0 and r["children"][1]["length"] == 1.0       # y's branch of 2 split in halves
+    assert r["name"] == "r" and r["children"][0]["name"] == "z" and r["children"][1]["name"] == "y"
+    # upside-down part: [former up-going part with the two root branches joined (1 + 1), then the former sibling c]
+    up = r["children"][0]["children"]
+    assert up[0]["name"] == "x" and up[0]["length"] == 2.0 and up[1]["name"] == "c" and up[1]["length"] == 3.0
+    pw0, pw1 = _pairwise(t), _pairwise(r)
+    assert pw0.keys() == pw1.keys() and all(abs(pw0[k] - pw1[k]) < 1e-12 for k in pw0)
+    # a single leaf as outgroup, two levels down
+    r2 = prepare.outgroup({"e"}, t)
+    assert [sorted(prepare._leaf_set(c)) for c in r2["children"]] == [["a", "b", "c", "d"], ["e"]]
+    pw2 = _pairwise(r2)
+    assert all(abs(pw0[k] - pw2[k]) < 1e-12 for k in pw0)
+    assert r2["children"][1]["length"] == 2.5 and r2["children"][0]["children"][1]["name"] == "d"
+    # multifurcating (unrooted) input: a bifurcating root is introduced on the leftmost branch first
+    u = tree.parse_newick("(a:1,b:2,(c:3,d:4):5);")
+    ru = prepare.outgroup({"c", "d"}, u)
+    assert [sorted(prepare._leaf_set(c)) for c in ru["children"]] in ([["a", "b"], ["c", "d"]], [["c", "d"], ["a", "b"]])
+    pu0, pu1 = _pairwise(u), _pairwise(ru)
+    assert all(abs(pu0[k] - pu1[k]) < 1e-12 for k in pu0)
+    parent, c0, c1, names, lens = tree.flatten_preorder(ru)      # bifurcating everywhere now
+    assert len(parent) == 7
+    with pytest.raises(ValueError):
+        prepare.outgroup({"a", "c"}, t)                           # not monophyletic on either side
+    with pytest.raises(ValueError):
+        prepare.outgroup(set(), t)
+
+
+def test_prepare_reroots_the_tree_list_and_checks_topologies():
+    rng = np.random.default_rng(3)
+    L = rng.uniform(0.5, 2.0, size=(24, 8))
+    fmt = "((a:{0},b:{1}):{2},(c:{3},(d:{4},e:{5}):{6}):{7});"
+    trees_ = [fmt.format(*row) for row in L]
+    rooted = "((d:1,e:1):1,((a:1,b:1):1,c:1):1);"              # same topology, rooted on the branch above (d, e)
+    pr = prepare.prepare_from_treelist("\n".join(trees_), rooted_tree_text=rooted)
+    names = pr["names"]
+    assert [names[i] for i in range(len(names)) if names[i]] == ["a", "b", "c", "d", "e"]
+    assert np.nonzero(pr["parent"] == 0)[0].tolist() == [1, 6]          # ((a,b),c) first, (d,e) second
+    kept = L[len(L) // 6:]
+    assert len(pr["mean"]) == 7 and pr["mean"][0] == pytest.approx(kept[:, 6].mean())    # the split branch: both halves summed
+    assert pr["mean"][1] == pytest.approx((kept[:, 2] + kept[:, 7]).mean())             # the two old root branches joined
+    assert np.allclose(pr["precision"] @ pr["cov"], np.eye(7), atol=1e-8)
+    with pytest.raises(ValueError, match="single topology"):
+        prepare.prepare_from_treelist("\n".join(trees_), rooted_tree_text="((d:1,e:1):1,((a:1,c:1):1,b:1):1);")
+    with pytest.raises(ValueError, match="duplicate leaves"):
+        prepare.prepare_from_treelist("((a:1,a:2):1,(c:3,(d:4,e:5):2):1);\n" * 6)
+    with pytest.raises(ValueError, match="equal sub tree orders"):
+        prepare.prepare_from_treelist("\n".join(trees_[:12] + ["((b:2,a:1):1,(c:3,(d:4,e:5):2):1);"] * 6))
+
+
+def test_calibrations_from_an_mcmctree_labelled_tree():
+    """loadCalibrationsFromTree (lib/Mcmc/Tree/Prior/Node/CalibrationFromTree.hs): quoted labels, L / U / B bounds, default
+    probability mass 0.01, leftmost / rightmost leaf naming, pre-order of the labelled tree"""
+    mean_tree = tree.parse_newick("((((h:1,(c:1,b:1):1):1,g:1):1,(o:1,s:1):1):1,x:1);")
+    parent, c0, c1, names, _ = tree.flatten_preorder(mean_tree)
+    text = "((((h, (c, b)) 'B(6,8,2.5e-2,2.5e-2)', g) 'L(9)', (o, s)) 'B(12,16)', x) 'U(100,2.5e-2)';"
+    cal = prepare.load_calibrations_from_tree(text, parent, names)
+    assert cal["names"] == ["h-x", "h-s", "h-g", "h-b"] and cal["node"].tolist() == [0, 1, 2, 3]
+    assert cal["lo"].tolist() == [0.0, 12.0, 9.0, 6.0] and cal["hi"].tolist() == [100.0, 16.0, np.inf, 8.0]
+    assert cal["lo_p"].tolist() == [0.5, 0.01, 0.01, 0.025] and cal["hi_p"].tolist() == [0.025, 0.01, 0.5, 0.025]
+    assert prepare.mean_root_height(cal) == 50.0                      # getMeanRootHeight: b / 2 without a lower bound
+    # attoparsec's `double` needs a leading digit: MCMCtree's 'B(.06,.08)' is not a calibration for McmcDate
+    assert prepare._parse_mcmctree_label("B(.06,.08)") is None and prepare._parse_mcmctree_label("U(1.0)") == (None, None, 1.0, 0.01)
+    with pytest.raises(ValueError, match="no calibrations"):
+        prepare.load_calibrations_from_tree("((h,(c,b)),x);", parent, names)
+    with pytest.raises(ValueError, match="Lower boundary larger equal"):
+        prepare.load_calibrations_from_tree("((((h,(c,b))'B(8,6)',g),(o,s)),x);", parent, names)
+    # the reference's own file for the 7-taxon set is what the fixture was built from
+    _, z7 = load_fixture("mtcdnapri-7-leaves")
+    assert z7["cal_node"].tolist() == [0, 1, 3] and z7["cal_hi"].tolist() == [100.0, 16.0, 8.0] and z7["cal_lo"].tolist() == [0.0, 12.0, 6.0]
+    assert z7["cal_hi_p"].tolist() == [0.025] * 3
+
+
+def test_auto_tuner_and_cycle_order():
+    from mcmc_date_b200 import mh_cycle
+    md, _ = load_fixture("mtcdnapri-7-leaves")
+    cyc = mh_cycle.reference_cycle(md)
+    assert sum(e[5] for e in cyc) == 253                                  # proposal steps per iteration of the 7-taxon cycle
+    assert [mh_cycle.optimal_rate(d) for d in (1, 2, 3, 4, 5, 50)] == pytest.approx([0.44, 0.3885, 0.337, 0.2855, 0.234, 0.234])
+    dims = {e[:2]: mh_cycle.proposal_dimension(md, e) for e in cyc}
+    from mcmc_date_b200 import binding as B
+    assert dims[(B.MH_SCALE_RATES_TREE_CONTRA, 0)] == 7 and dims[(B.MH_SLIDE_ROOT_CONTRA, 0)] == 9 and dims[(B.MH_PULLEY, 0)] == 5 \
+        if (B.MH_PULLEY, 0) in dims else True
+    assert dims[(B.MH_SCALE_NORM_TREE_CONTRA_M, 0)] == 13 and dims[(B.MH_SCALE_H_M_CONTRA, 0)] == 2
+    lst, idx = mh_cycle.random_order(cyc, np.random.default_rng(0))
+    assert len(lst) == 253 and np.bincount(idx, minlength=len(cyc)).tolist() == [e[5] for e in cyc] and all(e[5] == 1 for e in lst)
+    acc = np.array([0.9 * e[5] for e in cyc])
+    tuned = mh_cycle.auto_tune(md, cyc, acc, np.array([float(e[5]) for e in cyc]))
+    assert all(t[3] > c[3] for t, c in zip(tuned, cyc))                   # rates above every target: larger steps
+    assert tuned[0][3] == pytest.approx(np.exp(2 * (0.9 - 0.44)))
