@@ -140,8 +140,15 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(O
 // t / n_pr, P-row tile t % n_pr), so CTAs that run together share the chains' planes and sweep P, which stays
 // L2-resident.  The shared-memory ring and its parities run on across tiles: the producer prefetches the next
 // tile's first k-blocks while the epilogue warps drain TMEM.
+#ifndef MCD_OZ_MAXNREG
+#define MCD_OZ_MAXNREG 0
+#endif
 template <int S>
+#if MCD_OZ_MAXNREG > 0
+__global__ void __maxnreg__(MCD_OZ_MAXNREG)   // register cap: leaves room for CTAs of the HBM-side kernels on the same SM
+#else
 __global__ void __launch_bounds__(OZ_THREADS, 1)
+#endif
 gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ Y,
                      int nkb, int ldy, int Bp, int Mp, int bt_base, int n_pr, int n_tiles, int upper_tri, int kb_lo,

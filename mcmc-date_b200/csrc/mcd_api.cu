@@ -103,6 +103,12 @@ struct mcd_handle {
   int oz_U_S = 0;
   CUtensorMap tmA8{}, tmB8{}, tmU8{};
   cudaStream_t streams[N_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+  // device-path pipeline (eval_device on large dense models): chunks of chains run K1 / contraction / K3 on three streams so
+  // that the HBM-side kernels of one chunk overlap the tensor-core contraction of its neighbours
+  cudaStream_t pipe_st[3] = {nullptr, nullptr, nullptr};  // K1, contraction (high priority), K3
+  std::vector<cudaEvent_t> pipe_ev;
+  int pipe_chunks = 0;            // 0 / 1: off
+  int pipe_k3_per_sm = 1;         // resident K3 CTAs per SM for all but the last chunk (0: unlimited)
   std::mutex mtx;
   std::string err;
   int64_t launches = 0;
@@ -408,6 +414,82 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   return 0;
 }
 
+// Device-path pipeline for large dense models on the INT8 contraction: the batch is cut into `pipe_chunks` chunks (multiples
+// of 128 chains); chunk j runs K1 on pipe_st[0], the contraction on pipe_st[1] (high priority: its persistent CTAs get the SMs
+// first) and K3 on pipe_st[2].  K1 of chunk j + 1 and K3 of chunk j - 1 are resident on the SMs beside the contraction's one CTA
+// per SM (its register budget leaves room for them), so the FP64 / HBM work hides behind the tensor-core work.
+template <bool GRAD, int S>
+int enqueue_pipelined(mcd_handle* h, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
+                      cudaStream_t user) {
+  DevModel M = h->dm;
+  M.quad_from_z = 0;
+  const int nc = h->pipe_chunks;
+  const int per = ((n + nc - 1) / nc + OZ_M - 1) / OZ_M * OZ_M;
+  if (!h->pipe_st[0]) {
+    int lo = 0, hi = 0;
+    CU_TRY(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU_TRY(h, cudaStreamCreateWithPriority(&h->pipe_st[0], cudaStreamNonBlocking, lo));
+    CU_TRY(h, cudaStreamCreateWithPriority(&h->pipe_st[1], cudaStreamNonBlocking, hi));
+    CU_TRY(h, cudaStreamCreateWithPriority(&h->pipe_st[2], cudaStreamNonBlocking, lo));
+    // every kernel of the pipeline asks for the maximum shared-memory carve-out: an SM never has to drain to change its
+    // L1 / shared split before a CTA of another kernel can join
+    if (!getenv("MCD_PIPE_NO_CARVEOUT")) {
+      cudaFuncSetAttribute(residual_split_kernel<S>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(posterior_kernel<256, 0, GRAD, POST_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(posterior_kernel<256, 1, GRAD, POST_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(posterior_kernel<256, 2, GRAD, POST_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(posterior_kernel<256, 3, GRAD, POST_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
+  }
+  const size_t need = 2 + 3 * (size_t)nc;
+  while (h->pipe_ev.size() < need) {
+    cudaEvent_t e;
+    CU_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->pipe_ev.push_back(e);
+  }
+  cudaEvent_t e_in = h->pipe_ev[0];
+  CU_TRY(h, cudaEventRecord(e_in, user));
+  for (int i = 0; i < 3; ++i) CU_TRY(h, cudaStreamWaitEvent(h->pipe_st[i], e_in, 0));
+  const size_t stride = (size_t)h->cap * h->ld8;
+  const size_t smem = POST_SMEM_FIXED + (size_t)M.S * 8;
+  int j = 0;
+  for (int c0 = 0; c0 < n; c0 += per, ++j) {
+    const int m = std::min(per, n - c0);
+    const double* xs = d_states + (size_t)c0 * M.S;
+    cudaEvent_t e1 = h->pipe_ev[2 + 3 * j], e2 = h->pipe_ev[3 + 3 * j], e3 = h->pipe_ev[4 + 3 * j];
+    residual_split_kernel<S><<<m, 256, (size_t)h->ld8 * 8, h->pipe_st[0]>>>(
+        M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs, h->d_pX.as<signed char>() + (size_t)c0 * h->ld8, h->ld8, stride,
+        h->d_sX.as<double>() + c0, m);
+    CU_TRY(h, cudaEventRecord(e1, h->pipe_st[0]));
+    CU_TRY(h, cudaStreamWaitEvent(h->pipe_st[1], e1, 0));
+    const int np = (m + OZ_M - 1) / OZ_M * OZ_M;
+    CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, h->tmB8, h->d_sX.as<double>(), h->d_sP.as<double>(), h->d_y.as<double>(), h->Mp8, np,
+                                      h->ld8, M.ldy, h->cap, h->pipe_st[1], c0, h->n_sms, 0));
+    CU_TRY(h, cudaEventRecord(e2, h->pipe_st[1]));
+    CU_TRY(h, cudaStreamWaitEvent(h->pipe_st[2], e2, 0));
+    const double* y = h->d_y.as<double>() + (size_t)c0 * M.ldy;
+    double* o = d_out + (size_t)c0 * MCD_OUT_COLS;
+    double* g = GRAD ? d_grad + (size_t)c0 * M.S : nullptr;
+    int32_t* st_ = d_status + c0;
+    // all but the last chunk: at most `pipe_k3_per_sm` CTAs per SM, so that the next chunk's contraction CTA fits beside them
+    const bool last = c0 + per >= n;
+    const int k3grid = last || h->pipe_k3_per_sm <= 0 ? m : std::min(m, h->pipe_k3_per_sm * h->n_sms);
+#define MCD_LAUNCH_POST_P(CC) posterior_kernel<256, CC, GRAD, POST_MINB><<<k3grid, POST_THREADS, smem, h->pipe_st[2]>>>(M, xs, y, o, g, st_, m)
+    switch (M.clock) {
+      case 0: MCD_LAUNCH_POST_P(0); break;
+      case 1: MCD_LAUNCH_POST_P(1); break;
+      case 2: MCD_LAUNCH_POST_P(2); break;
+      default: MCD_LAUNCH_POST_P(3); break;
+    }
+#undef MCD_LAUNCH_POST_P
+    CU_TRY(h, cudaEventRecord(e3, h->pipe_st[2]));
+    CU_TRY(h, cudaStreamWaitEvent(user, e3, 0));
+    h->launches += 3;
+  }
+  CU_TRY(h, cudaGetLastError());
+  return 0;
+}
+
 template <bool GRAD>
 int eval_device(mcd_handle* h, int n, const double* d_states, double* d_out, double* d_grad, int32_t* d_status,
                 void* stream) {
@@ -418,6 +500,11 @@ int eval_device(mcd_handle* h, int n, const double* d_states, double* d_out, dou
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, false, GRAD)) return -1;
   if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && (ensure_cholesky(h, nullptr) || ensure_i8(h))) return -1;
+  // pipelined form: value + gradient on a large dense model with the INT8 contraction, not while per-kernel timing is on
+  if (GRAD && h->pipe_chunks > 1 && !h->timing && h->dm.lik == MCD_LIK_FULL && !h->sparse && h->oz_S != 0 &&
+      h->N > SMALL_TREE_MAX_NODES && n >= 2 * OZ_M * h->pipe_chunks)
+    return h->oz_S == 6 ? enqueue_pipelined<GRAD, 6>(h, n, d_states, d_out, d_grad, d_status, static_cast<cudaStream_t>(stream))
+                        : enqueue_pipelined<GRAD, 7>(h, n, d_states, d_out, d_grad, d_status, static_cast<cudaStream_t>(stream));
   return enqueue<GRAD>(h, 0, n, d_states, d_out, d_grad, d_status, static_cast<cudaStream_t>(stream));
 }
 
@@ -1260,6 +1347,10 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
     else if (e && !strcmp(e, "i8s6")) h->oz_S = 6;
     else if (e && !strcmp(e, "i8s7")) h->oz_S = 7;
     else if (e && *e) return bail("mcd_create: MCD_CONTRACTION must be one of dmma, i8s6, i8s7");
+    const char* pc = getenv("MCD_PIPE");   // chunks of the device-path pipeline (experiments; 0 / 1 = off)
+    if (pc) h->pipe_chunks = std::max(0, std::min(16, atoi(pc)));
+    const char* pk = getenv("MCD_PIPE_K3");
+    if (pk) h->pipe_k3_per_sm = atoi(pk);
   }
   h->parent.assign(d->parent, d->parent + N);
   h->child1 = child1;
@@ -1464,6 +1555,9 @@ void mcd_destroy(mcd_handle* h) {
   cudaDeviceSynchronize();
   for (int i = 0; i < N_STREAMS; ++i)
     if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+  for (int i = 0; i < 3; ++i)
+    if (h->pipe_st[i]) cudaStreamDestroy(h->pipe_st[i]);
+  for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
   if (h->nuts_flags) cudaFreeHost(h->nuts_flags);
   for (int i = 0; i < 2; ++i)
     if (h->nuts_ev[i]) cudaEventDestroy(h->nuts_ev[i]);
