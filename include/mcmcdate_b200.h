@@ -122,6 +122,12 @@ int mcd_eval_grad(mcd_handle* h, int32_t n_chains, const double* states /*[B][S]
 int mcd_eval_grad_theta(mcd_handle* h, int32_t n_chains, const double* theta /*[B][D]*/,
                         const double* base_state /*[S]*/, double* out /*[B][MCD_OUT_COLS]*/,
                         double* grad_theta /*[B][D]*/, int32_t* status /*[B]*/);
+/* Ordering between entry points.  All calls on one handle share its device work buffers.  The library orders them itself:
+ * a call that runs on a single stream (the *_device forms on the caller's stream; mcd_leapfrog, mcd_nuts, mcd_chains_*,
+ * mcd_mh_*, mcd_mc3_* on the library's) first waits, on the device, for whatever earlier pipelined host-buffer calls
+ * (mcd_eval*, mcd_eval*_async) and the previous single-stream call still have in flight, and the pipelined calls wait for the
+ * last single-stream call.  No mcd_wait / mcd_synchronize is needed between calls for correctness of the DEVICE work; host
+ * OUTPUT buffers of asynchronous calls are of course valid only after their ticket has been waited for. */
 /* The same without the final wait: returns a ticket (>= 0; < 0: error) after enqueueing; the outputs are valid after
  * mcd_wait(ticket) (or mcd_synchronize); the host buffers must stay alive and untouched until then.  Back-to-back calls
  * overlap the PCIe fill of one with the drain of the previous one (chunk k of every call runs in order on stream k % 4 on

@@ -86,6 +86,11 @@ struct mcd_handle {
   int inc_steps = 0, refresh_every = 512, ldyc = 0;
   std::vector<double> base_host;       // base state currently on the device (theta-packed entry points)
   cudaEvent_t ticket_ev[8][N_STREAMS] = {};  // completion events of the last 8 asynchronous calls
+  // ordering between the pipelined host-buffer calls (streams 0..3, shared work buffers) and everything else
+  cudaEvent_t join_ev[N_STREAMS] = {};       // 'pipeline stream i has reached this point'
+  cudaEvent_t serial_ev = nullptr;           // 'the last non-pipelined call has reached this point'
+  cudaStream_t serial_stream = nullptr;
+  bool pipeline_dirty = false, serial_dirty = false;
   int64_t next_ticket = 0;
   const double* y_override = nullptr;  // see enqueue(posterior_only)
   int y_override_ld = 0;
@@ -414,6 +419,50 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   return 0;
 }
 
+// ---- stream ordering.  All entry points share the handle's work buffers (digit planes, y, staging rows).  The pipelined
+// host-buffer calls leave work in flight on streams 0..3; every other entry point works on ONE stream (streams[0] or the
+// caller's).  begin_serial makes that stream wait for whatever the pipeline and the previous non-pipelined call still have in
+// flight; end_serial publishes its own completion point; begin_pipelined makes the pipeline streams wait for that point.
+// Without these, mixing e.g. mcd_eval_grad_theta_async with mcd_mh_cycle, or mcd_eval_device on two user streams, raced.
+int begin_serial(mcd_handle* h, cudaStream_t st) {
+  if (h->pipeline_dirty) {
+    for (int i = 0; i < N_STREAMS; ++i) {
+      if (h->streams[i] == st) continue;
+      if (!h->join_ev[i]) CU_TRY(h, cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
+      CU_TRY(h, cudaEventRecord(h->join_ev[i], h->streams[i]));
+      CU_TRY(h, cudaStreamWaitEvent(st, h->join_ev[i], 0));
+    }
+    h->pipeline_dirty = false;
+  }
+  if (h->serial_dirty && h->serial_stream != st) CU_TRY(h, cudaStreamWaitEvent(st, h->serial_ev, 0));
+  return 0;
+}
+int end_serial(mcd_handle* h, cudaStream_t st) {
+  if (!h->serial_ev) CU_TRY(h, cudaEventCreateWithFlags(&h->serial_ev, cudaEventDisableTiming));
+  CU_TRY(h, cudaEventRecord(h->serial_ev, st));
+  h->serial_stream = st;
+  h->serial_dirty = true;
+  return 0;
+}
+int begin_pipelined(mcd_handle* h) {
+  if (h->serial_dirty) {
+    for (int i = 0; i < N_STREAMS; ++i)
+      if (h->streams[i] != h->serial_stream) CU_TRY(h, cudaStreamWaitEvent(h->streams[i], h->serial_ev, 0));
+    h->serial_dirty = false;
+    // a later non-pipelined call on another stream is ordered after the pipeline, which is now ordered after this point
+  }
+  h->pipeline_dirty = true;
+  return 0;
+}
+// scope guard for the single-stream entry points
+struct SerialScope {
+  mcd_handle* h;
+  cudaStream_t st;
+  int rc;
+  SerialScope(mcd_handle* h_, cudaStream_t st_) : h(h_), st(st_), rc(begin_serial(h_, st_)) {}
+  ~SerialScope() { if (rc == 0) end_serial(h, st); }
+};
+
 // Device-path pipeline for large dense models on the INT8 contraction: the batch is cut into `pipe_chunks` chunks (multiples
 // of 128 chains); chunk j runs K1 on pipe_st[0], the contraction on pipe_st[1] (high priority: its persistent CTAs get the SMs
 // first) and K3 on pipe_st[2].  K1 of chunk j + 1 and K3 of chunk j - 1 are resident on the SMs beside the contraction's one CTA
@@ -500,6 +549,8 @@ int eval_device(mcd_handle* h, int n, const double* d_states, double* d_out, dou
   CU_TRY(h, cudaSetDevice(h->device));
   if (ensure_capacity(h, n, false, GRAD)) return -1;
   if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && (ensure_cholesky(h, nullptr) || ensure_i8(h))) return -1;
+  SerialScope order(h, static_cast<cudaStream_t>(stream));
+  if (order.rc) return -1;
   // pipelined form: value + gradient on a large dense model with the INT8 contraction, not while per-kernel timing is on
   if (GRAD && h->pipe_chunks > 1 && !h->timing && h->dm.lik == MCD_LIK_FULL && !h->sparse && h->oz_S != 0 &&
       h->N > SMALL_TREE_MAX_NODES && n >= 2 * OZ_M * h->pipe_chunks)
@@ -536,6 +587,7 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
   if (!GRAD && h->dm.lik == MCD_LIK_FULL && !getenv("MCD_NO_CHOLESKY") && (ensure_cholesky(h, nullptr) || ensure_i8(h))) return -1;
   const int S = h->S;
   int ci = 0;
+  if (begin_pipelined(h)) return -1;
   for (const auto& cm : chunk_schedule(n, S)) {
     const int c0 = cm.first, m = cm.second;
     cudaStream_t st = h->streams[ci++ % N_STREAMS];
@@ -551,6 +603,7 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
   }
   if (async) return record_ticket(h, ticket_out);
   for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
+  h->pipeline_dirty = false;
   return 0;
 }
 
@@ -576,6 +629,7 @@ int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* bas
     h->base_host.assign(base, base + S);
   }
   int ci = 0;
+  if (begin_pipelined(h)) return -1;
   for (const auto& cm : chunk_schedule(n, S)) {
     const int c0 = cm.first, m = cm.second;
     cudaStream_t st = h->streams[ci++ % N_STREAMS];
@@ -596,6 +650,7 @@ int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* bas
   }
   if (!async) {
     for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaStreamSynchronize(h->streams[i]));
+    h->pipeline_dirty = false;
     return 0;
   }
   return record_ticket(h, ticket_out);
@@ -604,9 +659,11 @@ int wait_ticket(mcd_handle* h, int64_t ticket) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
   if (ticket < 0 || ticket >= h->next_ticket) return fail(h, "mcd_wait: unknown ticket");
-  if (ticket + 8 <= h->next_ticket) return 0;  // older than the ring: completed when a later call reused its streams' events
   CU_TRY(h, cudaSetDevice(h->device));
-  for (int i = 0; i < N_STREAMS; ++i) CU_TRY(h, cudaEventSynchronize(h->ticket_ev[ticket % 8][i]));
+  // a ticket older than the ring of 8: its slot now holds the events of a LATER call, recorded on the same in-order streams, so
+  // their completion implies the old call's
+  for (int i = 0; i < N_STREAMS; ++i)
+    if (h->ticket_ev[ticket % 8][i]) CU_TRY(h, cudaEventSynchronize(h->ticket_ev[ticket % 8][i]));
   return 0;
 }
 
@@ -621,6 +678,8 @@ int leapfrog_host(mcd_handle* h, int n, int L, const double* theta0, const doubl
   if (!theta0 || !mom0 || !base || !inv_mass || !eps || !theta_out || !mom_out || !out || !energy || !status)
     return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   if (ensure_capacity(h, n, true, true)) return -1;
   const int S = h->S, D = h->D;
   const size_t nd = (size_t)h->cap * D * 8;
@@ -700,6 +759,8 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
   if (!inv_mass || !eps || !accept_stat || !info || !status || (!resident && (!theta0 || !base || !theta_out || !out)))
     return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   if (ensure_capacity(h, n, true, true)) return -1;
   const int S = h->S, D = h->D;
   const size_t BD = (size_t)n * D;
@@ -868,6 +929,8 @@ int chains_set(mcd_handle* h, int n, const double* states) {
   std::lock_guard<std::mutex> lock(h->mtx);
   if (n <= 0 || !states) return fail(h, "mcd_chains_set: need n > 0 and a state buffer");
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   if (mh_prepare_value_path(h, n)) return -1;
   const int S = h->S, N = h->N;
   h->undo_stride = S + MH_MAX_OPS;
@@ -944,6 +1007,8 @@ int chains_get(mcd_handle* h, int n, double* states, double* out, int32_t* statu
   std::lock_guard<std::mutex> lock(h->mtx);
   if (n <= 0 || n > h->n_resident) return fail(h, "mcd_chains_get: more chains requested than are resident");
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   cudaStream_t st = h->streams[0];
   if (states) CU_TRY(h, cudaMemcpyAsync(states, h->d_chain.p, (size_t)n * h->S * 8, cudaMemcpyDeviceToHost, st));
   if (out) CU_TRY(h, cudaMemcpyAsync(out, h->d_chain_out.p, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost, st));
@@ -1161,6 +1226,8 @@ int mh_step(mcd_handle* h, int kind, int node, double param, double tune, int us
   if (n <= 0) return fail(h, "mcd_mh_step: no resident chains (call mcd_chains_set first)");
   if (mh_check(h, kind, node, param, tune)) return -1;
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   if (mh_prepare_value_path(h, n)) return -1;
   if (mh_enqueue(h, kind, node, param, tune, use_root_jacobian, seed, iteration, nullptr)) return -1;
   if (accepted) {
@@ -1182,6 +1249,8 @@ int mh_cycle(mcd_handle* h, int n_props, const mcd_mh_proposal* props, int n_ite
   for (int p = 0; p < n_props; ++p)
     if (props[p].repeat < 0 || mh_check(h, props[p].kind, props[p].node, props[p].param, props[p].tune)) return -1;
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   if (mh_prepare_value_path(h, n)) return -1;
   cudaStream_t st = h->streams[0];
   unsigned long long* cnt = h->d_counters.as<unsigned long long>();
@@ -1208,6 +1277,8 @@ int mc3_configure(mcd_handle* h, int n_global, int chain_offset, int C, const do
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   if (C == 0) {  // back to cold chains (the global chain offset of the random streams stays)
     h->mc3_C = 0;
     if (chain_offset >= 0) h->mc3_offset = chain_offset;
@@ -1237,6 +1308,8 @@ int mc3_swap(mcd_handle* h, int pair, uint64_t seed, uint32_t iteration, const d
   if (!d_stats_global && (h->mc3_offset != 0 || h->mc3_n_global != h->n_resident))
     return fail(h, "mcd_mc3_swap: groups span ranks -- pass the all-gathered (ln prior, ln likelihood) table");
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   cudaStream_t st = h->streams[0];
   const int G = h->mc3_n_global / h->mc3_C;
   const double* stats = d_stats_global ? d_stats_global : h->d_chain_out.as<double>() + MCD_OUT_LNPRIOR;
@@ -1256,6 +1329,8 @@ int mc3_slots(mcd_handle* h, int32_t* slots) {
   std::lock_guard<std::mutex> lock(h->mtx);
   if (h->mc3_C <= 0 || !slots) return fail(h, "mcd_mc3_slots: no temperature ladder configured");
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   CU_TRY(h, cudaMemcpyAsync(slots, h->d_slot.p, (size_t)h->mc3_n_global * 4, cudaMemcpyDeviceToHost, h->streams[0]));
   CU_TRY(h, cudaStreamSynchronize(h->streams[0]));
   return 0;
@@ -1670,6 +1745,8 @@ int mcd_chains_stats_device(mcd_handle* h, double* d_stats) {
   std::lock_guard<std::mutex> lock(h->mtx);
   if (h->n_resident <= 0 || !d_stats) return fail(h, "mcd_chains_stats_device: no resident chains or null buffer");
   CU_TRY(h, cudaSetDevice(h->device));
+  SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
+  if (order.rc) return -1;
   CU_TRY(h, cudaMemcpy2DAsync(d_stats, 16, h->d_chain_out.as<double>() + MCD_OUT_LNPRIOR, MCD_OUT_COLS * 8, 16, h->n_resident,
                               cudaMemcpyDeviceToDevice, h->streams[0]));
   CU_TRY(h, cudaStreamSynchronize(h->streams[0]));

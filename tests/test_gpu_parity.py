@@ -970,6 +970,60 @@ def test_asynchronous_theta_calls_overlap_safely():
     ev.close()
 
 
+def test_mixed_entry_points_are_ordered_without_explicit_waits():
+    """The pipelined host-buffer calls leave work in flight on four streams over the handle's shared work buffers; device-pointer
+    calls run on the caller's streams and the resident-chain calls on the library's.  The library orders them against each
+    other itself: mixing them WITHOUT mcd_wait / mcd_synchronize in between gives what the serial sequence gives."""
+    import torch
+    md, h = synth.synthetic_model(300, seed=12, n_cal=3, n_con=2, n_brace=1)
+    B = 1400
+    ev = binding.Evaluator(md)
+    mask = ev.mask().astype(bool)
+    D, S = ev.D, md.state_len
+    XA, XB, XC = (synth.synthetic_states(md, h, B, seed=300 + i) for i in range(3))
+    for X in (XB, XC):
+        X[:, 2] = XA[0, 2]
+    theta = torch.from_numpy(np.ascontiguousarray(XA[:, mask][:, ::-1])).pin_memory()
+    base = torch.from_numpy(XA[0].copy()).pin_memory()
+    # serial reference
+    refA = ev.eval_grad_theta(theta.numpy(), base.numpy())
+    refB = ev.eval_grad(XB)
+    ev.chains_set(XC)
+    accC = ev.mh_step(binding.MH_SCALE_BRANCH, -1, 50.0, seed=9, iteration=1)
+    refC = ev.chains_get()
+    ev.synchronize()
+    dev = torch.device("cuda", 0)
+    dXB = torch.from_numpy(XB).to(dev)
+    for rep in range(3):
+        oA = (torch.empty((B, model.OUT_COLS), dtype=torch.float64).pin_memory(), torch.empty((B, D), dtype=torch.float64).pin_memory(),
+              torch.empty(B, dtype=torch.int32).pin_memory())
+        d_out = torch.zeros((B, model.OUT_COLS), dtype=torch.float64, device=dev)
+        d_grad = torch.zeros((B, S), dtype=torch.float64, device=dev)
+        d_st = torch.zeros(B, dtype=torch.int32, device=dev)
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        torch.cuda.synchronize()
+        t = ev.eval_grad_theta_async_ptr(B, theta.data_ptr(), base.data_ptr(), oA[0].data_ptr(), oA[1].data_ptr(), oA[2].data_ptr())
+        # no wait: a device-pointer call on one user stream, the resident-chain calls on the library's stream, then another
+        # device-pointer call on a second user stream
+        ev.eval_grad_device(B, dXB.data_ptr(), d_out.data_ptr(), d_grad.data_ptr(), d_st.data_ptr(), s1.cuda_stream)
+        ev.chains_set(XC)
+        acc = ev.mh_step(binding.MH_SCALE_BRANCH, -1, 50.0, seed=9, iteration=1)
+        d_out2 = torch.zeros_like(d_out)
+        d_grad2 = torch.zeros_like(d_grad)
+        d_st2 = torch.zeros_like(d_st)
+        ev.eval_grad_device(B, dXB.data_ptr(), d_out2.data_ptr(), d_grad2.data_ptr(), d_st2.data_ptr(), s2.cuda_stream)
+        t2 = ev.eval_grad_theta_async_ptr(B, theta.data_ptr(), base.data_ptr(), oA[0].data_ptr(), oA[1].data_ptr(), oA[2].data_ptr())
+        Xc, oc, sc = ev.chains_get()
+        ev.wait(t)
+        ev.wait(t2)
+        torch.cuda.synchronize()
+        assert np.array_equal(oA[0].numpy(), refA[0]) and np.array_equal(oA[1].numpy(), refA[1]) and np.array_equal(oA[2].numpy(), refA[2])
+        for o_, g_, s_ in ((d_out, d_grad, d_st), (d_out2, d_grad2, d_st2)):
+            assert np.array_equal(o_.cpu().numpy(), refB[0]) and np.array_equal(g_.cpu().numpy(), refB[1]) and np.array_equal(s_.cpu().numpy(), refB[2])
+        assert np.array_equal(acc, accC) and np.array_equal(Xc, refC[0]) and np.array_equal(oc, refC[1]) and np.array_equal(sc, refC[2])
+    ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)
