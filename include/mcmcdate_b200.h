@@ -49,7 +49,9 @@ enum { MCD_ST_REF_ERROR = 1,    /* the reference would have called `error` (abor
        MCD_ST_ZERO = 2,         /* ln posterior = -inf (probability zero) */
        MCD_ST_NAN = 4,          /* ln posterior is NaN */
        MCD_ST_NEARCRIT = 8,     /* |lambda - mu| < 1e-6 (BirthDeath.hs:125-126) */
-       MCD_ST_LEAF_HEIGHT = 16  /* a leaf height != 0: HeightTree invariant violated */ };
+       MCD_ST_LEAF_HEIGHT = 16, /* a leaf height != 0: HeightTree invariant violated */
+       MCD_ST_FP64_FALLBACK = 32 /* informational: this chain's residuals span too wide a range for the INT8 digit planes (largest
+                                  * standardised residual > 512 x their mean); its contraction was recomputed in plain FP64 */ };
 /* columns of one output row (MCD_OUT_COLS doubles per chain) */
 enum { MCD_OUT_LNA = 0,     /* calibrations * constraints * braces */
        MCD_OUT_LNB = 1,     /* exponential(lambda) * exponential(mu) * birth-death */

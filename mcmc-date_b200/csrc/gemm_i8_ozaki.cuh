@@ -49,6 +49,15 @@ constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, w
 constexpr int OZ_TMEM_COLS = 512;
 constexpr int OZ_MAX_SLICES = 7;  // 8 S bits must fit one int64
 
+// A chain in which at least half of the equilibrated residuals are more than this factor below the largest one is recomputed
+// in FP64 (fp64_rows_kernel): the digits are relative to the row maximum, so with a typical residual R times below it the error
+// of y relative to a typical component is bounded by K 2^-56 R -- 1.5e-11 at K = 2048 for R = 512.  (Relative to
+// the chain's LARGEST component the split is always accurate to K 2^-55.)
+#ifndef MCD_OZ_WIDE_RATIO
+#define MCD_OZ_WIDE_RATIO 512.0
+#endif
+constexpr double OZ_WIDE_RATIO = MCD_OZ_WIDE_RATIO;
+
 template <int S>
 __host__ __device__ constexpr int oz_stage_bytes() { return S * (OZ_M + OZ_N) * OZ_KB; }
 template <int S>
@@ -340,18 +349,23 @@ __device__ __forceinline__ unsigned long long oz_digit_bytes(double x, double mu
   return ((unsigned long long)__double2ll_rn(x * mult) + C) ^ C;
 }
 
+// colmul / rowmul (nullable): the row that is split is x[k] * colmul[k] * rowmul[row] -- the power-of-two equilibration of the
+// precision matrix (P' = C P C, see oz_equilibration) -- and rowpost[row] (nullable) multiplies the published row scale.
 template <int S>
 __global__ void __launch_bounds__(256)
 oz_split_rows_kernel(const double* __restrict__ X, int ldx, int rows, int K, signed char* __restrict__ planes, int ld8,
-                     size_t plane_stride, double* __restrict__ scale, double post_scale) {
+                     size_t plane_stride, double* __restrict__ scale, double post_scale,
+                     const double* __restrict__ colmul = nullptr, const double* __restrict__ rowmul = nullptr,
+                     const double* __restrict__ rowpost = nullptr) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const double* x = X + (size_t)row * ldx;
+  const double rm = rowmul ? rowmul[row] : 1.0;
   double amax = 0.0;
   bool finite = true;
   for (int k = lane; k < K; k += 32) {
-    const double a = fabs(x[k]);
+    const double a = fabs(x[k] * (colmul ? colmul[k] : 1.0) * rm);
     finite = finite && (a <= 1.7976931348623157e308);
     amax = fmax(amax, a);
   }
@@ -362,10 +376,10 @@ oz_split_rows_kernel(const double* __restrict__ X, int ldx, int rows, int K, sig
   }
   double mult;
   const double sc = oz_row_scale<S>(amax, finite, &mult);
-  if (lane == 0) scale[row] = sc * post_scale;
+  if (lane == 0) scale[row] = sc * post_scale * (rowpost ? rowpost[row] : 1.0);
   signed char* out = planes + (size_t)row * ld8;
   for (int k = lane; k < K; k += 32) {
-    const unsigned long long q = oz_digit_bytes<S>(finite ? x[k] : 0.0, mult);
+    const unsigned long long q = oz_digit_bytes<S>(finite ? x[k] * (colmul ? colmul[k] : 1.0) * rm : 0.0, mult);
 #pragma unroll
     for (int s = 0; s < S; ++s) out[(size_t)s * plane_stride + k] = (signed char)(q >> (8 * (S - 1 - s)));
   }
@@ -381,7 +395,7 @@ template <int S>
 __global__ void __launch_bounds__(256)
 residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ parent, const double* __restrict__ mu,
                       const double* __restrict__ states, signed char* __restrict__ planes, int ld8, size_t plane_stride,
-                      double* __restrict__ scale, int B) {
+                      double* __restrict__ scale, int B, const double* __restrict__ ick, int* __restrict__ widecnt) {
   extern __shared__ __align__(16) unsigned char smem_rs[];
   double* sdx = reinterpret_cast<double*>(smem_rs);  // [ld8]
   __shared__ double s_amax[8];
@@ -401,7 +415,8 @@ residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ 
     double e = (h[parent[i] & 0x7fffffff] - h[i]) * r[i];
     if (i == 1) e = e + (h[0] - h[root_r]) * r[root_r];
     const int k = i < root_r ? i - 1 : i - 2;
-    const double d = e * sc - mu[k];
+    // the residual in the equilibrated coordinates x'_k = (d_k - mu_k) / c_k (c_k a power of two: exact)
+    const double d = (e * sc - mu[k]) * ick[k];
     sdx[k] = d;
     const double a = fabs(d);
     bad |= !(a <= 1.7976931348623157e308);
@@ -420,10 +435,17 @@ residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ 
   double mult;  // non-finite rows: zero digits, NaN scale
   const double scl = oz_row_scale<S>(amax, finite, &mult);
   if (tid == 0) scale[chain] = scl;
+  // dynamic range of this chain's residuals: the digits are relative to the LARGEST one.  Every warp counts the residuals it
+  // converts that are more than OZ_WIDE_RATIO times smaller than the largest; fp64_rows_kernel adds the counts up and
+  // recomputes the chain in FP64 when they are the majority (no extra barrier here)
+  const double small_below = finite ? amax * (1.0 / OZ_WIDE_RATIO) : -1.0;
+  int n_small = 0;
   signed char* prow = planes + (size_t)chain * ld8;
   for (int q4 = tid; q4 < ld8 / 4; q4 += 256) {
     const double2 x01 = *reinterpret_cast<const double2*>(sdx + 4 * q4);
     const double2 x23 = *reinterpret_cast<const double2*>(sdx + 4 * q4 + 2);
+    n_small += (int)(fabs(x01.x) < small_below && 4 * q4 < K) + (int)(fabs(x01.y) < small_below && 4 * q4 + 1 < K) +
+               (int)(fabs(x23.x) < small_below && 4 * q4 + 2 < K) + (int)(fabs(x23.y) < small_below && 4 * q4 + 3 < K);
     const unsigned long long j0 = oz_digit_bytes<S>(finite ? x01.x : 0.0, mult), j1 = oz_digit_bytes<S>(finite ? x01.y : 0.0, mult),
                              j2 = oz_digit_bytes<S>(finite ? x23.x : 0.0, mult), j3 = oz_digit_bytes<S>(finite ? x23.y : 0.0, mult);
 #pragma unroll
@@ -435,6 +457,11 @@ residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ 
       const uint32_t lo = __byte_perm(a0, a1, sel), hi = __byte_perm(a2, a3, sel);   // {a0[b], a1[b]}, {a2[b], a3[b]}
       *reinterpret_cast<uint32_t*>(prow + (size_t)s * plane_stride + 4 * q4) = __byte_perm(lo, hi, 0x5410);
     }
+  }
+  if (widecnt) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) n_small += __shfl_xor_sync(0xffffffffu, n_small, off);
+    if ((tid & 31) == 0) widecnt[chain * 8 + (tid >> 5)] = n_small;
   }
 }
 
@@ -452,7 +479,7 @@ __global__ void __launch_bounds__(256)
 delta_split_kernel(int N, int SL, int root_r, const int* __restrict__ parent, const double* __restrict__ states,
                    const double* __restrict__ undo, int undo_stride, const int4* __restrict__ meta, int mode, int j, int size,
                    int k_lo, int span, int kb_lo, int kb_hi, signed char* __restrict__ planes, int ld8, size_t plane_stride,
-                   double* __restrict__ scale, int B) {
+                   double* __restrict__ scale, int B, const double* __restrict__ ick) {
   extern __shared__ __align__(16) unsigned char smem_ds[];
   double* sd = reinterpret_cast<double*>(smem_ds);  // [(kb_hi - kb_lo) * OZ_KB]
   __shared__ double s_amax[8];
@@ -486,7 +513,7 @@ delta_split_kernel(int N, int SL, int root_r, const int* __restrict__ parent, co
       }
       if (mode == 1) r_o = i > j ? ub[size + (i - j - 1)] : ub[2 * size - 1];
       if (mode == 2) r_o = ub[i - j];
-      d = ((hp_n - hi_n) * r_n) * sc - ((hp_o - hi_o) * r_o) * sc;
+      d = (((hp_n - hi_n) * r_n) * sc - ((hp_o - hi_o) * r_o) * sc) * ick[k];  // equilibrated coordinates, as in K1
     }
     sd[q] = d;
     const double a = fabs(d);
@@ -521,6 +548,54 @@ delta_split_kernel(int N, int SL, int root_r, const int* __restrict__ parent, co
       const uint32_t lo = __byte_perm(a0, a1, sel), hi = __byte_perm(a2, a3, sel);
       *reinterpret_cast<uint32_t*>(prow + (size_t)s * plane_stride + 4 * q4) = __byte_perm(lo, hi, 0x5410);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------ FP64 fall-back for flagged chains
+// y[chain][m] = sum_k M[m][k] dx_k in plain FP64 for the chains whose residual range is too wide (majority of K1's per-warp
+// counts, see residual_split_kernel; the decision is published in wide[chain] for the status word); every other CTA exits at once.
+// M = P (symmetric product) or U = L^T (upper triangular, value-only path: k >= m).  One CTA per chain: residuals into shared
+// memory (K1's arithmetic, not equilibrated), one warp per row with coalesced 256-byte reads of the row, fixed shuffle tree.
+__global__ void __launch_bounds__(256)
+fp64_rows_kernel(int N, int K, int SL, int root_r, const int* __restrict__ parent, const double* __restrict__ mu,
+                 const double* __restrict__ states, const double* __restrict__ Mx, int ldm, int upper_tri,
+                 const int* __restrict__ widecnt, int* __restrict__ wide, double* __restrict__ Y, int ldy, int B) {
+  extern __shared__ __align__(16) unsigned char smem_fb[];
+  double* sdx = reinterpret_cast<double*>(smem_fb);  // [K]
+  const int chain = blockIdx.x;
+  if (chain >= B) return;
+  const int tid = threadIdx.x;
+  const int4 c0 = *reinterpret_cast<const int4*>(widecnt + chain * 8), c1 = *reinterpret_cast<const int4*>(widecnt + chain * 8 + 4);
+  const bool flagged = 2 * (c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w) >= K;
+  if (tid == 0) wide[chain] = flagged ? 1 : 0;
+  if (!flagged) return;
+  const double* x = states + (size_t)chain * SL;
+  const double* h = x + 3;
+  const double* r = x + 5 + N;
+  const double sc = x[2] * x[3 + N];
+  for (int i = 1 + tid; i < N; i += 256) {
+    if (i == root_r) continue;
+    double e = (h[parent[i] & 0x7fffffff] - h[i]) * r[i];
+    if (i == 1) e = e + (h[0] - h[root_r]) * r[root_r];
+    const int k = i < root_r ? i - 1 : i - 2;
+    sdx[k] = e * sc - mu[k];
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  double* y = Y + (size_t)chain * ldy;
+  for (int m = warp; m < K; m += 8) {
+    const double* row = Mx + (size_t)m * ldm;
+    double a0 = 0.0, a1 = 0.0;
+    int k = (upper_tri ? (m & ~31) : 0) + lane;
+    for (; k + 32 < K; k += 64) {
+      a0 = fma(row[k], sdx[k], a0);
+      a1 = fma(row[k + 32], sdx[k + 32], a1);
+    }
+    if (k < K) a0 = fma(row[k], sdx[k], a0);
+    double a = a0 + a1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if (lane == 0) y[m] = a;
   }
 }
 

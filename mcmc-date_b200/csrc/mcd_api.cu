@@ -58,6 +58,8 @@ struct mcd_handle {
   // device model
   DevModel dm{};
   DevBuf d_parent, d_child1, d_inner, d_mu, d_var, d_P, d_U;
+  DevBuf d_ck, d_ick;             // INT8 contraction: power-of-two equilibration c_k ~ 1 / sqrt(P_kk) and its reciprocal, [ld8]
+  DevBuf d_wide, d_widecnt;       // [cap] chains whose residual range is too wide for the digit planes (FP64 fall-back); [cap][8] counts
   std::vector<double> hostP;      // K x K copy kept for the lazy Cholesky factorisation
   bool sparse = false;            // MCD_LIK_SPARSE on a large tree: CSR contraction instead of the dense one
   DevBuf d_sp_ptr, d_sp_col, d_sp_val;
@@ -152,7 +154,7 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
   if (need > h->cap) {
     CU_TRY(h, cudaDeviceSynchronize());
     for (DevBuf* b : {&h->d_dx, &h->d_y, &h->d_states, &h->d_out, &h->d_grad, &h->d_status, &h->d_theta, &h->d_gtheta,
-                      &h->d_mom, &h->d_eps, &h->d_energy, &h->d_status_acc, &h->d_pX, &h->d_sX}) {
+                      &h->d_mom, &h->d_eps, &h->d_energy, &h->d_status_acc, &h->d_pX, &h->d_sX, &h->d_wide, &h->d_widecnt}) {
       if (b->p) cudaFree(b->p);
       b->p = nullptr;
     }
@@ -238,8 +240,12 @@ int ensure_i8_planes(mcd_handle* h) {
     CU_TRY(h, cudaMemset(h->d_pP.p, 0, stride * S));
     CU_TRY(h, cudaMalloc(&h->d_sP.p, (size_t)h->Mp8 * 8));
     CU_TRY(h, cudaMemset(h->d_sP.p, 0, (size_t)h->Mp8 * 8));
+    // digit planes of the equilibrated matrix P' = C P C (C = diag(c_k), powers of two ~ 1 / sqrt(P_kk)): y = P x =
+    // C (P' x') with x' = C x ... in the kernels' terms x'_k = x_k * ick[k] (ick = 1 / c_k), P'_mk = P_mk c_m c_k, and
+    // y_m = ick[m] * sum_k P'_mk x'_k  -- the factor ick[m] goes into the published row scale
     oz_split_rows_kernel<S><<<(K + 7) / 8, 256>>>(h->d_P.as<double>(), h->ldk, K, K, h->d_pP.as<signed char>(), h->ld8,
-                                                   stride, h->d_sP.as<double>(), 1.52587890625e-05 /* 2^-16 */);
+                                                   stride, h->d_sP.as<double>(), 1.52587890625e-05 /* 2^-16 */,
+                                                   h->d_ck.as<double>(), h->d_ck.as<double>(), h->d_ick.as<double>());
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaDeviceSynchronize());
     if (oz_make_plane_map(&h->tmB8, h->d_pP.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ_N) != 0)
@@ -259,8 +265,10 @@ int ensure_i8_planes(mcd_handle* h) {
     CU_TRY(h, cudaMemset(h->d_pU.p, 0, stride * S));
     CU_TRY(h, cudaMalloc(&h->d_sU.p, (size_t)h->Mp8 * 8));
     CU_TRY(h, cudaMemset(h->d_sU.p, 0, (size_t)h->Mp8 * 8));
+    // z = U x = (U C)(C^-1 x): columns only, no row factor
     oz_split_rows_kernel<S><<<(K + 7) / 8, 256>>>(h->d_U.as<double>(), h->ldk, K, K, h->d_pU.as<signed char>(), h->ld8,
-                                                   stride, h->d_sU.as<double>(), 1.52587890625e-05 /* 2^-16 */);
+                                                   stride, h->d_sU.as<double>(), 1.52587890625e-05 /* 2^-16 */,
+                                                   h->d_ck.as<double>(), nullptr, nullptr);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaDeviceSynchronize());
     if (oz_make_plane_map(&h->tmU8, h->d_pU.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ_N) != 0)
@@ -275,6 +283,12 @@ int ensure_i8_planes(mcd_handle* h) {
     CU_TRY(h, cudaMemset(h->d_pX.p, 0, stride * S));
     CU_TRY(h, cudaMalloc(&h->d_sX.p, (size_t)h->cap * 8));
     CU_TRY(h, cudaMemset(h->d_sX.p, 0, (size_t)h->cap * 8));
+    if (!h->d_wide.p) {
+      CU_TRY(h, cudaMalloc(&h->d_wide.p, (size_t)h->cap * 4));
+      CU_TRY(h, cudaMemset(h->d_wide.p, 0, (size_t)h->cap * 4));
+      CU_TRY(h, cudaMalloc(&h->d_widecnt.p, (size_t)h->cap * 32));
+      CU_TRY(h, cudaMemset(h->d_widecnt.p, 0, (size_t)h->cap * 32));
+    }
     if (oz_make_plane_map(&h->tmA8, h->d_pX.as<signed char>(), (size_t)S * h->cap, h->ld8, OZ_M) != 0)
       return fail(h, "cuTensorMapEncodeTiled failed for the residual digit planes");
     h->oz_X_S = S;
@@ -292,12 +306,17 @@ int enqueue_i8(mcd_handle* h, int c0, int n, const double* xs, cudaStream_t st, 
   const size_t stride = (size_t)h->cap * h->ld8;
   residual_split_kernel<S><<<n, 256, (size_t)h->ld8 * 8, st>>>(
       M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs, h->d_pX.as<signed char>() + (size_t)c0 * h->ld8, h->ld8, stride,
-      h->d_sX.as<double>() + c0, n);
+      h->d_sX.as<double>() + c0, n, h->d_ick.as<double>(), h->d_widecnt.as<int>() + (size_t)c0 * 8);
   if (ev_mid) CU_TRY(h, cudaEventRecord(ev_mid, st));
   const int np = (n + OZ_M - 1) / OZ_M * OZ_M;
   CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, tri ? h->tmU8 : h->tmB8, h->d_sX.as<double>(),
                                     (tri ? h->d_sU : h->d_sP).as<double>(), h->d_y.as<double>(), h->Mp8, np, h->ld8, M.ldy,
                                     h->cap, st, c0, h->n_sms, tri ? 1 : 0));
+  // chains K1 flagged (residual range too wide for 56-bit digits relative to the row maximum): their rows of y in plain FP64
+  fp64_rows_kernel<<<n, 256, (size_t)M.K * 8, st>>>(M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs,
+                                                     (tri ? h->d_U : h->d_P).as<double>(), M.ldk, tri ? 1 : 0,
+                                                     h->d_widecnt.as<int>() + (size_t)c0 * 8, h->d_wide.as<int>() + c0,
+                                                     h->d_y.as<double>() + (size_t)c0 * M.ldy, M.ldy, n);
   return 0;
 }
 
@@ -384,7 +403,8 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   } else if (M.lik == MCD_LIK_FULL && h->oz_S != 0) {
     const int rc = h->oz_S == 6 ? enqueue_i8<6>(h, c0, n, xs, st, ev[1], tri) : enqueue_i8<7>(h, c0, n, xs, st, ev[1], tri);
     if (rc) return rc;
-    h->launches += 2;
+    h->launches += 3;
+    M.wide = h->d_wide.as<int>() + c0;
   } else if (M.lik == MCD_LIK_FULL) {
     residual_kernel<256><<<grid, POST_THREADS, 0, st>>>(M, xs, dx, n);
     if (h->timing) CU_TRY(h, cudaEventRecord(ev[1], st));
@@ -508,12 +528,16 @@ int enqueue_pipelined(mcd_handle* h, int n, const double* d_states, double* d_ou
     cudaEvent_t e1 = h->pipe_ev[2 + 3 * j], e2 = h->pipe_ev[3 + 3 * j], e3 = h->pipe_ev[4 + 3 * j];
     residual_split_kernel<S><<<m, 256, (size_t)h->ld8 * 8, h->pipe_st[0]>>>(
         M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs, h->d_pX.as<signed char>() + (size_t)c0 * h->ld8, h->ld8, stride,
-        h->d_sX.as<double>() + c0, m);
+        h->d_sX.as<double>() + c0, m, h->d_ick.as<double>(), h->d_widecnt.as<int>() + (size_t)c0 * 8);
     CU_TRY(h, cudaEventRecord(e1, h->pipe_st[0]));
     CU_TRY(h, cudaStreamWaitEvent(h->pipe_st[1], e1, 0));
     const int np = (m + OZ_M - 1) / OZ_M * OZ_M;
     CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, h->tmB8, h->d_sX.as<double>(), h->d_sP.as<double>(), h->d_y.as<double>(), h->Mp8, np,
                                       h->ld8, M.ldy, h->cap, h->pipe_st[1], c0, h->n_sms, 0));
+    fp64_rows_kernel<<<m, 256, (size_t)M.K * 8, h->pipe_st[1]>>>(M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs, h->d_P.as<double>(), M.ldk, 0,
+                                                                  h->d_widecnt.as<int>() + (size_t)c0 * 8, h->d_wide.as<int>() + c0,
+                                                                  h->d_y.as<double>() + (size_t)c0 * M.ldy, M.ldy, m);
+    M.wide = h->d_wide.as<int>() + c0;
     CU_TRY(h, cudaEventRecord(e2, h->pipe_st[1]));
     CU_TRY(h, cudaStreamWaitEvent(h->pipe_st[2], e2, 0));
     const double* y = h->d_y.as<double>() + (size_t)c0 * M.ldy;
@@ -533,7 +557,7 @@ int enqueue_pipelined(mcd_handle* h, int n, const double* d_states, double* d_ou
 #undef MCD_LAUNCH_POST_P
     CU_TRY(h, cudaEventRecord(e3, h->pipe_st[2]));
     CU_TRY(h, cudaStreamWaitEvent(user, e3, 0));
-    h->launches += 3;
+    h->launches += 4;
   }
   CU_TRY(h, cudaGetLastError());
   return 0;
@@ -1134,7 +1158,7 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
   delta_split_kernel<SS><<<n, 256, (size_t)(kb_hi - kb_lo) * OZ_KB * 8, st>>>(                                            \
       h->N, h->S, h->dm.root_r, h->dm.parent, h->d_chain.as<double>(), h->d_undo.as<double>(), h->undo_stride,            \
       h->d_meta.as<int4>(), mode, node, size, k_lo, size, kb_lo, kb_hi, h->d_pX.as<signed char>(), h->ld8, stride,        \
-      h->d_sX.as<double>(), n);                                                                                           \
+      h->d_sX.as<double>(), n, h->d_ick.as<double>());                                                                    \
   CU_TRY(h, gemm_i8_ozaki_launch<SS>(h->tmA8, h->tmB8, h->d_sX.as<double>(), h->d_sP.as<double>(), h->d_y.as<double>(),   \
                                      h->Mp8, np, h->ld8, h->dm.ldy, h->cap, st, 0, h->n_sms, 0, kb_lo, kb_hi,             \
                                      h->d_chain_y.as<double>(), h->ldyc))
@@ -1521,6 +1545,24 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
       }
     }
     if (upload(h, h->d_P, P.data(), P.size())) return bail("upload precision");
+    {  // power-of-two equilibration of the INT8 contraction: c_k = 2^round(-log2(P_kk) / 2), so that the digit planes of a
+       // row of P' = C P C are relative to entries of order 1 and those of a chain's residuals to standardised residuals
+       // (a precision matrix D P D with the diagonal D spread over many orders of magnitude splits like P itself)
+      std::vector<double> ck(h->ld8, 1.0), ick(h->ld8, 1.0);
+      bool ok = true;
+      for (int k = 0; k < K; ++k) {
+        const double pkk = P[(size_t)k * h->ldk + k];
+        if (!(pkk > 0.0) || !std::isfinite(pkk)) { ok = false; break; }
+      }
+      if (ok)
+        for (int k = 0; k < K; ++k) {
+          const int e = (int)std::lround(-0.5 * std::log2(P[(size_t)k * h->ldk + k]));
+          const int ec = std::max(-500, std::min(500, e));
+          ck[k] = std::ldexp(1.0, ec);
+          ick[k] = std::ldexp(1.0, -ec);
+        }
+      if (upload(h, h->d_ck, ck.data(), ck.size()) || upload(h, h->d_ick, ick.data(), ick.size())) return bail("upload equilibration");
+    }
     if (d->precision_chol) {
       if (ensure_cholesky(h, d->precision_chol)) return bail("upload Cholesky factor");
     } else {

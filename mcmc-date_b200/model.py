@@ -20,7 +20,7 @@ CLOCK_NAMES = {"ug": 0, "ul": 1, "uw": 2, "al": 3}
 LIK_FULL, LIK_UNIVARIATE, LIK_NONE, LIK_SPARSE = 0, 1, 2, 3
 
 # per-chain status bits returned by the evaluator (include/mcmcdate_b200.h)
-ST_REF_ERROR, ST_ZERO, ST_NAN, ST_NEARCRIT, ST_LEAF_HEIGHT = 1, 2, 4, 8, 16
+ST_REF_ERROR, ST_ZERO, ST_NAN, ST_NEARCRIT, ST_LEAF_HEIGHT, ST_FP64_FALLBACK = 1, 2, 4, 8, 16, 32
 
 # columns of the per-chain output row
 OUT_LNA, OUT_LNB, OUT_LNC, OUT_LNPRIOR, OUT_LNLIK, OUT_LNJAC, OUT_LNPOST = range(7)

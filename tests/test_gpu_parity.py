@@ -9,7 +9,7 @@ import pytest
 
 from mcmc_date_b200 import binding, model, synth
 from oracle import oracle as O
-from util import FIXTURES, TOL, grad_relerr, load_fixture, relerr
+from util import FIXTURES, TOL, grad_relerr, grad_relerr_scalar_block, load_fixture, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -217,7 +217,7 @@ def test_device_entry_points_match_host_entry_points(full_size):
     ev.eval_grad_device(B, d_x.data_ptr(), d_out.data_ptr(), d_grad.data_ptr(), d_st.data_ptr(),
                         torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert ev.kernel_launches() - n0 == 3          # residual, contraction, posterior
+    assert ev.kernel_launches() - n0 == 4          # residual split, contraction, FP64 fall-back (flagged chains only), posterior
     assert np.array_equal(d_out.cpu().numpy(), out[:B]) and np.array_equal(d_grad.cpu().numpy(), grad[:B])
     assert np.array_equal(d_st.cpu().numpy(), st[:B])
 
@@ -322,6 +322,82 @@ def test_contraction_pipes_agree_with_oracle(n_leaves, B):
     # seven planes are of FP64-GEMM quality: within a small factor of the DMMA path's own rounding error
     assert errs["i8s7"][0] < max(50 * errs["dmma"][0], 1e-13) and errs["i8s7"][1] < max(50 * errs["dmma"][1], 1e-13)
     ev.close()
+
+
+def _check_against_oracle(md, X, n_oracle=None, expect_fallback=None):
+    """value / gradient / status parity of the default (INT8) path against the oracle, with the scalar gradient block on its
+    own scale; returns (status words of the CUDA path, worst errors)"""
+    ev = binding.Evaluator(md)
+    assert ev.get_contraction() == 7
+    out, grad, st = ev.eval_grad(X)
+    n = len(X) if n_oracle is None else n_oracle
+    orc = O.Oracle(md)
+    oo, og, ost = orc.eval_grad(X[:n], nthreads=4)
+    assert np.array_equal(st[:n] & ~model.ST_FP64_FALLBACK, ost)
+    ev_val = relerr(out[:n, :7], oo).max()
+    eg = grad_relerr(grad[:n], og).max()
+    es = grad_relerr_scalar_block(grad[:n], og, md.n_nodes).max()
+    assert ev_val < TOL and eg < TOL and es < TOL, (ev_val, eg, es)
+    if expect_fallback is not None:
+        assert np.array_equal((st & model.ST_FP64_FALLBACK) != 0, expect_fallback), np.nonzero((st & model.ST_FP64_FALLBACK) != 0)[0]
+    # the FP64 tensor-instruction contraction on the same inputs: same answer
+    ev.set_contraction("dmma")
+    out2, grad2, st2 = ev.eval_grad(X)
+    assert relerr(out2[:, :7], out[:, :7]).max() < TOL and grad_relerr(grad2, grad).max() < TOL
+    ev.close()
+    return st, (ev_val, eg, es)
+
+
+def test_int8_contraction_with_badly_scaled_precision():
+    """Sigma^-1 = D P D with the diagonal D spread over ten orders of magnitude (branches of very different length and
+    variance): the power-of-two equilibration built at mcd_create makes the digit planes those of P itself"""
+    md, h = synth.synthetic_model(200, seed=41, n_cal=3, n_con=2, n_brace=1)
+    K = md.dim
+    rng = np.random.default_rng(5)
+    dvec = 10.0 ** rng.uniform(-5.0, 5.0, K)
+    P = md.precision * dvec[:, None] * dvec[None, :]
+    P = 0.5 * (P + P.T)
+    md.precision = P
+    md.logdet_sigma = md.logdet_sigma - 2.0 * float(np.sum(np.log(dvec)))
+    X = synth.synthetic_states(md, h, 300, seed=77)
+    _check_against_oracle(md, X, n_oracle=64)
+
+
+def test_int8_contraction_with_the_inverse_of_a_sample_covariance():
+    """what `prepare` really produces (app/Main.hs:214-230): the LU inverse of a sample covariance of correlated branch lengths --
+    ill-conditioned, rows with a wide dynamic range, symmetric only up to rounding"""
+    md, h = synth.synthetic_model(150, seed=43, n_cal=2)
+    K = md.dim
+    rng = np.random.default_rng(9)
+    n_s = 3 * K
+    A = rng.normal(size=(K, 12)) * (0.3 * md.mean[:, None])           # a few strong common factors (rate variation shared by clades)
+    Z = rng.normal(size=(n_s, 12)) @ A.T + rng.normal(size=(n_s, K)) * (0.02 * md.mean[None, :] + 1e-5) + md.mean[None, :]
+    mean = Z.mean(axis=0)
+    cov = np.cov(Z, rowvar=False, ddof=1)
+    sign, logdet = np.linalg.slogdet(cov)
+    assert sign == 1.0
+    prec = np.linalg.inv(cov)                                           # not symmetrised, like invlndet
+    assert np.linalg.cond(cov) > 1e4 and np.abs(prec - prec.T).max() > 0.0
+    md.mean, md.precision, md.logdet_sigma = mean, prec, float(logdet)
+    X = synth.synthetic_states(md, h, 300, seed=78)
+    _check_against_oracle(md, X, n_oracle=64)
+
+
+def test_int8_contraction_falls_back_to_fp64_for_chains_with_outlier_residuals():
+    """digits are relative to a chain's largest (standardised) residual: chains where one residual dwarfs the others by more
+    than 512 x the mean are recomputed in plain FP64 and say so in their status word; results stay within the bar either way"""
+    md, h = synth.synthetic_model(200, seed=47, n_cal=3)
+    N = md.n_nodes
+    B = 260
+    X = synth.synthetic_states(md, h, B, seed=79)
+    X[:, 5 + N + 1:] = 1.0 + 0.01 * (X[:, 5 + N + 1:] - 1.0)          # residuals of ordinary size
+    expect = np.zeros(B, bool)
+    for b, factor in ((3, 1e4), (130, 1e7), (259, 3e3)):                # one branch rate off by orders of magnitude
+        leaf = int(np.nonzero(md.child0 < 0)[0][5 + b % 7])
+        X[b, 5 + N + leaf] *= factor
+        expect[b] = True
+    st, errs = _check_against_oracle(md, X, expect_fallback=expect)
+    assert ((st & model.ST_FP64_FALLBACK) != 0).sum() == 3
 
 
 def test_int8_contraction_is_bit_reproducible_and_tiling_invariant():

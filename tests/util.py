@@ -39,3 +39,18 @@ def grad_relerr(g, ref):
     """gradient error relative to max(1, largest reference component of that chain)"""
     sc = np.maximum(1.0, np.nanmax(np.abs(ref), axis=-1, keepdims=True))
     return np.abs(g - ref) / sc
+
+
+def grad_relerr_scalar_block(g, ref, n_nodes):
+    """the scalar block (lambda, mu, H, m, v) of the gradient on ITS OWN scale: |g - ref| / max(1, largest scalar-block reference
+    component of that chain).  The rate gradients are orders of magnitude larger, so the chain-wide normwise measure of
+    grad_relerr says little about these five entries."""
+    idx = np.array([0, 1, 2, 3 + n_nodes, 4 + n_nodes])
+    gs, rs = np.asarray(g)[..., idx], np.asarray(ref)[..., idx]
+    sc = np.maximum(1.0, np.nanmax(np.abs(rs), axis=-1, keepdims=True))
+    return np.abs(gs - rs) / sc
+
+
+def grad_relerr_componentwise(g, ref, floor):
+    """|g - ref| / max(floor, |ref|) for every component"""
+    return np.abs(np.asarray(g) - np.asarray(ref)) / np.maximum(floor, np.abs(ref))
