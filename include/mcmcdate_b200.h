@@ -50,8 +50,9 @@ enum { MCD_ST_REF_ERROR = 1,    /* the reference would have called `error` (abor
        MCD_ST_NAN = 4,          /* ln posterior is NaN */
        MCD_ST_NEARCRIT = 8,     /* |lambda - mu| < 1e-6 (BirthDeath.hs:125-126) */
        MCD_ST_LEAF_HEIGHT = 16, /* a leaf height != 0: HeightTree invariant violated */
-       MCD_ST_FP64_FALLBACK = 32 /* informational: this chain's residuals span too wide a range for the INT8 digit planes (largest
-                                  * standardised residual > 512 x their mean); its contraction was recomputed in plain FP64 */ };
+       MCD_ST_FP64_FALLBACK = 32 /* informational: this chain's residuals span too wide a range for the INT8 digit planes (at least half
+                                  * of its standardised residuals are more than 512 x below the largest one); its contraction was
+                                  * recomputed in plain FP64 */ };
 /* columns of one output row (MCD_OUT_COLS doubles per chain) */
 enum { MCD_OUT_LNA = 0,     /* calibrations * constraints * braces */
        MCD_OUT_LNB = 1,     /* exponential(lambda) * exponential(mu) * birth-death */
@@ -89,7 +90,9 @@ typedef struct mcd_model_desc {
   int32_t max_batch;         /* capacity hint; buffers grow on demand */
   const double* precision_chol; /* optional (FULL): lower-triangular Cholesky factor L of Sigma^-1 = L L^T,
                                    [K*K] row-major, used by the value-only path (half the flops); NULL: the
-                                   library factorises on the first mcd_eval call */
+                                   library factorises on the GPU at the first value-only call (blocked FP64 Cholesky,
+                                   ~K^3/3 flops: a few milliseconds at K = 2000; one extra K x K work matrix for its
+                                   duration).  A matrix that is not positive definite keeps the symmetric product. */
   int32_t n_sparse;          /* SPARSE: the association list ((i, j), v) of the sparse Sigma^-1 exactly as the */
   const int32_t* sparse_row; /*   reference stores it (SparseS, app/Main.hs:75-81; mkSparse :95-97);        */
   const int32_t* sparse_col; /*   duplicates add up; `precision` is ignored, logdet_sigma = ln det of the   */

@@ -24,6 +24,7 @@
 
 #include "../../include/mcmcdate_b200.h"
 #include "gemm_f64.cuh"
+#include "cholesky.cuh"
 #include "gemm_i8_ozaki.cuh"
 #include "hmc_kernels.cuh"
 #include "mh_kernels.cuh"
@@ -60,7 +61,6 @@ struct mcd_handle {
   DevBuf d_parent, d_child1, d_inner, d_mu, d_var, d_P, d_U;
   DevBuf d_ck, d_ick;             // INT8 contraction: power-of-two equilibration c_k ~ 1 / sqrt(P_kk) and its reciprocal, [ld8]
   DevBuf d_wide, d_widecnt;       // [cap] chains whose residual range is too wide for the digit planes (FP64 fall-back); [cap][8] counts
-  std::vector<double> hostP;      // K x K copy kept for the lazy Cholesky factorisation
   bool sparse = false;            // MCD_LIK_SPARSE on a large tree: CSR contraction instead of the dense one
   DevBuf d_sp_ptr, d_sp_col, d_sp_val;
   int chol_state = 0;             // 0 = not tried, 1 = U = L^T uploaded, -1 = not positive definite
@@ -183,47 +183,45 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
 }
 
 // Value-only path (MH proposals): quad = |L^T dx|^2 with P = L L^T needs only the triangular half of the
-// contraction's flops.  L is taken from the model description when supplied, else factorised here once
-// (row-oriented Cholesky, ~K^3/3 flops on the host).  Not positive definite -> keep the symmetric product.
+// contraction's flops.  L is taken from the model description when supplied, else factorised here once ON THE DEVICE
+// (cholesky.cuh, blocked right-looking, ~K^3/3 flops: milliseconds at K = 2000).  Not positive definite -> keep the symmetric
+// product.
 int ensure_cholesky(mcd_handle* h, const double* L_in) {
   if (h->chol_state != 0) return 0;
-  if (!L_in && h->hostP.empty()) { h->chol_state = -1; return 0; }  // sparse models: no dense factor
+  if (!L_in && (h->sparse || !h->d_P.p || h->dm.lik != MCD_LIK_FULL)) { h->chol_state = -1; return 0; }  // sparse models: no dense factor
   const int K = h->K;
-  std::vector<double> L;
-  if (L_in) {
-    L.assign(L_in, L_in + (size_t)K * K);
-  } else {
-    L.assign((size_t)K * K, 0.0);
-    const double* P = h->hostP.data();
-    for (int i = 0; i < K && h->chol_state == 0; ++i) {
-      double* Li = &L[(size_t)i * K];
-      for (int j = 0; j <= i; ++j) {
-        const double* Lj = &L[(size_t)j * K];
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        int k = 0;
-        for (; k + 4 <= j; k += 4) {
-          s0 += Li[k] * Lj[k]; s1 += Li[k + 1] * Lj[k + 1]; s2 += Li[k + 2] * Lj[k + 2]; s3 += Li[k + 3] * Lj[k + 3];
-        }
-        for (; k < j; ++k) s0 += Li[k] * Lj[k];
-        const double s = P[(size_t)i * K + j] - ((s0 + s1) + (s2 + s3));
-        if (i == j) {
-          if (!(s > 0.0)) { h->chol_state = -1; break; }
-          Li[i] = std::sqrt(s);
-        } else {
-          Li[j] = s / Lj[j];
-        }
-      }
-    }
-    if (h->chol_state == -1) return 0;
+  const size_t nU = (size_t)h->Mp * h->ldk;
+  if (!h->d_U.p) {
+    CU_TRY(h, cudaMalloc(&h->d_U.p, nU * 8));
   }
-  std::vector<double> U((size_t)h->Mp * h->ldk, 0.0);  // U[m][k] = L[k][m], k >= m
-  for (int k = 0; k < K; ++k)
-    for (int m = 0; m <= k; ++m) U[(size_t)m * h->ldk + k] = L[(size_t)k * K + m];
-  if (upload(h, h->d_U, U.data(), U.size())) return -1;
+  CU_TRY(h, cudaMemset(h->d_U.p, 0, nU * 8));
+  if (L_in) {
+    std::vector<double> U(nU, 0.0);  // U[m][k] = L[k][m], k >= m
+    for (int k = 0; k < K; ++k)
+      for (int m = 0; m <= k; ++m) U[(size_t)m * h->ldk + k] = L_in[(size_t)k * K + m];
+    CU_TRY(h, cudaMemcpy(h->d_U.p, U.data(), nU * 8, cudaMemcpyHostToDevice));
+  } else {
+    double* W = nullptr;
+    int* d_flag = nullptr;
+    CU_TRY(h, cudaMalloc(&W, (size_t)K * h->ldk * 8));
+    CU_TRY(h, cudaMalloc(&d_flag, 4));
+    CU_TRY(h, cudaMemset(d_flag, 0, 4));
+    CU_TRY(h, cudaMemcpy(W, h->d_P.p, (size_t)K * h->ldk * 8, cudaMemcpyDeviceToDevice));
+    cudaError_t e = cholesky_device(W, h->ldk, K, d_flag, 0);
+    if (e == cudaSuccess) {
+      chol_transpose_kernel<<<dim3((K + 255) / 256, K), 256>>>(W, h->ldk, K, h->d_U.as<double>(), h->ldk);
+      e = cudaGetLastError();
+    }
+    int flag = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost);
+    cudaFree(W);
+    cudaFree(d_flag);
+    if (e != cudaSuccess) return fail(h, std::string("Cholesky factorisation: ") + cudaGetErrorString(e));
+    h->launches += 3 * ((K + CH_NB - 1) / CH_NB) + 1;
+    if (flag) { h->chol_state = -1; return 0; }   // not positive definite
+  }
   if (make_tile_map(&h->tmU, h->d_U.as<double>(), h->Mp, h->ldk) != 0) return fail(h, "cuTensorMapEncodeTiled failed for the Cholesky factor");
   h->chol_state = 1;
-  h->hostP.clear();
-  h->hostP.shrink_to_fit();
   return 0;
 }
 
@@ -1565,10 +1563,7 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
     }
     if (d->precision_chol) {
       if (ensure_cholesky(h, d->precision_chol)) return bail("upload Cholesky factor");
-    } else {
-      h->hostP.resize((size_t)K * K);
-      for (int i = 0; i < K; ++i) std::copy(&P[(size_t)i * h->ldk], &P[(size_t)i * h->ldk] + K, &h->hostP[(size_t)i * K]);
-    }
+    }  // else: factorised on the device at the first value-only evaluation (ensure_cholesky)
     if (make_tile_map(&h->tmP, h->d_P.as<double>(), h->Mp, h->ldk) != 0) return bail("cuTensorMapEncodeTiled failed for the precision matrix");
     if (gemm_f64_dmma_configure() != cudaSuccess) return bail("cudaFuncSetAttribute(gemm smem) failed");
   }

@@ -128,8 +128,29 @@ def mtcdnapri():
     make("mtcdnapri-7-leaves", md, {"names": names}, init, seed=3)
 
 
+def abi_case():
+    """tests/golden/abi_case_12_leaves.txt: the 12-leaf data set as plain numbers for the C program tests/c_abi/abi_check.c
+    (model arrays, 8 states incl. two edge states, the oracle's outputs / gradient / status for the log-normal clock)"""
+    z = np.load(os.path.join(HERE, "12-leaves-variable-rate.npz"))
+    clock = 1
+    pick = [0, 1, 2, 3, 4, 5, 25, 27]                      # valid states + a non-positive branch + a zero rate
+    X, out, grad, st = z["states"][pick], z[f"out_{clock}"][pick], z[f"grad_{clock}"][pick], z[f"status_{clock}"][pick]
+    fmt = lambda a: " ".join("inf" if v == np.inf else "-inf" if v == -np.inf else "nan" if v != v else repr(float(v)) for v in np.ravel(a))
+    ints = lambda a: " ".join(str(int(v)) for v in np.ravel(a))
+    N = len(z["parent"])
+    with open(os.path.join(HERE, "abi_case_12_leaves.txt"), "w") as f:
+        f.write(f"{N} {clock} {int(z['likelihood'])} {len(z['cal_node'])} {len(z['con_young'])} {len(pick)}\n")
+        for a, kind in ((z["parent"], ints), (z["mean"], fmt), (z["precision"], fmt), ([float(z["logdet_sigma"]), float(z["ht"])], fmt),
+                        (z["cal_node"], ints), (z["cal_lo"], fmt), (z["cal_lo_p"], fmt), (z["cal_hi"], fmt), (z["cal_hi_p"], fmt),
+                        (z["con_young"], ints), (z["con_old"], ints), (z["con_p"], fmt), (X, fmt), (out[:, :7], fmt),
+                        (np.where(np.isfinite(grad), grad, 0.0), fmt), (st, ints)):
+            f.write(kind(a) + "\n")
+    print("abi_case_12_leaves.txt", X.shape, st.tolist())
+
+
 if __name__ == "__main__":
     dataset("06-leaves-constant-rate", "06-leaves-constant-rate", seed=0)
     dataset("12-leaves-variable-rate", "12-leaves-variable-rate", con=True, seed=1)
     dataset("24-leaves-braces", "24-leaves-braces", con=True, br=True, seed=2)
     mtcdnapri()
+    abi_case()

@@ -40,6 +40,7 @@ def test_fixture_parity_value_gradient_status(name, clock):
     assert np.array_equal(st, ost)
     assert relerr(out[:, :7], oo).max() < TOL
     assert grad_relerr(grad[fin], og[fin]).max() < TOL
+    assert grad_relerr_scalar_block(grad[fin], og[fin], md.n_nodes).max() < TOL    # (lambda, mu, H, m, v) on their own scale
     # masked entries are exactly zero
     assert (grad[:, orc.mask == 0] == 0).all()
     # value-only entry point returns the same numbers
@@ -125,6 +126,7 @@ def test_thousand_leaf_tree_against_oracle():
     assert np.array_equal(st, ost) and (st == 0).all()
     assert relerr(out[:, :7], oo).max() < TOL
     assert grad_relerr(grad, og).max() < TOL
+    assert grad_relerr_scalar_block(grad, og, md.n_nodes).max() < TOL             # (lambda, mu, H, m, v) on their own scale
     # gradient truth at this size: one dual-number pass along a random direction
     u = np.random.default_rng(5).normal(size=md.state_len) * orc.mask
     dd, _ = orc.dir_derivative(X[0], u)
