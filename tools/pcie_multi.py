@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Host <-> device copy bandwidth of N concurrent processes, one per GPU (the traffic pattern of bench.py's host-buffer `e2e`
-leg at N GPUs): every rank copies pinned host memory to its GPU and back at the same time as all the others.  With --numa
+leg at N GPUs): every rank copies pinned host memory to its GPU and back at the same time as all the others.  With PCIE_NUMA=1 in the environment
 each rank first pins itself to the CPUs of its GPU's NUMA node (bench.bind_to_gpu_numa_node), so that the pinned buffers are
 allocated there.  Rank 0 prints one JSON line: per-rank and aggregate GB/s for H2D alone, D2H alone and both together.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/pcie_multi.py [--numa]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/pcie_multi.py
 """
 import json
 import os
@@ -22,7 +22,7 @@ def main():
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    placement = bench.bind_to_gpu_numa_node(local) if "--numa" in sys.argv else {"bound": False}
+    placement = bench.bind_to_gpu_numa_node(local) if bool(os.environ.get("PCIE_NUMA")) else {"bound": False}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -72,7 +72,7 @@ def main():
         allr = [res]
     if rank == 0:
         t = torch.stack(allr).cpu()
-        print(json.dumps({"n_processes": world, "numa_pinned": "--numa" in sys.argv, "rank0_placement": placement,
+        print(json.dumps({"n_processes": world, "numa_pinned": bool(os.environ.get("PCIE_NUMA")), "rank0_placement": placement,
                           "per_rank_GBps": {"h2d_alone": t[:, 0].tolist(), "d2h_alone": t[:, 1].tolist(), "both_each_direction": t[:, 2].tolist()},
                           "aggregate_GBps": {"h2d_alone": float(t[:, 0].sum()), "d2h_alone": float(t[:, 1].sum()),
                                              "both_each_direction": float(t[:, 2].sum()), "both_total": 2 * float(t[:, 2].sum())}}))
