@@ -1635,7 +1635,7 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
                                  : POST_SMEM_FIXED + (size_t)h->S * 8;
     if (post_smem > 220 * 1024)
       return bail("mcd_create: tree too large for the posterior kernel's shared-memory staging (more than ~14000 nodes)");
-    const int lim = 225 * 1024;
+    const int lim = 220 * 1024;   // dynamic part; the kernels also hold ~2 KB of static shared memory (227 KB per CTA in total)
 #define MCD_SET_SMEM(CC)                                                                                               \
   cudaFuncSetAttribute(posterior_kernel<256, CC, true, POST_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
   cudaFuncSetAttribute(posterior_kernel<256, CC, false, POST_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);

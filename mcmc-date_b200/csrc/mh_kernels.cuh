@@ -1081,7 +1081,7 @@ mh_small_tree_kernel(DevModel M, const MhTopo T, const MhParams P, const double*
   const int n_undo = 2 * N + 8;
   unsigned char* mh_base = reinterpret_cast<unsigned char*>(stage + (size_t)(POST_THREADS / 32) * (S + N + K));
   const size_t mh_per_warp = sizeof(MhOp) * MH_MAX_OPS + (size_t)n_undo * 16;
-  const Topo Tp{M.parent, M.mu, M.var, M.inner};
+  const Topo Tp{M.parent, M.mu, M.var, M.inner, nullptr};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (M.lik == 0) {
     for (int e = threadIdx.x; e < K * K; e += POST_THREADS) sP[e] = Pm[(size_t)(e / K) * M.ldk + (e % K)];
