@@ -444,8 +444,9 @@ residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ 
   for (int q4 = tid; q4 < ld8 / 4; q4 += 256) {
     const double2 x01 = *reinterpret_cast<const double2*>(sdx + 4 * q4);
     const double2 x23 = *reinterpret_cast<const double2*>(sdx + 4 * q4 + 2);
-    n_small += (int)(fabs(x01.x) < small_below && 4 * q4 < K) + (int)(fabs(x01.y) < small_below && 4 * q4 + 1 < K) +
-               (int)(fabs(x23.x) < small_below && 4 * q4 + 2 < K) + (int)(fabs(x23.y) < small_below && 4 * q4 + 3 < K);
+    // (the zero padding beyond K counts as small here; fp64_rows_kernel subtracts it)
+    n_small += (int)(fabs(x01.x) < small_below) + (int)(fabs(x01.y) < small_below) + (int)(fabs(x23.x) < small_below) +
+               (int)(fabs(x23.y) < small_below);
     const unsigned long long j0 = oz_digit_bytes<S>(finite ? x01.x : 0.0, mult), j1 = oz_digit_bytes<S>(finite ? x01.y : 0.0, mult),
                              j2 = oz_digit_bytes<S>(finite ? x23.x : 0.0, mult), j3 = oz_digit_bytes<S>(finite ? x23.y : 0.0, mult);
 #pragma unroll
@@ -559,14 +560,15 @@ delta_split_kernel(int N, int SL, int root_r, const int* __restrict__ parent, co
 __global__ void __launch_bounds__(256)
 fp64_rows_kernel(int N, int K, int SL, int root_r, const int* __restrict__ parent, const double* __restrict__ mu,
                  const double* __restrict__ states, const double* __restrict__ Mx, int ldm, int upper_tri,
-                 const int* __restrict__ widecnt, int* __restrict__ wide, double* __restrict__ Y, int ldy, int B) {
+                 const int* __restrict__ widecnt, int n_pad, int* __restrict__ wide, double* __restrict__ Y, int ldy, int B) {
   extern __shared__ __align__(16) unsigned char smem_fb[];
   double* sdx = reinterpret_cast<double*>(smem_fb);  // [K]
   const int chain = blockIdx.x;
   if (chain >= B) return;
   const int tid = threadIdx.x;
   const int4 c0 = *reinterpret_cast<const int4*>(widecnt + chain * 8), c1 = *reinterpret_cast<const int4*>(widecnt + chain * 8 + 4);
-  const bool flagged = 2 * (c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w) >= K;
+  const int n_small = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;   // includes the n_pad zero entries beyond K, if any counted
+  const bool flagged = n_small > 0 && 2 * (n_small - n_pad) >= K;
   if (tid == 0) wide[chain] = flagged ? 1 : 0;
   if (!flagged) return;
   const double* x = states + (size_t)chain * SL;

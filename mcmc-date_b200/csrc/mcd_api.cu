@@ -313,7 +313,7 @@ int enqueue_i8(mcd_handle* h, int c0, int n, const double* xs, cudaStream_t st, 
   // chains K1 flagged (residual range too wide for 56-bit digits relative to the row maximum): their rows of y in plain FP64
   fp64_rows_kernel<<<n, 256, (size_t)M.K * 8, st>>>(M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs,
                                                      (tri ? h->d_U : h->d_P).as<double>(), M.ldk, tri ? 1 : 0,
-                                                     h->d_widecnt.as<int>() + (size_t)c0 * 8, h->d_wide.as<int>() + c0,
+                                                     h->d_widecnt.as<int>() + (size_t)c0 * 8, h->ld8 - M.K, h->d_wide.as<int>() + c0,
                                                      h->d_y.as<double>() + (size_t)c0 * M.ldy, M.ldy, n);
   return 0;
 }
@@ -533,7 +533,7 @@ int enqueue_pipelined(mcd_handle* h, int n, const double* d_states, double* d_ou
     CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, h->tmB8, h->d_sX.as<double>(), h->d_sP.as<double>(), h->d_y.as<double>(), h->Mp8, np,
                                       h->ld8, M.ldy, h->cap, h->pipe_st[1], c0, h->n_sms, 0));
     fp64_rows_kernel<<<m, 256, (size_t)M.K * 8, h->pipe_st[1]>>>(M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs, h->d_P.as<double>(), M.ldk, 0,
-                                                                  h->d_widecnt.as<int>() + (size_t)c0 * 8, h->d_wide.as<int>() + c0,
+                                                                  h->d_widecnt.as<int>() + (size_t)c0 * 8, h->ld8 - M.K, h->d_wide.as<int>() + c0,
                                                                   h->d_y.as<double>() + (size_t)c0 * M.ldy, M.ldy, m);
     M.wide = h->d_wide.as<int>() + c0;
     CU_TRY(h, cudaEventRecord(e2, h->pipe_st[1]));
