@@ -22,6 +22,10 @@
 #include <string>
 #include <vector>
 
+#ifndef MCD_NO_NVTX
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler is attached
+#endif
+
 #include "../../include/mcmcdate_b200.h"
 #include "gemm_f64.cuh"
 #include "cholesky.cuh"
@@ -41,6 +45,16 @@ constexpr int SMALL_TREE_MAX_NODES = 96;  // warp-per-chain kernels up to this m
 #ifndef POST_MINB
 #define POST_MINB 4
 #endif
+
+// NVTX range over one entry point (tracing): shows up as "mcd:<name>" in nsys / ncu --nvtx timelines
+struct NvtxRange {
+#ifndef MCD_NO_NVTX
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+#else
+  explicit NvtxRange(const char*) {}
+#endif
+};
 
 struct DevBuf {
   void* p = nullptr;
@@ -566,6 +580,7 @@ int eval_device(mcd_handle* h, int n, const double* d_states, double* d_out, dou
                 void* stream) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:eval_device");
   if (n <= 0) return 0;
   if (!d_states || !d_out || !d_status || (GRAD && !d_grad)) return fail(h, "null device buffer");
   CU_TRY(h, cudaSetDevice(h->device));
@@ -601,6 +616,7 @@ int eval_host(mcd_handle* h, int n, const double* states, double* out, double* g
               int64_t* ticket_out = nullptr) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:eval_host");
   if (n <= 0) return async ? record_ticket(h, ticket_out) : 0;
   if (!states || !out || !status || (GRAD && !grad)) return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
@@ -636,6 +652,7 @@ int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* bas
                     int32_t* status, bool async = false, int64_t* ticket_out = nullptr) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:eval_theta_host");
   if (n <= 0) return async ? record_ticket(h, ticket_out) : 0;
   if (!theta || !base || !out || !gtheta || !status) return fail(h, "null host buffer");
   CU_TRY(h, cudaSetDevice(h->device));
@@ -680,6 +697,7 @@ int eval_theta_host(mcd_handle* h, int n, const double* theta, const double* bas
 int wait_ticket(mcd_handle* h, int64_t ticket) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:wait_ticket");
   if (ticket < 0 || ticket >= h->next_ticket) return fail(h, "mcd_wait: unknown ticket");
   CU_TRY(h, cudaSetDevice(h->device));
   // a ticket older than the ring of 8: its slot now holds the events of a LATER call, recorded on the same in-order streams, so
@@ -695,6 +713,7 @@ int leapfrog_host(mcd_handle* h, int n, int L, const double* theta0, const doubl
                   double* energy, int32_t* status) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:leapfrog_host");
   if (n <= 0) return 0;
   if (L < 1) return fail(h, "mcd_leapfrog: n_steps must be >= 1");
   if (!theta0 || !mom0 || !base || !inv_mass || !eps || !theta_out || !mom_out || !out || !energy || !status)
@@ -774,6 +793,7 @@ int nuts_host(mcd_handle* h, int n, const double* theta0, const double* base, co
               double* accept_stat, int32_t* info, int32_t* status, bool resident = false) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:nuts_host");
   if (resident) n = h->n_resident;
   if (n <= 0) return resident ? fail(h, "mcd_chains_nuts: no resident chains (call mcd_chains_set first)") : 0;
   if (max_depth < 1 || max_depth > 16) return fail(h, "mcd_nuts: max_depth must be in 1..16");
@@ -949,6 +969,7 @@ bool mh_kind_incremental(const mcd_handle* h, int kind, int node) {
 int chains_set(mcd_handle* h, int n, const double* states) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:chains_set");
   if (n <= 0 || !states) return fail(h, "mcd_chains_set: need n > 0 and a state buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
@@ -1027,6 +1048,7 @@ int chains_set(mcd_handle* h, int n, const double* states) {
 int chains_get(mcd_handle* h, int n, double* states, double* out, int32_t* status) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:chains_get");
   if (n <= 0 || n > h->n_resident) return fail(h, "mcd_chains_get: more chains requested than are resident");
   CU_TRY(h, cudaSetDevice(h->device));
   SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
@@ -1244,6 +1266,7 @@ int mh_step(mcd_handle* h, int kind, int node, double param, double tune, int us
             int32_t* accepted) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mh_step");
   const int n = h->n_resident;
   if (n <= 0) return fail(h, "mcd_mh_step: no resident chains (call mcd_chains_set first)");
   if (mh_check(h, kind, node, param, tune)) return -1;
@@ -1265,6 +1288,7 @@ int mh_cycle(mcd_handle* h, int n_props, const mcd_mh_proposal* props, int n_ite
              uint64_t* accepted, uint64_t* invalid, uint32_t* iteration_next) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mh_cycle");
   const int n = h->n_resident;
   if (n <= 0) return fail(h, "mcd_mh_cycle: no resident chains (call mcd_chains_set first)");
   if (n_props <= 0 || n_props > MH_MAX_CYCLE || !props || n_iterations < 0) return fail(h, "mcd_mh_cycle: bad proposal list");
@@ -1298,6 +1322,7 @@ int mh_cycle(mcd_handle* h, int n_props, const mcd_mh_proposal* props, int n_ite
 int mc3_configure(mcd_handle* h, int n_global, int chain_offset, int C, const double* ladder_prior, const double* ladder_lik) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mc3_configure");
   CU_TRY(h, cudaSetDevice(h->device));
   SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
   if (order.rc) return -1;
@@ -1325,6 +1350,7 @@ int mc3_configure(mcd_handle* h, int n_global, int chain_offset, int C, const do
 int mc3_swap(mcd_handle* h, int pair, uint64_t seed, uint32_t iteration, const double* d_stats_global, int32_t* accepted) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mc3_swap");
   if (h->mc3_C < 2) return fail(h, "mcd_mc3_swap: configure at least two temperatures first (mcd_mc3_configure)");
   if (pair >= h->mc3_C - 1) return fail(h, "mcd_mc3_swap: pair index out of range");
   if (!d_stats_global && (h->mc3_offset != 0 || h->mc3_n_global != h->n_resident))
@@ -1349,6 +1375,7 @@ int mc3_swap(mcd_handle* h, int pair, uint64_t seed, uint32_t iteration, const d
 int mc3_slots(mcd_handle* h, int32_t* slots) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mc3_slots");
   if (h->mc3_C <= 0 || !slots) return fail(h, "mcd_mc3_slots: no temperature ladder configured");
   CU_TRY(h, cudaSetDevice(h->device));
   SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
@@ -1769,6 +1796,7 @@ void* mcd_chains_out_device(mcd_handle* h) { return h ? h->d_chain_out.p : nullp
 int mcd_mh_set_incremental(mcd_handle* h, int32_t on, int32_t refresh_every) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mcd_mh_set_incremental");
   if (refresh_every < 0) return fail(h, "mcd_mh_set_incremental: refresh_every must be >= 0 (0 keeps the current value)");
   if (on && !h->inc_enabled && h->n_resident > 0)
     return fail(h, "mcd_mh_set_incremental: switch the mode on before mcd_chains_set (the cached contraction results are built there)");
@@ -1780,6 +1808,7 @@ int mcd_mh_get_incremental(const mcd_handle* h) { return h ? (h->inc_enabled && 
 int mcd_chains_stats_device(mcd_handle* h, double* d_stats) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mcd_chains_stats_device");
   if (h->n_resident <= 0 || !d_stats) return fail(h, "mcd_chains_stats_device: no resident chains or null buffer");
   CU_TRY(h, cudaSetDevice(h->device));
   SerialScope order(h, h->streams[0]);  // after whatever the pipelined calls / other streams have in flight
@@ -1803,6 +1832,7 @@ int mcd_eval_grad_device(mcd_handle* h, int32_t n, const double* d_states, doubl
 int mcd_set_contraction(mcd_handle* h, int32_t mode) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mcd_set_contraction");
   if (mode != MCD_CONTRACT_DMMA && mode != MCD_CONTRACT_I8_S6 && mode != MCD_CONTRACT_I8_S7)
     return fail(h, "mcd_set_contraction: unknown mode");
   CU_TRY(h, cudaSetDevice(h->device));
@@ -1815,6 +1845,7 @@ int64_t mcd_kernel_launches(const mcd_handle* h) { return h ? h->launches : -1; 
 int mcd_set_kernel_timing(mcd_handle* h, int on) {
   if (!h) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mcd_set_kernel_timing");
   h->timing = on != 0;
   return 0;
 }
@@ -1823,6 +1854,7 @@ int mcd_set_kernel_timing(mcd_handle* h, int on) {
 int mcd_kernel_times(mcd_handle* h, double* ms, int64_t* n_calls) {
   if (!h || !ms || !n_calls) return -1;
   std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:mcd_kernel_times");
   CU_TRY(h, cudaSetDevice(h->device));
   CU_TRY(h, cudaDeviceSynchronize());
   ms[0] = ms[1] = ms[2] = 0.0;
