@@ -599,3 +599,31 @@ def test_auto_tuner_and_cycle_order():
     tuned = mh_cycle.auto_tune(md, cyc, acc, np.array([float(e[5]) for e in cyc]))
     assert all(t[3] > c[3] for t, c in zip(tuned, cyc))                   # rates above every target: larger steps
     assert tuned[0][3] == pytest.approx(np.exp(2 * (0.9 - 0.44)))
+
+
+def test_prepare_on_every_reference_data_set_with_its_rooted_tree():
+    """all six analysis.conf files of the reference's tests/: the tree list re-rooted at the outgroup of the configured rooted tree
+    passes the topology checks and gives what the un-rooted call gives (the lists are already rooted there); the MCMCtree-labelled
+    calibration tree of 06-leaves-constant-rate (the reference's own use of `calibrations="data/calibrations.tree"`) loads to the
+    same table as its CSV twin"""
+    base = "/root/reference/tests"
+    if not os.path.isdir(base):
+        pytest.skip("reference checkout not present (GPU box)")
+    seen = 0
+    for d in sorted(os.listdir(base)):
+        conf = open(os.path.join(base, d, "analysis.conf")).read()
+        get = lambda k: re.search(rf'^{k}="([^"]+)"', conf, re.M).group(1)
+        rooted = open(os.path.join(base, d, get("rooted_tree"))).read()
+        tl = open(os.path.join(base, d, get("trees"))).read()
+        a = prepare.prepare_from_treelist(tl, rooted_tree_text=rooted)
+        b = prepare.prepare_from_treelist(tl)
+        assert np.array_equal(a["parent"], b["parent"]) and np.array_equal(a["mean"], b["mean"]) and a["names"] == b["names"]
+        seen += 1
+    assert seen == 6
+    d = os.path.join(base, "06-leaves-constant-rate", "data")
+    pr = prepare.prepare_from_treelist(open(os.path.join(d, "test.treelist")).read(), rooted_tree_text=open(os.path.join(d, "time.tree")).read())
+    c_csv = prepare.load_calibrations(open(os.path.join(d, "calibrations.csv")).read(), pr["parent"], pr["names"])
+    c_tree = prepare.load_calibrations_from_tree(open(os.path.join(d, "calibrations.tree")).read(), pr["parent"], pr["names"])
+    for k in ("node", "lo", "lo_p", "hi", "hi_p"):
+        assert np.array_equal(c_csv[k], c_tree[k]), k
+    assert c_tree["names"] == ["a-f"] and prepare.mean_root_height(c_tree) == 1.0
