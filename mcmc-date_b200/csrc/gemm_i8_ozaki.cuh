@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gemm_f64.cuh"  // mbarrier / TMA wrappers, get_encode_tiled
 
@@ -61,7 +62,7 @@ constexpr double OZ_WIDE_RATIO = MCD_OZ_WIDE_RATIO;
 template <int S>
 __host__ __device__ constexpr int oz_stage_bytes() { return S * (OZ_M + OZ_N) * OZ_KB; }
 template <int S>
-__host__ __device__ constexpr size_t oz_smem_bytes() { return (size_t)OZ_STAGES * oz_stage_bytes<S>() + 1024 /*align*/ + 256 /*barriers*/; }
+__host__ __device__ constexpr size_t oz_smem_bytes() { return (size_t)OZ_STAGES * oz_stage_bytes<S>() + 1024 /*align*/ + 512 /*barriers*/; }
 
 // ------------------------------------------------------------------------------ tcgen05 wrappers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -284,16 +285,28 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const double* arow = yadd ? yadd + (size_t)b * ldyadd + pr0 : nullptr;
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
+      // two chunks of 16 columns per warp.  The accumulators are handed back to the MMA warp as soon as this warp's LAST
+      // tcgen05.ld has completed -- before the Horner evaluation and the stores of that chunk, which only touch registers:
+      // the next tile's first MMAs overlap them
 #ifdef MCD_OZ_NO_EPI
-      for (int c = 0; c < (int)(sa == 12345.678); ++c) {
+      const int n_chunks = (int)(sa == 12345.678);
 #else
-#pragma unroll 1
-      for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
+      const int n_chunks = 2;
 #endif
+#pragma unroll 1
+      for (int cc = 0; cc < n_chunks; ++cc) {
+        const int c = 2 * chalf + cc;
         uint32_t v[S][16];
 #pragma unroll
         for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
         tmem_ld_wait();
+#ifndef MCD_OZ_LATE_HANDBACK
+        if (cc == n_chunks - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
           double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
@@ -312,10 +325,200 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           *reinterpret_cast<double2*>(yrow + c * 16 + j) = o;
         }
       }
-      // this warp's TMEM reads are complete (tcgen05.wait::ld above): hand the accumulators back
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
+#ifdef MCD_OZ_LATE_HANDBACK
+      if (n_chunks > 0) {  // (A/B build: hand back after the whole epilogue, as in round 1)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+#endif
+      if (n_chunks == 0) {  // (experiment build without an epilogue)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, OZ_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------ the contraction, plane-granular pipeline
+// Same tiles, same MMAs, same epilogue as gemm_i8_ozaki_kernel -- bit-identical results (integer accumulation) -- but the
+// shared-memory ring is recycled PLANE BY PLANE instead of stage by stage.  ncu on the stage-granular kernel: tensor pipe 78 %
+// busy, every SM ingesting 38 B/clk of digit planes from L2; with two stages of one 84 KB k-block each, the refill of a stage
+// could only start when ALL 56 MMAs of its k-block had retired and had to land within the 56 MMAs of the next one.  Here the
+// MMAs of a k-block run with the chains' plane index a DESCENDING (a = S-1 needs only P's plane 0, a = S-2 planes 0..1, ...):
+//   * plane a of the chains is released right after its 2 (S - a) MMAs (after 2, 6, 12, 20, 30, 42 of the 56 MMAs for a = 6..1),
+//     so its refill for k-block g + 2 starts up to two k-blocks before it is needed;
+//   * a k-block starts as soon as chains' plane S-1 and P's plane 0 (12 KB) have landed; the other planes may still be in flight.
+// Barriers per stage: one "full" per plane (2 S), "empty" per chains' plane a >= 1 (S - 1) and one for chains' plane 0 + all of
+// P's planes (released by the last MMAs of the k-block).
+template <int S>
+#if MCD_OZ_MAXNREG > 0
+__global__ void __maxnreg__(MCD_OZ_MAXNREG)
+#else
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+#endif
+gemm_i8_ozaki_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ Y,
+                        int nkb, int ldy, int Bp, int Mp, int bt_base, int n_pr, int n_tiles, int upper_tri, int kb_lo,
+                        const double* __restrict__ yadd, int ldyadd) {
+  static_assert(S >= 2 && S <= OZ_MAX_SLICES && S * OZ_N <= OZ_TMEM_COLS, "digit planes must fit TMEM");
+  static_assert(OZ_STAGES * (3 * S) + 2 <= 62, "barrier block is 512 bytes");
+  constexpr int STAGE = oz_stage_bytes<S>();
+  constexpr int A_PLANE = OZ_M * OZ_KB, B_PLANE = OZ_N * OZ_KB;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_A = reinterpret_cast<uint64_t*>(smem + (size_t)OZ_STAGES * STAGE);  // [stage][a]
+  uint64_t* full_B = full_A + OZ_STAGES * S;                                         // [stage][b]
+  uint64_t* empty_A = full_B + OZ_STAGES * S;   // [stage][a]; entry a = 0 stands for chains' plane 0 AND all planes of P
+  uint64_t* acc_full = empty_A + OZ_STAGES * S;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      for (int i = 0; i < OZ_STAGES * S; ++i) {
+        mbar_init(&full_A[i], 1);
+        mbar_init(&full_B[i], 1);
+        mbar_init(&empty_A[i], 1);
+      }
+      mbar_init(acc_full, 1);
+      mbar_init(acc_empty, OZ_EPI_WARPS);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, OZ_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected lane does everything)
+    if (elect_one()) {
+      int g = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int pr0 = (t % n_pr) * OZ_N, bt0 = bt_base + (t / n_pr) * OZ_M;
+        for (int kb = upper_tri ? pr0 / OZ_KB : kb_lo; kb < nkb; ++kb, ++g) {
+          const int st = g % OZ_STAGES;
+          const uint32_t prev = (uint32_t)((g / OZ_STAGES) - 1) & 1u;
+          unsigned char* dst = smem + (size_t)st * STAGE;
+          // chains' planes S-1 .. 1 in the order the MMA warp releases (and needs) them
+#pragma unroll
+          for (int a = S - 1; a >= 1; --a) {
+            if (g >= OZ_STAGES) mbar_wait(&empty_A[st * S + a], prev);
+            mbar_arrive_expect_tx(&full_A[st * S + a], A_PLANE);
+            tma_load_2d(dst + a * A_PLANE, &tmA, kb * OZ_KB, a * Bp + bt0, &full_A[st * S + a]);
+          }
+          // P's planes (needed from the start of the k-block on, plane 0 first) and chains' plane 0 (needed last)
+          if (g >= OZ_STAGES) mbar_wait(&empty_A[st * S + 0], prev);
+#pragma unroll
+          for (int b = 0; b < S; ++b) {
+            mbar_arrive_expect_tx(&full_B[st * S + b], B_PLANE);
+            tma_load_2d(dst + S * A_PLANE + b * B_PLANE, &tmB, kb * OZ_KB, b * Mp + pr0, &full_B[st * S + b]);
+          }
+          mbar_arrive_expect_tx(&full_A[st * S + 0], A_PLANE);
+          tma_load_2d(dst, &tmA, kb * OZ_KB, bt0, &full_A[st * S + 0]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane)
+    if (elect_one()) {
+      int g = 0, it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        if (it > 0) {  // the epilogue warps must have read the previous tile out of TMEM
+          mbar_wait(acc_empty, (it - 1) & 1);
+          tc_fence_after();
+        }
+        const int kb0 = upper_tri ? ((t % n_pr) * OZ_N) / OZ_KB : kb_lo;
+        for (int kb = kb0; kb < nkb; ++kb, ++g) {
+          const int st = g % OZ_STAGES;
+          const uint32_t par = (uint32_t)(g / OZ_STAGES) & 1u;
+          const uint64_t dbase = oz_smem_desc(smem_u32(smem + (size_t)st * STAGE));
+#pragma unroll
+          for (int a = S - 1; a >= 0; --a) {
+            mbar_wait(&full_A[st * S + a], par);
+            mbar_wait(&full_B[st * S + (S - 1 - a)], par);   // the plane of P this a needs for the first time
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < OZ_KB / OZ_UK; ++ks) {
+              const uint64_t da = dbase + (uint64_t)((a * A_PLANE + ks * OZ_UK) >> 4);
+#pragma unroll
+              for (int b = 0; b + a < S; ++b) {
+                const uint64_t db = dbase + (uint64_t)((S * A_PLANE + b * B_PLANE + ks * OZ_UK) >> 4);
+                // the first product into accumulator d = a + b is (a = d, b = 0) of the tile's first k-step
+                const uint32_t acc = ((kb - kb0) | ks | b) != 0 ? 1u : 0u;
+                const uint32_t td = tmem_base + (uint32_t)((a + b) * OZ_N);
+                if (S - a == 1) umma_i8<OZ_A_DISCARD>(td, da, db, OZ_IDESC, acc);
+                else if (b == 0) umma_i8<OZ_A_FILL>(td, da, db, OZ_IDESC, acc);
+                else if (b + a == S - 1) umma_i8<OZ_A_LASTUSE>(td, da, db, OZ_IDESC, acc);
+                else umma_i8<OZ_A_USE>(td, da, db, OZ_IDESC, acc);
+              }
+            }
+            umma_commit(&empty_A[st * S + a]);   // plane a of the chains (a = 0: and all of P's planes) may be refilled
+          }
+          if (kb == nkb - 1) umma_commit(acc_full);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (as in gemm_i8_ozaki_kernel)
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int chalf = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int pr0 = (t % n_pr) * OZ_N, bt0 = bt_base + (t / n_pr) * OZ_M;
+      const int b = bt0 + row;
+      const double sa = scaleA[b];
+      double* yrow = Y + (size_t)b * ldy + pr0;
+      const double* arow = yadd ? yadd + (size_t)b * ldyadd + pr0 : nullptr;
+      mbar_wait(acc_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * chalf + cc;
+        uint32_t v[S][16];
+#pragma unroll
+        for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
+        tmem_ld_wait();
+        if (cc == 1) {  // last TMEM read of this warp: hand the accumulators back before the arithmetic of this chunk
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
+#pragma unroll
+          for (int d = S - 2; d >= 0; --d) {
+            r0 = fma(r0, 0.00390625, oz_i2d(v[d][j]));
+            r1 = fma(r1, 0.00390625, oz_i2d(v[d][j + 1]));
+          }
+          const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
+          double2 o = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
+          if (arow) {
+            const double2 ya = *reinterpret_cast<const double2*>(arow + c * 16 + j);
+            o.x += ya.x;
+            o.y += ya.y;
+          }
+          *reinterpret_cast<double2*>(yrow + c * 16 + j) = o;
+        }
+      }
     }
   }
   tc_fence_before();
@@ -617,9 +820,16 @@ inline int oz_make_plane_map(CUtensorMap* tm, const signed char* base, size_t to
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// MCD_OZ_V1 in the environment: the stage-granular pipeline of round 1 (A/B timing; results are bit-identical)
+inline bool oz_use_v1() {
+  static const bool v1 = getenv("MCD_OZ_V1") != nullptr;
+  return v1;
+}
 template <int S>
 inline cudaError_t gemm_i8_ozaki_configure() {
-  return cudaFuncSetAttribute(gemm_i8_ozaki_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes<S>());
+  cudaError_t e = cudaFuncSetAttribute(gemm_i8_ozaki_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes<S>());
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_i8_ozaki_v2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes<S>());
 }
 
 // n_chains_padded chains (multiple of 128) starting at bt_base, Mp P rows (multiple of 64), ld8 = padded K
@@ -632,8 +842,12 @@ inline cudaError_t gemm_i8_ozaki_launch(const CUtensorMap& tmA, const CUtensorMa
   const int n_pr = Mp / OZ_N, n_tiles = n_pr * (n_chains_padded / OZ_M);
   const int grid = n_tiles < n_sms ? n_tiles : n_sms;
   const int nkb = kb_hi > 0 ? kb_hi : ld8 / OZ_KB;  // [kb_lo, kb_hi): non-empty by the caller's contract
-  gemm_i8_ozaki_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), st>>>(tmA, tmB, scaleA, scaleB, Y, nkb, ldy, Bp_total, Mp,
-                                                                         bt_base, n_pr, n_tiles, upper_tri, kb_lo, yadd, ldyadd);
+  if (oz_use_v1())
+    gemm_i8_ozaki_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), st>>>(tmA, tmB, scaleA, scaleB, Y, nkb, ldy, Bp_total, Mp,
+                                                                           bt_base, n_pr, n_tiles, upper_tri, kb_lo, yadd, ldyadd);
+  else
+    gemm_i8_ozaki_v2_kernel<S><<<grid, OZ_THREADS, oz_smem_bytes<S>(), st>>>(tmA, tmB, scaleA, scaleB, Y, nkb, ldy, Bp_total, Mp,
+                                                                              bt_base, n_pr, n_tiles, upper_tri, kb_lo, yadd, ldyadd);
   return cudaGetLastError();
 }
 
