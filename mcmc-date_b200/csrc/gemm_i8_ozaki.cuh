@@ -526,6 +526,229 @@ gemm_i8_ozaki_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 1) tmem_dealloc(tmem_base, OZ_TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------ the contraction on CTA pairs (cta_group::2)
+// ncu on the one-CTA kernels: every tcgen05.mma M128 N64 K32 reads its whole B operand (2 KB) from shared memory, A once per
+// S - a products (collector): 94 B/clk of operand reads + 47 B/clk of TMA fill against a 128 B/clk shared-memory pipe -- the
+// tensor pipe tops out below 80 %.  Two SMs of a TPC as ONE tile of 256 chains x 64 P rows (UMMA M = 256): each CTA holds its own
+// 128 chains' planes and HALF of P's rows (32), the pair's tensor cores read both halves, so the per-CTA operand traffic of B and
+// its TMA fill halve (stage 70 KB instead of 84 KB: three stages fit).  CTA rank 0 issues the MMAs for the pair; both CTAs run a
+// TMA producer (its completion bytes go to rank 0's "full" barrier) and the epilogue of their own 128 chains; tcgen05.commit is
+// multicast to both CTAs' "empty" / "accumulators full" barriers; epilogue warps of both CTAs arrive on rank 0's "accumulators
+// empty" barrier.  Same integer products as the one-CTA kernels: bit-identical results.
+constexpr int OZ2_STAGES = 3;
+constexpr int OZ2_NH = OZ_N / 2;   // P rows held by each CTA of the pair
+template <int S>
+__host__ __device__ constexpr int oz2_stage_bytes() { return S * (OZ_M + OZ2_NH) * OZ_KB; }
+template <int S>
+__host__ __device__ constexpr size_t oz2_smem_bytes() { return (size_t)OZ2_STAGES * oz2_stage_bytes<S>() + 1024 + 256; }
+constexpr uint32_t OZ2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)((2 * OZ_M) >> 4) << 24);
+constexpr uint32_t OZ_PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: rank 0's copy
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot_smem, uint32_t ncols) {  // whole warp, in BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(slot_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load whose completion bytes are credited to the barrier at the same offset in CTA rank 0
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::
+          "r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar) & OZ_PEER_MASK) : "memory");
+}
+template <int COLLECT>
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+#define MCD_UMMA_I8_2(SUFFIX)                                                                     \
+  asm volatile(                                                                                   \
+      "{\n"                                                                                       \
+      ".reg .pred p;\n"                                                                           \
+      "setp.ne.b32 p, %4, 0;\n"                                                                   \
+      "tcgen05.mma.cta_group::2.kind::i8" SUFFIX " [%0], %1, %2, %3, p;\n"                        \
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)                  \
+      : "memory")
+  if (COLLECT == OZ_A_FILL) MCD_UMMA_I8_2(".collector::a::fill");
+  else if (COLLECT == OZ_A_USE) MCD_UMMA_I8_2(".collector::a::use");
+  else if (COLLECT == OZ_A_LASTUSE) MCD_UMMA_I8_2(".collector::a::lastuse");
+  else MCD_UMMA_I8_2("");
+#undef MCD_UMMA_I8_2
+}
+// arrive (once every MMA issued so far has completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
+                   "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & OZ_PEER_MASK) : "memory");
+}
+
+// tmA: chains' planes, box 128 rows; tmBh: P's planes, box 32 rows.  Grid = 2 x (number of pairs), persistent: pair p walks the
+// tiles t = p, p + n_pairs, ...; tile t = (chain tile of 256 rows t / n_pr, P-row tile t % n_pr).  Chain rows beyond the batch (an odd
+// number of 128-row tiles) are computed and discarded by the caller's padding (buffers hold a multiple of 256 rows).
+template <int S>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
+gemm_i8_ozaki_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                          const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ Y,
+                          int nkb, int ldy, int Bp, int Mp, int bt_base, int n_pr, int n_tiles, int upper_tri, int kb_lo,
+                          const double* __restrict__ yadd, int ldyadd) {
+  static_assert(S >= 2 && S <= OZ_MAX_SLICES && S * OZ_N <= OZ_TMEM_COLS, "digit planes must fit TMEM");
+  constexpr int STAGE = oz2_stage_bytes<S>();
+  constexpr int A_PLANE = OZ_M * OZ_KB, B_PLANE = OZ2_NH * OZ_KB;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)OZ2_STAGES * STAGE);
+  uint64_t* empty = full + OZ2_STAGES;
+  uint64_t* acc_full = empty + OZ2_STAGES;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmBh);
+#pragma unroll
+      for (int s = 0; s < OZ2_STAGES; ++s) {
+        mbar_init(&full[s], 1);    // rank 0's producer (arrive.expect_tx for the bytes of BOTH CTAs)
+        mbar_init(&empty[s], 1);   // the multicast commit
+      }
+      mbar_init(acc_full, 1);
+      mbar_init(acc_empty, 2 * OZ_EPI_WARPS);   // epilogue warps of both CTAs (used on rank 0 only)
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
+  cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / TMA credit
+  if (warp == 1) tmem_alloc2(tmem_slot, OZ_TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      int g = 0;
+      for (int t = pair; t < n_tiles; t += n_pairs) {
+        const int pr0 = (t % n_pr) * OZ_N, bt0 = bt_base + (t / n_pr) * (2 * OZ_M) + (int)rank * OZ_M;
+        for (int kb = upper_tri ? pr0 / OZ_KB : kb_lo; kb < nkb; ++kb, ++g) {
+          const int st = g % OZ2_STAGES;
+          if (g >= OZ2_STAGES) mbar_wait(&empty[st], (uint32_t)((g / OZ2_STAGES) - 1) & 1u);
+          unsigned char* dst = smem + (size_t)st * STAGE;
+          if (rank == 0) mbar_arrive_expect_tx(&full[st], 2 * STAGE);
+#pragma unroll
+          for (int s = 0; s < S; ++s) tma_load_2d_pair(dst + s * A_PLANE, &tmA, kb * OZ_KB, s * Bp + bt0, &full[st]);
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            tma_load_2d_pair(dst + S * A_PLANE + s * B_PLANE, &tmBh, kb * OZ_KB, s * Mp + pr0 + (int)rank * OZ2_NH, &full[st]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: one elected lane of CTA rank 0
+    if (rank == 0 && elect_one()) {
+      int g = 0, it = 0;
+      for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
+        if (it > 0) {
+          mbar_wait(acc_empty, (it - 1) & 1);
+          tc_fence_after();
+        }
+        const int kb0 = upper_tri ? ((t % n_pr) * OZ_N) / OZ_KB : kb_lo;
+        for (int kb = kb0; kb < nkb; ++kb, ++g) {
+          const int st = g % OZ2_STAGES;
+          mbar_wait(&full[st], (uint32_t)(g / OZ2_STAGES) & 1u);
+          tc_fence_after();
+          const uint64_t dbase = oz_smem_desc(smem_u32(smem + (size_t)st * STAGE));
+#pragma unroll
+          for (int ks = 0; ks < OZ_KB / OZ_UK; ++ks) {
+#pragma unroll
+            for (int a = 0; a < S; ++a) {
+              const uint64_t da = dbase + (uint64_t)((a * A_PLANE + ks * OZ_UK) >> 4);
+#pragma unroll
+              for (int b = 0; b + a < S; ++b) {
+                const uint64_t db = dbase + (uint64_t)((S * A_PLANE + b * B_PLANE + ks * OZ_UK) >> 4);
+                const uint32_t acc = ((kb - kb0) | ks | a) != 0 ? 1u : 0u;
+                const uint32_t td = tmem_base + (uint32_t)((a + b) * OZ_N);
+                if (S - a == 1) umma_i8_pair<OZ_A_DISCARD>(td, da, db, OZ2_IDESC, acc);
+                else if (b == 0) umma_i8_pair<OZ_A_FILL>(td, da, db, OZ2_IDESC, acc);
+                else if (b + a == S - 1) umma_i8_pair<OZ_A_LASTUSE>(td, da, db, OZ2_IDESC, acc);
+                else umma_i8_pair<OZ_A_USE>(td, da, db, OZ2_IDESC, acc);
+              }
+            }
+          }
+          umma_commit_pair(&empty[st]);
+          if (kb == nkb - 1) umma_commit_pair(acc_full);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue of this CTA's 128 chains
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int chalf = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int it = 0;
+    for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
+      const int pr0 = (t % n_pr) * OZ_N, bt0 = bt_base + (t / n_pr) * (2 * OZ_M) + (int)rank * OZ_M;
+      const int b = bt0 + row;
+      const double sa = scaleA[b];
+      double* yrow = Y + (size_t)b * ldy + pr0;
+      const double* arow = yadd ? yadd + (size_t)b * ldyadd + pr0 : nullptr;
+      mbar_wait(acc_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * chalf + cc;
+        uint32_t v[S][16];
+#pragma unroll
+        for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
+        tmem_ld_wait();
+        if (cc == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_rank0(acc_empty);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
+#pragma unroll
+          for (int d = S - 2; d >= 0; --d) {
+            r0 = fma(r0, 0.00390625, oz_i2d(v[d][j]));
+            r1 = fma(r1, 0.00390625, oz_i2d(v[d][j + 1]));
+          }
+          const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
+          double2 o = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
+          if (arow) {
+            const double2 ya = *reinterpret_cast<const double2*>(arow + c * 16 + j);
+            o.x += ya.x;
+            o.y += ya.y;
+          }
+          *reinterpret_cast<double2*>(yrow + c * 16 + j) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs are done with the pair's tensor memory
+  if (warp == 1) tmem_dealloc2(tmem_base, OZ_TMEM_COLS);
+}
+
 // ------------------------------------------------------------------------------ digit planes
 // scale = 2^(e+1) with 2^(e-1) <= max|x| < 2^e (2^(e+2) if max|x| > 0.996 * 2^e), so |x / scale| <= 0.498, the
 // range S balanced base-256 digits cover.  A row holding a non-finite value gets scale = NaN (and zero
@@ -830,6 +1053,30 @@ inline cudaError_t gemm_i8_ozaki_configure() {
   cudaError_t e = cudaFuncSetAttribute(gemm_i8_ozaki_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes<S>());
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(gemm_i8_ozaki_v2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes<S>());
+}
+
+inline int oz_pair_mode() {   // MCD_OZ_PAIR=1: the cta_group::2 kernel (experiment switch until it is the default)
+  static const int m = getenv("MCD_OZ_PAIR") ? atoi(getenv("MCD_OZ_PAIR")) : 0;
+  return m;
+}
+template <int S>
+inline cudaError_t gemm_i8_ozaki_pair_launch(const CUtensorMap& tmA, const CUtensorMap& tmBh, const double* scaleA,
+                                             const double* scaleB, double* Y, int Mp, int n_chains_padded256, int ld8, int ldy,
+                                             int Bp_total, cudaStream_t st, int bt_base, int n_sms, int upper_tri, int kb_lo,
+                                             int kb_hi, const double* yadd, int ldyadd) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_ozaki_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz2_smem_bytes<S>());
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int n_pr = Mp / OZ_N, n_tiles = n_pr * (n_chains_padded256 / (2 * OZ_M));
+  const int max_pairs = n_sms / 2;
+  const int pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
+  const int nkb = kb_hi > 0 ? kb_hi : ld8 / OZ_KB;
+  gemm_i8_ozaki_pair_kernel<S><<<2 * pairs, OZ_THREADS, oz2_smem_bytes<S>(), st>>>(tmA, tmBh, scaleA, scaleB, Y, nkb, ldy, Bp_total, Mp,
+                                                                                    bt_base, n_pr, n_tiles, upper_tri, kb_lo, yadd, ldyadd);
+  return cudaGetLastError();
 }
 
 // n_chains_padded chains (multiple of 128) starting at bt_base, Mp P rows (multiple of 64), ld8 = padded K

@@ -123,6 +123,7 @@ struct mcd_handle {
   DevBuf d_pP, d_sP, d_pX, d_sX, d_pU, d_sU;   // planes + scales of Sigma^-1, of the residuals, of U = L^T
   int oz_U_S = 0;
   CUtensorMap tmA8{}, tmB8{}, tmU8{};
+  CUtensorMap tmB8h{}, tmU8h{};   // the same planes with 32-row boxes: each CTA of a pair (cta_group::2 kernel) loads half a P-row tile
   cudaStream_t streams[N_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
   // device-path pipeline (eval_device on large dense models): chunks of chains run K1 / contraction / K3 on three streams so
   // that the HBM-side kernels of one chunk overlap the tensor-core contraction of its neighbours
@@ -164,7 +165,7 @@ int upload(mcd_handle* h, DevBuf& b, const T* src, size_t n) {
 int ensure_i8(mcd_handle* h);
 
 int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
-  int need = (n_chains + GEMM_BT - 1) / GEMM_BT * GEMM_BT;
+  int need = (n_chains + 2 * GEMM_BT - 1) / (2 * GEMM_BT) * (2 * GEMM_BT);   // whole CTA-pair tiles of 256 chains
   if (need > h->cap) {
     CU_TRY(h, cudaDeviceSynchronize());
     for (DevBuf* b : {&h->d_dx, &h->d_y, &h->d_states, &h->d_out, &h->d_grad, &h->d_status, &h->d_theta, &h->d_gtheta,
@@ -260,7 +261,8 @@ int ensure_i8_planes(mcd_handle* h) {
                                                    h->d_ck.as<double>(), h->d_ck.as<double>(), h->d_ick.as<double>());
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaDeviceSynchronize());
-    if (oz_make_plane_map(&h->tmB8, h->d_pP.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ_N) != 0)
+    if (oz_make_plane_map(&h->tmB8, h->d_pP.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ_N) != 0 ||
+        oz_make_plane_map(&h->tmB8h, h->d_pP.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ2_NH) != 0)
       return fail(h, "cuTensorMapEncodeTiled failed for the precision digit planes");
     CU_TRY(h, gemm_i8_ozaki_configure<S>());
     CU_TRY(h, cudaFuncSetAttribute(residual_split_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -283,7 +285,8 @@ int ensure_i8_planes(mcd_handle* h) {
                                                    h->d_ck.as<double>(), nullptr, nullptr);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaDeviceSynchronize());
-    if (oz_make_plane_map(&h->tmU8, h->d_pU.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ_N) != 0)
+    if (oz_make_plane_map(&h->tmU8, h->d_pU.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ_N) != 0 ||
+        oz_make_plane_map(&h->tmU8h, h->d_pU.as<signed char>(), (size_t)S * h->Mp8, h->ld8, OZ2_NH) != 0)
       return fail(h, "cuTensorMapEncodeTiled failed for the Cholesky-factor digit planes");
     h->oz_U_S = S;
   }
@@ -311,6 +314,25 @@ int ensure_i8(mcd_handle* h) {
   if (h->oz_S == 0 || h->dm.lik != MCD_LIK_FULL || h->sparse || h->N <= SMALL_TREE_MAX_NODES) return 0;
   return h->oz_S == 6 ? ensure_i8_planes<6>(h) : ensure_i8_planes<7>(h);
 }
+// the contraction launch: CTA pairs (256-chain tiles, cta_group::2) when selected and the chunk is aligned to them, else one CTA per tile
+template <int S>
+int oz_contract(mcd_handle* h, bool tri, int n, int c0, cudaStream_t st, int kb_lo = 0, int kb_hi = -1, const double* yadd = nullptr,
+                int ldyadd = 0) {
+  const double* sB = (tri ? h->d_sU : h->d_sP).as<double>();
+  if (oz_pair_mode() && !yadd && c0 % (2 * OZ_M) == 0) {   // (the rank-limited MH update keeps the one-CTA kernel: its y buffer is padded to 128 rows)
+    const int np2 = (n + 2 * OZ_M - 1) / (2 * OZ_M) * (2 * OZ_M);
+    if (c0 + np2 <= h->cap) {
+      CU_TRY(h, gemm_i8_ozaki_pair_launch<S>(h->tmA8, tri ? h->tmU8h : h->tmB8h, h->d_sX.as<double>(), sB, h->d_y.as<double>(), h->Mp8, np2,
+                                             h->ld8, h->dm.ldy, h->cap, st, c0, h->n_sms, tri ? 1 : 0, kb_lo, kb_hi, yadd, ldyadd));
+      return 0;
+    }
+  }
+  const int np = (n + OZ_M - 1) / OZ_M * OZ_M;
+  CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, tri ? h->tmU8 : h->tmB8, h->d_sX.as<double>(), sB, h->d_y.as<double>(), h->Mp8, np, h->ld8,
+                                    h->dm.ldy, h->cap, st, c0, h->n_sms, tri ? 1 : 0, kb_lo, kb_hi, yadd, ldyadd));
+  return 0;
+}
+
 // K1 + contraction on the INT8 tensor pipe for chains [c0, c0 + n)
 template <int S>
 int enqueue_i8(mcd_handle* h, int c0, int n, const double* xs, cudaStream_t st, cudaEvent_t ev_mid, bool tri) {
@@ -320,10 +342,7 @@ int enqueue_i8(mcd_handle* h, int c0, int n, const double* xs, cudaStream_t st, 
       M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs, h->d_pX.as<signed char>() + (size_t)c0 * h->ld8, h->ld8, stride,
       h->d_sX.as<double>() + c0, n, h->d_ick.as<double>(), h->d_widecnt.as<int>() + (size_t)c0 * 8);
   if (ev_mid) CU_TRY(h, cudaEventRecord(ev_mid, st));
-  const int np = (n + OZ_M - 1) / OZ_M * OZ_M;
-  CU_TRY(h, gemm_i8_ozaki_launch<S>(h->tmA8, tri ? h->tmU8 : h->tmB8, h->d_sX.as<double>(),
-                                    (tri ? h->d_sU : h->d_sP).as<double>(), h->d_y.as<double>(), h->Mp8, np, h->ld8, M.ldy,
-                                    h->cap, st, c0, h->n_sms, tri ? 1 : 0));
+  if (oz_contract<S>(h, tri, n, c0, st)) return -1;
   // chains K1 flagged (residual range too wide for 56-bit digits relative to the row maximum): their rows of y in plain FP64
   fp64_rows_kernel<<<n, 256, (size_t)M.K * 8, st>>>(M.N, M.K, M.S, M.root_r, M.parent, M.mu, xs,
                                                      (tri ? h->d_U : h->d_P).as<double>(), M.ldk, tri ? 1 : 0,
@@ -1173,15 +1192,12 @@ int mh_enqueue(mcd_handle* h, int kind, int node, double param, double tune, int
     const int kb_lo = k_lo / OZ_KB, kb_hi = (k_lo + size - 1) / OZ_KB + 1;
     const int mode = kind == MH_SCALE_SUBTREE ? 0 : kind == MH_SCALE_SUBTREE_CONTRA ? 1 : 2;
     const size_t stride = (size_t)h->cap * h->ld8;
-    const int np = (n + OZ_M - 1) / OZ_M * OZ_M;
 #define MCD_LAUNCH_RANGE(SS)                                                                                               \
   delta_split_kernel<SS><<<n, 256, (size_t)(kb_hi - kb_lo) * OZ_KB * 8, st>>>(                                            \
       h->N, h->S, h->dm.root_r, h->dm.parent, h->d_chain.as<double>(), h->d_undo.as<double>(), h->undo_stride,            \
       h->d_meta.as<int4>(), mode, node, size, k_lo, size, kb_lo, kb_hi, h->d_pX.as<signed char>(), h->ld8, stride,        \
       h->d_sX.as<double>(), n, h->d_ick.as<double>());                                                                    \
-  CU_TRY(h, gemm_i8_ozaki_launch<SS>(h->tmA8, h->tmB8, h->d_sX.as<double>(), h->d_sP.as<double>(), h->d_y.as<double>(),   \
-                                     h->Mp8, np, h->ld8, h->dm.ldy, h->cap, st, 0, h->n_sms, 0, kb_lo, kb_hi,             \
-                                     h->d_chain_y.as<double>(), h->ldyc))
+  if (oz_contract<SS>(h, false, n, 0, st, kb_lo, kb_hi, h->d_chain_y.as<double>(), h->ldyc)) return -1
     if (h->oz_S == 6) { MCD_LAUNCH_RANGE(6); } else { MCD_LAUNCH_RANGE(7); }
 #undef MCD_LAUNCH_RANGE
     h->launches += 2;

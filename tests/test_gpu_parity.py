@@ -416,6 +416,39 @@ def test_int8_contraction_is_bit_reproducible_and_tiling_invariant():
     ev.close()
 
 
+def test_contraction_kernel_variants_are_bit_identical():
+    """the three INT8 contraction kernels -- plane-granular pipeline (default), stage-granular pipeline of round 1 (MCD_OZ_V1) and
+    CTA pairs with cta_group::2 MMAs (MCD_OZ_PAIR) -- multiply the same integers: outputs and gradients agree bit for bit, also for a
+    batch that is an odd number of 128-chain tiles (the pair kernel pads to 256) and on the value-only triangular path"""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from mcmc_date_b200 import binding, synth\n"
+        "md, h = synth.synthetic_model(300, seed=31, n_cal=3, n_con=2, n_brace=1)\n"
+        "ev = binding.Evaluator(md)\n"
+        "m = hashlib.sha256()\n"
+        "for B in (640, 1100, 130):\n"
+        "    X = synth.synthetic_states(md, h, B, seed=500 + B)\n"
+        "    out, grad, st = ev.eval_grad(X)\n"
+        "    out2, st2 = ev.eval(X)\n"
+        "    for a in (out, grad, st, out2, st2): m.update(np.ascontiguousarray(a).tobytes())\n"
+        "print(m.hexdigest())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    digests = {}
+    for name, env in (("default", {}), ("v1", {"MCD_OZ_V1": "1"}), ("pair", {"MCD_OZ_PAIR": "1"})):
+        e = dict(os.environ, **env)
+        for k in ("MCD_OZ_V1", "MCD_OZ_PAIR"):
+            if k not in env:
+                e.pop(k, None)
+        r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (name, r.stderr[-500:])
+        digests[name] = r.stdout.strip().splitlines()[-1]
+    assert digests["default"] == digests["v1"] == digests["pair"], digests
+
+
 def test_int8_contraction_non_finite_states():
     """NaN / inf in a state poison that chain only (NaN propagates like in the FP64 product), on both pipes"""
     md, h = synth.synthetic_model(300, seed=99, n_cal=4, n_con=2, n_brace=1)
