@@ -74,6 +74,7 @@ struct mcd_handle {
   DevModel dm{};
   DevBuf d_parent, d_child1, d_inner, d_mu, d_var, d_P, d_U;
   DevBuf d_ck, d_ick;             // INT8 contraction: power-of-two equilibration c_k ~ 1 / sqrt(P_kk) and its reciprocal, [ld8]
+  DevBuf d_partials;              // [cap][POST_NPART] per-chain sums handed from posterior_kernel to posterior_assemble_kernel
   DevBuf d_wide, d_widecnt;       // [cap] chains whose residual range is too wide for the digit planes (FP64 fall-back); [cap][8] counts
   bool sparse = false;            // MCD_LIK_SPARSE on a large tree: CSR contraction instead of the dense one
   DevBuf d_sp_ptr, d_sp_col, d_sp_val;
@@ -169,12 +170,13 @@ int ensure_capacity(mcd_handle* h, int n_chains, bool staging, bool grad) {
   if (need > h->cap) {
     CU_TRY(h, cudaDeviceSynchronize());
     for (DevBuf* b : {&h->d_dx, &h->d_y, &h->d_states, &h->d_out, &h->d_grad, &h->d_status, &h->d_theta, &h->d_gtheta,
-                      &h->d_mom, &h->d_eps, &h->d_energy, &h->d_status_acc, &h->d_pX, &h->d_sX, &h->d_wide, &h->d_widecnt}) {
+                      &h->d_mom, &h->d_eps, &h->d_energy, &h->d_status_acc, &h->d_pX, &h->d_sX, &h->d_wide, &h->d_widecnt, &h->d_partials}) {
       if (b->p) cudaFree(b->p);
       b->p = nullptr;
     }
     h->oz_X_S = 0;
     h->cap = need;
+    CU_TRY(h, cudaMalloc(&h->d_partials.p, (size_t)need * POST_NPART * 8));
     {  // y = P dx (and scratch of the posterior kernel) exists for every likelihood kind
       const size_t ny = (size_t)need * h->ldy;
       CU_TRY(h, cudaMalloc(&h->d_y.p, ny * 8));
@@ -452,8 +454,9 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   int32_t* s = d_status + c0;
   // shared memory: reduction scratch + per chain group the staged state row [S] and contraction result [K]
   const size_t smem = POST_SMEM_FIXED + (size_t)cpb * M.S * 8;
+  double* pz = h->d_partials.as<double>() + (size_t)c0 * POST_NPART;
 #define MCD_LAUNCH_POST(GG, CC, MB) \
-  posterior_kernel<GG, CC, GRAD, MB><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n)
+  posterior_kernel<GG, CC, GRAD, MB><<<grid, POST_THREADS, smem, st>>>(M, xs, y, o, g, s, n, pz)
 #define MCD_LAUNCH_POST_G(GG, MB)                                              \
   switch (M.clock) {                                                           \
     case 0: MCD_LAUNCH_POST(GG, 0, MB); break;                                 \
@@ -464,7 +467,9 @@ int enqueue(mcd_handle* h, int c0, int n, const double* d_states, double* d_out,
   MCD_LAUNCH_POST_G(256, POST_MINB)
 #undef MCD_LAUNCH_POST_G
 #undef MCD_LAUNCH_POST
-  h->launches += 1;
+  // the scalar tail of every chain (product' semantics, status, scalar gradient entries) in parallel, one thread per chain
+  posterior_assemble_kernel<GRAD><<<(n + 127) / 128, 128, 0, st>>>(M, xs, pz, o, g, s, n);
+  h->launches += 2;
   if (h->timing) CU_TRY(h, cudaEventRecord(ev[3], st));
   CU_TRY(h, cudaGetLastError());
   return 0;
@@ -578,7 +583,8 @@ int enqueue_pipelined(mcd_handle* h, int n, const double* d_states, double* d_ou
     // all but the last chunk: at most `pipe_k3_per_sm` CTAs per SM, so that the next chunk's contraction CTA fits beside them
     const bool last = c0 + per >= n;
     const int k3grid = last || h->pipe_k3_per_sm <= 0 ? m : std::min(m, h->pipe_k3_per_sm * h->n_sms);
-#define MCD_LAUNCH_POST_P(CC) posterior_kernel<256, CC, GRAD, POST_MINB><<<k3grid, POST_THREADS, smem, h->pipe_st[2]>>>(M, xs, y, o, g, st_, m)
+    double* pz = h->d_partials.as<double>() + (size_t)c0 * POST_NPART;
+#define MCD_LAUNCH_POST_P(CC) posterior_kernel<256, CC, GRAD, POST_MINB><<<k3grid, POST_THREADS, smem, h->pipe_st[2]>>>(M, xs, y, o, g, st_, m, pz)
     switch (M.clock) {
       case 0: MCD_LAUNCH_POST_P(0); break;
       case 1: MCD_LAUNCH_POST_P(1); break;
@@ -586,9 +592,10 @@ int enqueue_pipelined(mcd_handle* h, int n, const double* d_states, double* d_ou
       default: MCD_LAUNCH_POST_P(3); break;
     }
 #undef MCD_LAUNCH_POST_P
+    posterior_assemble_kernel<GRAD><<<(m + 127) / 128, 128, 0, h->pipe_st[2]>>>(M, xs, pz, o, g, st_, m);
     CU_TRY(h, cudaEventRecord(e3, h->pipe_st[2]));
     CU_TRY(h, cudaStreamWaitEvent(user, e3, 0));
-    h->launches += 4;
+    h->launches += 5;
   }
   CU_TRY(h, cudaGetLastError());
   return 0;

@@ -219,7 +219,7 @@ def test_device_entry_points_match_host_entry_points(full_size):
     ev.eval_grad_device(B, d_x.data_ptr(), d_out.data_ptr(), d_grad.data_ptr(), d_st.data_ptr(),
                         torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert ev.kernel_launches() - n0 == 4          # residual split, contraction, FP64 fall-back (flagged chains only), posterior
+    assert ev.kernel_launches() - n0 == 5          # residual split, contraction, FP64 fall-back (flagged chains only), posterior, scalar assembly
     assert np.array_equal(d_out.cpu().numpy(), out[:B]) and np.array_equal(d_grad.cpu().numpy(), grad[:B])
     assert np.array_equal(d_st.cpu().numpy(), st[:B])
 
