@@ -141,6 +141,49 @@ __device__ __forceinline__ double oz_i2d(uint32_t v) {
 // instruction descriptor: D = S32 (2 @4), A = B = signed int8 (1 @7, 1 @10), both K-major, N>>3 @17, M>>4 @24
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
 
+// ------------------------------------------------------------------------------ epilogue of one tile (all contraction kernels)
+// One epilogue warp = 32 TMEM lanes (chains) x 32 columns (P rows) of every accumulator, in two chunks of 16 columns: tcgen05.ld of
+// the S accumulators, exact INT32 -> FP64, Horner in 1/256, row x column scales, 16-byte stores (plus the cached y of the MH range
+// update).  The accumulators are handed back to the MMA warp as soon as this warp's LAST tcgen05.ld has completed -- the arithmetic
+// and the stores of that chunk only touch registers.  RANK0: arrive on the barrier of CTA rank 0 of the pair (cta_group::2 kernel).
+template <int S, bool RANK0>
+__device__ __forceinline__ void oz_epilogue_tile(uint32_t tlane, int chalf, int lane, double sa, const double* __restrict__ sb_tile,
+                                                 double* __restrict__ yrow, const double* __restrict__ arow, uint64_t* acc_empty) {
+#pragma unroll 1
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c = 2 * chalf + cc;
+    uint32_t v[S][16];
+#pragma unroll
+    for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
+    tmem_ld_wait();
+    if (cc == 1) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (RANK0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(acc_empty) & 0xFEFFFFFFu) : "memory");
+        else mbar_arrive(acc_empty);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
+#pragma unroll
+      for (int d = S - 2; d >= 0; --d) {
+        r0 = fma(r0, 0.00390625, oz_i2d(v[d][j]));
+        r1 = fma(r1, 0.00390625, oz_i2d(v[d][j + 1]));
+      }
+      const double2 sb = *reinterpret_cast<const double2*>(sb_tile + c * 16 + j);
+      double2 o = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
+      if (arow) {
+        const double2 ya = *reinterpret_cast<const double2*>(arow + c * 16 + j);
+        o.x += ya.x;
+        o.y += ya.y;
+      }
+      *reinterpret_cast<double2*>(yrow + c * 16 + j) = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ the contraction
 // tmA: digit planes of the residuals, [S][Bp][ld8] int8 seen as a 2-D [S*Bp][ld8] tensor, box 128 x OZ_KB
 // tmB: digit planes of P,             [S][Mp][ld8]                        [S*Mp][ld8],       box  64 x OZ_KB
@@ -236,9 +279,6 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int kb0 = upper_tri ? ((t % n_pr) * OZ_N) / OZ_KB : kb_lo;
       for (int kb = kb0; kb < nkb; ++kb, ++g) {
         const int st = g % OZ_STAGES;
-#ifdef MCD_OZ_NO_REFILL
-        if (g < OZ_STAGES)
-#endif
         mbar_wait(&full[st], (g / OZ_STAGES) & 1);
         tc_fence_after();
         if (leader) {
@@ -285,58 +325,7 @@ gemm_i8_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const double* arow = yadd ? yadd + (size_t)b * ldyadd + pr0 : nullptr;
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
-      // two chunks of 16 columns per warp.  The accumulators are handed back to the MMA warp as soon as this warp's LAST
-      // tcgen05.ld has completed -- before the Horner evaluation and the stores of that chunk, which only touch registers:
-      // the next tile's first MMAs overlap them
-#ifdef MCD_OZ_NO_EPI
-      const int n_chunks = (int)(sa == 12345.678);
-#else
-      const int n_chunks = 2;
-#endif
-#pragma unroll 1
-      for (int cc = 0; cc < n_chunks; ++cc) {
-        const int c = 2 * chalf + cc;
-        uint32_t v[S][16];
-#pragma unroll
-        for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
-        tmem_ld_wait();
-#ifndef MCD_OZ_LATE_HANDBACK
-        if (cc == n_chunks - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty);
-        }
-#endif
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
-#pragma unroll
-          for (int d = S - 2; d >= 0; --d) {
-            r0 = fma(r0, 0.00390625, oz_i2d(v[d][j]));
-            r1 = fma(r1, 0.00390625, oz_i2d(v[d][j + 1]));
-          }
-          const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
-          double2 o = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
-          if (arow) {
-            const double2 ya = *reinterpret_cast<const double2*>(arow + c * 16 + j);
-            o.x += ya.x;
-            o.y += ya.y;
-          }
-          *reinterpret_cast<double2*>(yrow + c * 16 + j) = o;
-        }
-      }
-#ifdef MCD_OZ_LATE_HANDBACK
-      if (n_chunks > 0) {  // (A/B build: hand back after the whole epilogue, as in round 1)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty);
-      }
-#endif
-      if (n_chunks == 0) {  // (experiment build without an epilogue)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty);
-      }
+      oz_epilogue_tile<S, false>(tlane, chalf, lane, sa, scaleB + pr0, yrow, arow, acc_empty);
     }
   }
   tc_fence_before();
@@ -489,36 +478,7 @@ gemm_i8_ozaki_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const double* arow = yadd ? yadd + (size_t)b * ldyadd + pr0 : nullptr;
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * chalf + cc;
-        uint32_t v[S][16];
-#pragma unroll
-        for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
-        tmem_ld_wait();
-        if (cc == 1) {  // last TMEM read of this warp: hand the accumulators back before the arithmetic of this chunk
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
-#pragma unroll
-          for (int d = S - 2; d >= 0; --d) {
-            r0 = fma(r0, 0.00390625, oz_i2d(v[d][j]));
-            r1 = fma(r1, 0.00390625, oz_i2d(v[d][j + 1]));
-          }
-          const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
-          double2 o = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
-          if (arow) {
-            const double2 ya = *reinterpret_cast<const double2*>(arow + c * 16 + j);
-            o.x += ya.x;
-            o.y += ya.y;
-          }
-          *reinterpret_cast<double2*>(yrow + c * 16 + j) = o;
-        }
-      }
+      oz_epilogue_tile<S, false>(tlane, chalf, lane, sa, scaleB + pr0, yrow, arow, acc_empty);
     }
   }
   tc_fence_before();
@@ -586,9 +546,6 @@ __device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, u
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
                    "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & OZ_PEER_MASK) : "memory");
 }
 
 // tmA: chains' planes, box 128 rows; tmBh: P's planes, box 32 rows.  Grid = 2 x (number of pairs), persistent: pair p walks the
@@ -712,36 +669,7 @@ gemm_i8_ozaki_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const double* arow = yadd ? yadd + (size_t)b * ldyadd + pr0 : nullptr;
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * chalf + cc;
-        uint32_t v[S][16];
-#pragma unroll
-        for (int d = 0; d < S; ++d) tmem_ld_x16(tlane + (uint32_t)(d * OZ_N + c * 16), v[d]);
-        tmem_ld_wait();
-        if (cc == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_rank0(acc_empty);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          double r0 = oz_i2d(v[S - 1][j]), r1 = oz_i2d(v[S - 1][j + 1]);
-#pragma unroll
-          for (int d = S - 2; d >= 0; --d) {
-            r0 = fma(r0, 0.00390625, oz_i2d(v[d][j]));
-            r1 = fma(r1, 0.00390625, oz_i2d(v[d][j + 1]));
-          }
-          const double2 sb = *reinterpret_cast<const double2*>(scaleB + pr0 + c * 16 + j);
-          double2 o = make_double2(r0 * sa * sb.x, r1 * sa * sb.y);
-          if (arow) {
-            const double2 ya = *reinterpret_cast<const double2*>(arow + c * 16 + j);
-            o.x += ya.x;
-            o.y += ya.y;
-          }
-          *reinterpret_cast<double2*>(yrow + c * 16 + j) = o;
-        }
-      }
+      oz_epilogue_tile<S, true>(tlane, chalf, lane, sa, scaleB + pr0, yrow, arow, acc_empty);
     }
   }
   tc_fence_before();
