@@ -271,6 +271,20 @@ void* mcd_chains_out_device(mcd_handle* h); /* device pointer: [n_resident][MCD_
  * mcd_mc3_swap reads the gathered table. */
 int mcd_chains_stats_device(mcd_handle* h, double* d_stats);
 
+/* The one exchange between GPUs: MC3 swap statistics.  One process per GPU, one handle per process; the chains of a
+ * temperature group may be spread over the ranks.  NCCL is loaded at run time (dlopen "libnccl.so.2": the library itself has no
+ * link-time dependency on it).
+ *   mcd_comm_unique_id  rank 0 creates the 128-byte NCCL id; the host distributes it to the other ranks (any channel);
+ *   mcd_comm_init       every rank joins with (world, rank, id); collective;
+ *   mcd_allgather_stats (ln prior, ln likelihood) of this rank's resident chains -> [world * n_resident][2] on every rank, into a
+ *                       caller's DEVICE buffer (the table mcd_mc3_swap takes); all ranks must hold the same number of resident
+ *                       chains; ncclAllGather on the library's stream, returns after completion;
+ *   mcd_comm_destroy    leaves the communicator (also done by mcd_destroy). */
+int mcd_comm_unique_id(void* id128 /* [128] bytes out */);
+int mcd_comm_init(mcd_handle* h, int32_t world, int32_t rank, const void* id128);
+int mcd_allgather_stats(mcd_handle* h, double* d_stats_global /* device, [world * n_resident][2] */);
+int mcd_comm_destroy(mcd_handle* h);
+
 /* Arithmetic pipe of the precision-matrix contraction Y = DX . Sigma^-1 on large trees (the dominant kernel).
  *   MCD_CONTRACT_DMMA   FP64 tensor instructions (mma.sync m8n8k4.f64), plain FP64 GEMM rounding
  *   MCD_CONTRACT_I8_Sn  INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators) on n balanced base-256 digit

@@ -24,7 +24,7 @@ EXPORTS = [
     "mcd_chains_out_device", "mcd_chains_stats_device", "mcd_mh_set_incremental", "mcd_mh_get_incremental",
     "mcd_eval_device", "mcd_set_contraction", "mcd_get_contraction",
     "mcd_eval_grad_device", "mcd_kernel_launches", "mcd_synchronize", "mcd_version", "mcd_set_kernel_timing",
-    "mcd_kernel_times",
+    "mcd_kernel_times", "mcd_comm_unique_id", "mcd_comm_init", "mcd_allgather_stats", "mcd_comm_destroy",
 ]
 
 
@@ -117,6 +117,10 @@ def load_library():
     L.mcd_kernel_launches.restype = C.c_int64
     L.mcd_set_kernel_timing.argtypes = [vp, C.c_int]
     L.mcd_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+    L.mcd_comm_unique_id.argtypes = [vp]
+    L.mcd_comm_init.argtypes = [vp, i32, i32, C.c_char_p]
+    L.mcd_allgather_stats.argtypes = [vp, vp]
+    L.mcd_comm_destroy.argtypes = [vp]
     _LIB = L
     return L
 
@@ -350,6 +354,26 @@ class Evaluator:
 
     def mh_incremental_active(self) -> bool:
         return self._L.mcd_mh_get_incremental(self.h) == 1
+
+    # ---- MC3 swap statistics across GPUs (NCCL inside the library)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rank 0: the 128-byte NCCL id the other ranks need for comm_init"""
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        if L.mcd_comm_unique_id(buf) != 0:
+            raise RuntimeError("mcd_comm_unique_id: " + (L.mcd_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        self._check(self._L.mcd_comm_init(self.h, int(world), int(rank), C.c_char_p(bytes(unique_id))))
+
+    def allgather_stats(self, d_stats_global: int):
+        """(ln prior, ln lik) of the resident chains of every rank -> device buffer [world * n_resident][2]"""
+        self._check(self._L.mcd_allgather_stats(self.h, d_stats_global))
+
+    def comm_destroy(self):
+        self._check(self._L.mcd_comm_destroy(self.h))
 
     def chains_stats_device(self, d_stats: int):
         """(ln prior, ln lik) of the resident chains -> device buffer [n][2] (send buffer of the MC3 all-gather)"""

@@ -11,6 +11,7 @@
 //   residual_split_kernel -> gemm_i8_ozaki_kernel -> posterior_kernel           (MCD_CONTRACT_I8_*, default)
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdio>
@@ -74,6 +75,11 @@ struct mcd_handle {
   DevModel dm{};
   DevBuf d_parent, d_child1, d_inner, d_mu, d_var, d_P, d_U;
   DevBuf d_ck, d_ick;             // INT8 contraction: power-of-two equilibration c_k ~ 1 / sqrt(P_kk) and its reciprocal, [ld8]
+  // MC3 swap statistics across GPUs (NCCL, loaded at run time)
+  void* nccl_comm = nullptr;
+  int comm_world = 0, comm_rank = -1;
+  DevBuf d_stats_local;           // [n_resident][2] send buffer of the all-gather
+  size_t d_stats_local_n = 0;
   DevBuf d_partials;              // [cap][POST_NPART] per-chain sums handed from posterior_kernel to posterior_assemble_kernel
   DevBuf d_wide, d_widecnt;       // [cap] chains whose residual range is too wide for the digit planes (FP64 fall-back); [cap][8] counts
   bool sparse = false;            // MCD_LIK_SPARSE on a large tree: CSR contraction instead of the dense one
@@ -1410,6 +1416,52 @@ int mc3_slots(mcd_handle* h, int32_t* slots) {
 
 }  // namespace
 
+// ---- NCCL, bound at run time: the evaluation needs no collective, only MC3's swap statistics cross GPUs (16 bytes per chain)
+struct NcclId { char internal[128]; };   // ncclUniqueId
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId /* by value, as in nccl.h */, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi* nccl_api(std::string* err) {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+      *(void**)(&api.GetUniqueId) = dlsym(api.lib, "ncclGetUniqueId");
+      *(void**)(&api.CommInitRank) = dlsym(api.lib, "ncclCommInitRank");
+      *(void**)(&api.AllGather) = dlsym(api.lib, "ncclAllGather");
+      *(void**)(&api.CommDestroy) = dlsym(api.lib, "ncclCommDestroy");
+      *(void**)(&api.GetErrorString) = dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) {
+    if (err) *err = "NCCL (libnccl.so.2) could not be loaded";
+    return nullptr;
+  }
+  return &api;
+}
+static int comm_destroy(mcd_handle* h) {
+  if (h->nccl_comm) {
+    NcclApi* a = nccl_api(nullptr);
+    if (a) a->CommDestroy(h->nccl_comm);
+    h->nccl_comm = nullptr;
+    h->comm_world = 0;
+    h->comm_rank = -1;
+  }
+  return 0;
+}
+
 extern "C" {
 
 const char* mcd_version(void) { return "mcmcdate_b200 0.1 (sm_100a)"; }
@@ -1715,6 +1767,7 @@ void mcd_destroy(mcd_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  comm_destroy(h);
   for (int i = 0; i < N_STREAMS; ++i)
     if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
   for (int i = 0; i < 3; ++i)
@@ -1840,6 +1893,61 @@ int mcd_chains_stats_device(mcd_handle* h, double* d_stats) {
                               cudaMemcpyDeviceToDevice, h->streams[0]));
   CU_TRY(h, cudaStreamSynchronize(h->streams[0]));
   return 0;
+}
+int mcd_comm_unique_id(void* id128) {
+  std::string err;
+  NcclApi* a = nccl_api(&err);
+  if (!a || !id128) { g_create_error = a ? "mcd_comm_unique_id: null buffer" : err; return -1; }
+  const int rc = a->GetUniqueId(id128);
+  if (rc != 0) { g_create_error = std::string("ncclGetUniqueId: ") + (a->GetErrorString ? a->GetErrorString(rc) : "error"); return -1; }
+  return 0;
+}
+int mcd_comm_init(mcd_handle* h, int32_t world, int32_t rank, const void* id128) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:comm_init");
+  if (world < 1 || rank < 0 || rank >= world || !id128) return fail(h, "mcd_comm_init: bad world / rank / id");
+  std::string err;
+  NcclApi* a = nccl_api(&err);
+  if (!a) return fail(h, err);
+  CU_TRY(h, cudaSetDevice(h->device));
+  comm_destroy(h);
+  NcclId id;
+  memcpy(id.internal, id128, 128);
+  const int rc = a->CommInitRank(&h->nccl_comm, world, id, rank);
+  if (rc != 0) { h->nccl_comm = nullptr; return fail(h, std::string("ncclCommInitRank: ") + (a->GetErrorString ? a->GetErrorString(rc) : "error")); }
+  h->comm_world = world;
+  h->comm_rank = rank;
+  return 0;
+}
+int mcd_allgather_stats(mcd_handle* h, double* d_stats_global) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  NvtxRange nvtx_range("mcd:allgather_stats");
+  if (h->n_resident <= 0 || !d_stats_global) return fail(h, "mcd_allgather_stats: no resident chains or null buffer");
+  if (!h->nccl_comm) return fail(h, "mcd_allgather_stats: no communicator (call mcd_comm_init first)");
+  NcclApi* a = nccl_api(nullptr);
+  CU_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->streams[0];
+  SerialScope order(h, st);
+  if (order.rc) return -1;
+  const size_t n = (size_t)h->n_resident;
+  if (!h->d_stats_local.p || h->d_stats_local_n < n) {
+    if (h->d_stats_local.p) { CU_TRY(h, cudaStreamSynchronize(st)); cudaFree(h->d_stats_local.p); h->d_stats_local.p = nullptr; }
+    CU_TRY(h, cudaMalloc(&h->d_stats_local.p, n * 16));
+    h->d_stats_local_n = n;
+  }
+  CU_TRY(h, cudaMemcpy2DAsync(h->d_stats_local.p, 16, h->d_chain_out.as<double>() + MCD_OUT_LNPRIOR, MCD_OUT_COLS * 8, 16, n,
+                              cudaMemcpyDeviceToDevice, st));
+  const int rc = a->AllGather(h->d_stats_local.p, d_stats_global, n * 2, /* ncclFloat64 */ 8, h->nccl_comm, st);
+  if (rc != 0) return fail(h, std::string("ncclAllGather: ") + (a->GetErrorString ? a->GetErrorString(rc) : "error"));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  return 0;
+}
+int mcd_comm_destroy(mcd_handle* h) {
+  if (!h) return -1;
+  std::lock_guard<std::mutex> lock(h->mtx);
+  return comm_destroy(h);
 }
 int mcd_mh_step(mcd_handle* h, int32_t kind, int32_t node, double sd, double tune, int32_t use_root_jacobian, uint64_t seed,
                 uint32_t iteration, int32_t* accepted) {

@@ -1135,6 +1135,33 @@ def test_mixed_entry_points_are_ordered_without_explicit_waits():
     ev.close()
 
 
+def test_library_collective_on_a_single_rank():
+    """mcd_comm_* / mcd_allgather_stats with a one-rank communicator: NCCL is found at run time, the gathered table equals the local
+    (ln prior, ln likelihood) columns (tools/mc3_bench.py runs the same calls on 2..8 GPUs and compares with torch.distributed)"""
+    import torch
+    md, h = synth.synthetic_model(24, seed=24, n_cal=3, n_con=2, n_brace=1)
+    B = 64
+    X = synth.synthetic_states(md, h, B)
+    ev = binding.Evaluator(md)
+    ev.chains_set(X)
+    with pytest.raises(RuntimeError):
+        ev.allgather_stats(0)
+    uid = binding.Evaluator.comm_unique_id()
+    assert len(uid) == 128 and any(uid)
+    ev.comm_init(1, 0, uid)
+    dev = torch.device("cuda", 0)
+    g = torch.full((B, 2), float("nan"), dtype=torch.float64, device=dev)
+    with pytest.raises(RuntimeError):
+        ev.allgather_stats(0)                       # null buffer
+    ev.allgather_stats(g.data_ptr())
+    _, out, _ = ev.chains_get()
+    assert np.array_equal(g.cpu().numpy(), out[:, 3:5])
+    ev.comm_destroy()
+    with pytest.raises(RuntimeError):
+        ev.allgather_stats(g.data_ptr())            # no communicator any more
+    ev.close()
+
+
 def test_error_behaviour():
     md, z = load_fixture("12-leaves-variable-rate")
     ev = binding.Evaluator(md)

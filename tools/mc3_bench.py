@@ -2,7 +2,9 @@
 """BASELINE.json configs[3]: mtCDNApri-shaped data set (7 leaves), autocorrelated rates, MC3 with 64 heated chains spread
 over the GPUs of one box (one process per GPU; torchrun).  Every iteration = one sweep of the reference's proposal cycle
 (mcmc-date_b200/mh_cycle.py -> mcd_mh_cycle) on the resident chains, then -- every SWAP_PERIOD iterations -- the all-gather of
-(ln prior, ln likelihood) over NCCL and N_SWAPS slot swaps (mcd_mc3_swap), decided identically on every rank
+(ln prior, ln likelihood) over NCCL (mcd_allgather_stats: the library's own communicator, set up from an id that rank 0 creates and
+torch.distributed broadcasts; MC3_TORCH_ALLGATHER=1 uses torch.distributed's all-gather instead) and N_SWAPS slot swaps
+(mcd_mc3_swap), decided identically on every rank
 (`MC3Settings (NChains ..) (SwapPeriod 2) (NSwaps 3)`, app/Main.hs:477).
 usage: [torchrun --nproc-per-node N] tools/mc3_bench.py [groups=1] [iterations=200]"""
 import os
@@ -43,6 +45,13 @@ def main():
     ev.chains_set(X0[rank * B:(rank + 1) * B])
     ladder = 1.0 / (1.0 + 0.05 * np.arange(N_CHAINS))         # incremental heating, beta_i = 1 / (1 + i dT)
     ev.mc3_configure(n_global, rank * B, N_CHAINS, ladder, ladder)
+    lib_comm = world > 1 and not os.environ.get("MC3_TORCH_ALLGATHER")
+    if lib_comm:   # the library's communicator: rank 0 creates the NCCL id, everybody joins
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(binding.Evaluator.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ev.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
     props = mh_cycle.reference_cycle(md)
     steps_per_sweep = sum(p[5] for p in props)
     local_stats = torch.empty((B, 2), dtype=torch.float64, device=dev)
@@ -51,12 +60,15 @@ def main():
     def iteration(it, k):
         acc, inv, k = ev.mh_cycle(props, 1, seed=17, iteration0=k)
         if it % SWAP_PERIOD == SWAP_PERIOD - 1:
-            ev.chains_stats_device(local_stats.data_ptr())     # (ln prior, ln lik) of the resident chains
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, local_stats)
+            if lib_comm:
+                ev.allgather_stats(gathered.data_ptr())        # (ln prior, ln lik) of every rank's resident chains
             else:
-                gathered.copy_(local_stats)
-            torch.cuda.synchronize()
+                ev.chains_stats_device(local_stats.data_ptr())
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, local_stats)
+                else:
+                    gathered.copy_(local_stats)
+                torch.cuda.synchronize()
             for s in range(N_SWAPS):
                 ev.mc3_swap(-1, seed=23, iteration=it * N_SWAPS + s, d_stats_global=gathered.data_ptr(), want_accepted=False)
         return acc, k
@@ -99,7 +111,8 @@ def main():
                           "n_gpus": world, "chains_per_gpu": B, "iterations": iters, "proposal_steps_per_iteration": steps_per_sweep,
                           "swap_period": SWAP_PERIOD, "n_swaps": N_SWAPS, "iterations_per_s": iters / dt,
                           "proposals_per_s": iters * steps_per_sweep * n_global / dt, "acceptance": tot_acc / (iters * steps_per_sweep * B),
-                          "chains_off_initial_slot": moved, "slot_tables_identical_on_all_ranks": ok}))
+                          "chains_off_initial_slot": moved, "slot_tables_identical_on_all_ranks": ok,
+                          "allgather": "mcd_allgather_stats (library NCCL communicator)" if lib_comm else "torch.distributed / local copy"}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
