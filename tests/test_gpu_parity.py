@@ -342,6 +342,9 @@ def _check_against_oracle(md, X, n_oracle=None, expect_fallback=None):
     assert ev_val < TOL and eg < TOL and es < TOL, (ev_val, eg, es)
     if expect_fallback is not None:
         assert np.array_equal((st & model.ST_FP64_FALLBACK) != 0, expect_fallback), np.nonzero((st & model.ST_FP64_FALLBACK) != 0)[0]
+    # the value-only entry point (triangular Cholesky-factor contraction, its own FP64 fall-back for flagged chains)
+    outv, stv = ev.eval(X)
+    assert relerr(outv[:, :7], out[:, :7]).max() < TOL and np.array_equal(stv, st)
     # the FP64 tensor-instruction contraction on the same inputs: same answer
     ev.set_contraction("dmma")
     out2, grad2, st2 = ev.eval_grad(X)
