@@ -794,7 +794,7 @@ residual_split_kernel(int N, int K, int SL, int root_r, const int* __restrict__ 
         double e = (hp[j] - hi[j]) * ri[j];
         if (i == 1) e = e + root_e;
         const int k = i < root_r ? i - 1 : i - 2;
-        const double d = (e * sc - mu[k]) * ick[k];
+        const double d = (e * sc - mu[k]) * ick[k];   // (loading mu / 1/c with the first batch: 40 registers, no gain)
         sdx[k] = d;
         const double a = fabs(d);
         bad |= !(a <= 1.7976931348623157e308);
