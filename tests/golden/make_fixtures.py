@@ -90,9 +90,9 @@ def make(name, md, pr, init_state, n_valid=24, seed=0):
           "cal", md.cal_node.tolist(), "con", md.con_young.tolist(), md.con_old.tolist(), "brace", md.brace_node.tolist())
 
 
-def dataset(name, d, cal=True, con=False, br=False, seed=0):
+def dataset(name, d, cal=True, con=False, br=False, seed=0, trees="test.treelist"):
     md, pr = prepare.model_from_files(
-        read(f"tests/{d}/data/test.treelist"),
+        read(f"tests/{d}/data/{trees}"),
         read(f"tests/{d}/data/calibrations.csv") if cal else None,
         read(f"tests/{d}/data/constraints.csv") if con else None,
         read(f"tests/{d}/data/braces.json") if br else None)
@@ -148,9 +148,22 @@ def abi_case():
     print("abi_case_12_leaves.txt", X.shape, st.tolist())
 
 
+def more_datasets():
+    """the reference's three remaining tests/ directories: a calibration pinned to a 1e-6-wide interval with probability mass 1e-6
+    (very steep soft bounds), the 10-leaf autocorrelated-rate simulation (ages in the hundreds, ht = 1000), and the 25-leaf
+    empirical set with calibrations and constraints (3000 trees in the list)"""
+    dataset("06-leaves-pinned-node", "06-leaves-pinned-node", seed=4)
+    dataset("10-leaves-autocorrelated-rate", "10-leaves-autocorrelated-rate", seed=5)
+    dataset("25-leaves-bastien", "25-leaves-bastien", con=True, seed=6, trees="alignment.fasta.trees.only")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["more"]:           # only the fixtures added later; the earlier files stay byte-identical
+        more_datasets()
+        sys.exit(0)
     dataset("06-leaves-constant-rate", "06-leaves-constant-rate", seed=0)
     dataset("12-leaves-variable-rate", "12-leaves-variable-rate", con=True, seed=1)
     dataset("24-leaves-braces", "24-leaves-braces", con=True, br=True, seed=2)
     mtcdnapri()
     abi_case()
+    more_datasets()

@@ -6,7 +6,8 @@ import numpy as np
 from mcmc_date_b200 import model
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FIXTURES = ["06-leaves-constant-rate", "12-leaves-variable-rate", "24-leaves-braces", "mtcdnapri-7-leaves"]
+FIXTURES = ["06-leaves-constant-rate", "12-leaves-variable-rate", "24-leaves-braces", "mtcdnapri-7-leaves",
+            "06-leaves-pinned-node", "10-leaves-autocorrelated-rate", "25-leaves-bastien"]
 TOL = 1e-10  # north_star: 1e-10 relative error in FP64
 
 
