@@ -95,7 +95,7 @@ struct mcd_handle {
   DevBuf d_theta, d_gtheta, d_base, d_tidx, d_sidx;  // theta-packed API
   DevBuf d_mom, d_eps, d_invmass, d_energy, d_status_acc;  // device-resident leapfrog trajectories
   // chains resident in HBM for Metropolis-Hastings moves (mh_kernels.cuh)
-  DevBuf d_chain, d_chain_out, d_chain_status, d_new_out, d_new_status, d_undo, d_rng, d_meta, d_lq, d_accepted, d_counters;
+  DevBuf d_chain, d_chain_out, d_chain_status, d_new_out, d_new_status, d_undo, d_rng, d_meta, d_lq, d_accepted, d_counters, d_cycle;
   DevBuf d_mh_child1, d_mh_size, d_mh_inner_cnt, d_mh_inner_list;
   int n_resident = 0, chain_cap = 0, n_inner_nonroot = 0, undo_stride = 0;
   std::vector<int32_t> br_off_h, br_node_h, sub_size_h;  // host copies of the brace table (argument checks of the brace proposals)
@@ -1331,12 +1331,53 @@ int mh_cycle(mcd_handle* h, int n_props, const mcd_mh_proposal* props, int n_ite
   unsigned long long* cnt = h->d_counters.as<unsigned long long>();
   CU_TRY(h, cudaMemsetAsync(cnt, 0, (size_t)2 * n_props * sizeof(unsigned long long), st));
   uint32_t it = iteration0;
+  static const bool per_step = getenv("MCD_MH_UNFUSED") != nullptr || getenv("MCD_MH_PER_STEP") != nullptr;  // A/B switches
+  if (h->N <= SMALL_TREE_MAX_NODES && !per_step && n_iterations > 0) {
+    // small trees: all sweeps in ONE launch (mh_small_cycle_kernel), one warp per chain
+    std::vector<MhCycleEntry> tab((size_t)n_props);
+    uint64_t steps = 0;
+    for (int p = 0; p < n_props; ++p) {
+      tab[p] = MhCycleEntry{props[p].kind, props[p].node, props[p].use_root_jacobian, props[p].repeat, props[p].param, props[p].tune};
+      steps += (uint64_t)props[p].repeat;
+    }
+    steps *= (uint64_t)n_iterations;
+    if (steps > 0xffffffffull - iteration0) return fail(h, "mcd_mh_cycle: the Philox iteration counter would wrap");
+    if (!h->d_cycle.p) CU_TRY(h, cudaMalloc(&h->d_cycle.p, (size_t)MH_MAX_CYCLE * sizeof(MhCycleEntry)));
+    CU_TRY(h, cudaMemcpyAsync(h->d_cycle.p, tab.data(), tab.size() * sizeof(MhCycleEntry), cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaStreamSynchronize(st));  // `tab` is pageable host memory
+    DevModel M = h->dm;
+    M.quad_from_z = 0;
+    const MhTopo T = mh_topo(h);
+    const bool heated = h->mc3_C > 0;
+    // few chains: one warp per CTA spreads them over the SMs (the steps of a chain are a serial dependency chain);
+    // many chains: eight warps per CTA share the staged precision matrix
+    const int wpb = n <= 2 * h->n_sms ? 1 : POST_THREADS / 32;
+    const size_t fsmem = POST_SMEM_FIXED + ((size_t)M.K * M.K + (size_t)wpb * (M.S + M.N + M.K)) * 8 +
+                         (size_t)wpb * (sizeof(MhOp) * MH_MAX_OPS + (size_t)(2 * M.N + 8) * 16 + MH_CYCLE_WARP_EXTRA);
+    const int fgrid = std::min((n + wpb - 1) / wpb, 2 * h->n_sms);
+#define MCD_LAUNCH_MH_CYCLE(CC)                                                                                              \
+  mh_small_cycle_kernel<CC><<<fgrid, wpb * 32, fsmem, st>>>(M, T, h->d_cycle.as<MhCycleEntry>(), n_props, n_iterations, seed,  \
+      iteration0, h->mc3_offset, h->d_P.as<double>(), h->d_chain.as<double>(), h->d_chain_out.as<double>(),                  \
+      h->d_chain_status.as<int32_t>(), h->d_new_out.as<double>(), h->d_new_status.as<int32_t>(), h->d_accepted.as<int32_t>(),  \
+      cnt, heated ? h->d_slot.as<int>() : nullptr, h->d_ladder_p.as<double>(), h->d_ladder_l.as<double>(), n)
+    switch (M.clock) {
+      case 0: MCD_LAUNCH_MH_CYCLE(0); break;
+      case 1: MCD_LAUNCH_MH_CYCLE(1); break;
+      case 2: MCD_LAUNCH_MH_CYCLE(2); break;
+      default: MCD_LAUNCH_MH_CYCLE(3); break;
+    }
+#undef MCD_LAUNCH_MH_CYCLE
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    it += (uint32_t)steps;
+  } else {
   for (int sweep = 0; sweep < n_iterations; ++sweep)
     for (int p = 0; p < n_props; ++p)
       for (int r = 0; r < props[p].repeat; ++r)
         if (mh_enqueue(h, props[p].kind, props[p].node, props[p].param, props[p].tune, props[p].use_root_jacobian, seed, it++,
                        cnt + 2 * p))
           return -1;
+  }
   std::vector<unsigned long long> host((size_t)2 * n_props);
   CU_TRY(h, cudaMemcpyAsync(host.data(), cnt, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaStreamSynchronize(st));
@@ -1748,7 +1789,9 @@ int mcd_create(const mcd_model_desc* d, mcd_handle** out) {
   cudaFuncSetAttribute(small_tree_fused_kernel<CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     MCD_SET_SMEM(0) MCD_SET_SMEM(1) MCD_SET_SMEM(2) MCD_SET_SMEM(3)
 #undef MCD_SET_SMEM
-#define MCD_SET_SMEM(CC) cudaFuncSetAttribute(mh_small_tree_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+#define MCD_SET_SMEM(CC)                                                                               \
+  cudaFuncSetAttribute(mh_small_tree_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);     \
+  cudaFuncSetAttribute(mh_small_cycle_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     MCD_SET_SMEM(0) MCD_SET_SMEM(1) MCD_SET_SMEM(2) MCD_SET_SMEM(3)
 #undef MCD_SET_SMEM
 #define MCD_SET_SMEM(CC)                                                                                  \

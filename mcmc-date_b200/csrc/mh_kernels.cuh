@@ -1066,6 +1066,145 @@ mh_fused_small_kernel(const DevModel M, const MhTopo T, const MhParams P, const 
 // and arithmetic as mh_propose_kernel -> small_tree_fused_kernel -> mh_accept_kernel.
 // Dynamic shared memory: reduction scratch | P [K][K] | per warp: state row, y, residuals | per warp: operation list,
 // undo list (offset, old value) of up to 2N + 8 entries.
+// One Metropolis-Hastings step of one chain by one warp (the body shared by the one-step and the whole-cycle kernels):
+// propose in place, evaluate the proposed state from scratch, decide, restore on rejection.  Warp-level synchronisation only.
+struct MhSmallWarp {
+  double *sx, *sy, *sdx, *c_old;
+  int* c_off;
+  MhOp* ops;
+  int n_undo;
+  double *o_cur, *o_new;   // RESIDENT: the chain's current / proposed output row [8] in shared memory
+  int* st;                 // RESIDENT: [0] proposed, [1] current status word
+};
+// RESIDENT (whole-cycle kernel): the chain's state row lives in W.sx and its output row / status word in W.o_cur / W.st[1] for the
+// whole cycle; the step reads and writes shared memory only (a step is a serial chain of dependent operations: every global
+// round trip -- row, proposed row, output rows -- costs ~1 us of its ~9).  Otherwise (one step per launch) the row is modified in
+// global memory and staged, as mh_propose_kernel -> small_tree_fused_kernel -> mh_accept_kernel would.  Same arithmetic either way.
+template <int CLOCK, bool RESIDENT = false>
+__device__ __forceinline__ int mh_small_step(const DevModel& M, const MhTopo& T, const Topo& Tp, const MhParams& P, const double* sP,
+                                              const MhSmallWarp& W, double* scratch, int* iscratch, double* states, double* cur_out,
+                                              int* cur_status, double* new_out, int* new_status, int* __restrict__ accepted,
+                                              unsigned long long* __restrict__ counters, const int* __restrict__ slot,
+                                              const double* __restrict__ ladder_prior, const double* __restrict__ ladder_lik, int chain,
+                                              int lane) {
+  const int K = M.K, N = M.N, S = M.S, n_undo = W.n_undo;
+  double *sx = W.sx, *sy = W.sy, *sdx = W.sdx, *c_old = W.c_old;
+  int* c_off = W.c_off;
+  MhOp* ops = W.ops;
+  double* row = RESIDENT ? sx : states + (size_t)chain * S;
+  double rate_sum = 0.0;
+  if (P.kind == MH_SCALE_VAR_TREE) {
+    for (int i = 1 + lane; i < N; i += 32) rate_sum += row[5 + N + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rate_sum += __shfl_xor_sync(0xffffffffu, rate_sum, o);
+  }
+  int nops = 0, okv = 0;
+  double lqv = 0.0;
+  if (lane == 0) {
+    bool ok;
+    int node;
+    nops = mh_build_ops(T, P, row, chain, rate_sum, ops, &ok, &node, &lqv);
+    okv = ok ? 1 : 0;
+  }
+  nops = __shfl_sync(0xffffffffu, nops, 0);
+  okv = __shfl_sync(0xffffffffu, okv, 0);
+  __syncwarp();
+  if (!okv || nops == 0) {
+    if (lane == 0) {
+      if (!RESIDENT && accepted) accepted[chain] = okv ? 0 : -1;
+      if (counters && !okv) atomicAdd(counters + 1, 1ull);
+    }
+    return okv ? 0 : -1;
+  }
+  int n_raw = 0;
+  for (int o = 0; o < nops; ++o) {
+    const MhOp op = ops[o];
+    for (int i = lane; i < op.cnt && n_raw + i < n_undo; i += 32) {
+      const double old = row[op.off + i];
+      c_off[n_raw + i] = op.off + i;
+      c_old[n_raw + i] = old;
+      double y;
+      switch (op.mode) {
+        case OP_SET: y = op.b; break;
+        case OP_MUL: y = old * op.a; break;
+        case OP_DIV: y = old / op.a; break;
+        case OP_ADD: y = old + op.b; break;
+        default: y = (old - op.b) * op.a + op.b; if (!(y > 0.0)) y = CUDART_NAN; break;
+      }
+      row[op.off + i] = y;
+    }
+    n_raw += op.cnt;
+    __syncwarp();
+  }
+  MCD_ASSERT(n_raw <= n_undo);
+  if (n_raw > n_undo) n_raw = n_undo;
+  // evaluate the proposed state: small_tree_fused_kernel's body
+  if (!RESIDENT) {
+    __threadfence_block();
+    stage_chain<32>(M, chain, lane, sx, sy, states, nullptr);
+  }
+  if (M.lik == 0) {
+    const double* h = sx + 3;
+    const double* r = sx + 5 + N;
+    const double sc = sx[2] * sx[3 + N];
+    for (int i = 1 + lane; i < N; i += 32) {
+      if (i == M.root_r) continue;
+      double e = (h[M.parent[i] & ~LEAF_BIT] - h[i]) * r[i];
+      if (i == 1) e = e + (h[0] - h[M.root_r]) * r[M.root_r];
+      const int kk = i < M.root_r ? i - 1 : i - 2;
+      sdx[kk] = e * sc - M.mu[kk];
+    }
+    __syncwarp();
+    for (int kk = lane; kk < K; kk += 32) {
+      const double* prow = sP + (size_t)kk * K;
+      double a0 = 0.0, a1 = 0.0;
+      int j = 0;
+      for (; j + 2 <= K; j += 2) {
+        a0 = fma(prow[j], sdx[j], a0);
+        a1 = fma(prow[j + 1], sdx[j + 1], a1);
+      }
+      if (j < K) a0 = fma(prow[j], sdx[j], a0);
+      sy[kk] = a0 + a1;
+    }
+    __syncwarp();
+  }
+  if (RESIDENT) process_chain<32, CLOCK, false>(M, Tp, 0, lane, sx, sy, scratch, iscratch, W.o_new, nullptr, W.st);
+  else process_chain<32, CLOCK, false>(M, Tp, chain, lane, sx, sy, scratch, iscratch, new_out, nullptr, new_status);
+  __syncwarp();
+  int acc = 0;
+  if (lane == 0) {  // lane 0 wrote the proposed output row / status word itself
+    const double* o1 = RESIDENT ? W.o_new : new_out + (size_t)chain * 8;
+    double* o0 = RESIDENT ? W.o_cur : cur_out + (size_t)chain * 8;
+    double bp = 1.0, bl = 1.0;
+    if (slot) {
+      const int sl = slot[P.chain_offset + chain];
+      bp = ladder_prior[sl];
+      bl = ladder_lik[sl];
+    }
+    double lr = bp * (o1[3] - o0[3]) + bl * (o1[4] - o0[4]) + lqv;
+    if (P.use_root_jacobian) lr += o1[5] - o0[5];
+    const double u = mh_uniform(P.seed, (uint32_t)(P.chain_offset + chain), P.iteration, 1u);
+    acc = log(u) < lr;
+    if (!RESIDENT && accepted) accepted[chain] = acc;
+    if (counters && acc) atomicAdd(counters, 1ull);
+    if (acc) {
+      for (int j = 0; j < 8; ++j) o0[j] = o1[j];
+      if (RESIDENT) W.st[1] = W.st[0];
+      else cur_status[chain] = new_status[chain];
+    }
+  }
+  acc = __shfl_sync(0xffffffffu, acc, 0);
+  if (!acc) {  // restore: the first record of an offset holds its old value
+    for (int e = lane; e < n_raw; e += 32) {
+      const int off = c_off[e];
+      bool first = true;
+      for (int e2 = 0; e2 < e; ++e2) first = first && (c_off[e2] != off);
+      if (first) row[off] = c_old[e];
+    }
+  }
+  return acc;
+}
+
 template <int CLOCK>
 __global__ void __launch_bounds__(POST_THREADS, 2)
 mh_small_tree_kernel(DevModel M, const MhTopo T, const MhParams P, const double* __restrict__ Pm /*[Mp][ldk] padded*/, double* states,
@@ -1094,114 +1233,93 @@ mh_small_tree_kernel(DevModel M, const MhTopo T, const MhParams P, const double*
   double* c_old = reinterpret_cast<double*>(mh_base + (size_t)warp * mh_per_warp + sizeof(MhOp) * MH_MAX_OPS);
   int* c_off = reinterpret_cast<int*>(c_old + n_undo);
   for (int chain = blockIdx.x * (POST_THREADS / 32) + warp; chain < B; chain += gridDim.x * (POST_THREADS / 32)) {
-    double* row = states + (size_t)chain * S;
-    double rate_sum = 0.0;
-    if (P.kind == MH_SCALE_VAR_TREE) {
-      for (int i = 1 + lane; i < N; i += 32) rate_sum += row[5 + N + i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rate_sum += __shfl_xor_sync(0xffffffffu, rate_sum, o);
-    }
-    int nops = 0, okv = 0;
-    double lqv = 0.0;
-    if (lane == 0) {
-      bool ok;
-      int node;
-      nops = mh_build_ops(T, P, row, chain, rate_sum, ops, &ok, &node, &lqv);
-      okv = ok ? 1 : 0;
-    }
-    nops = __shfl_sync(0xffffffffu, nops, 0);
-    okv = __shfl_sync(0xffffffffu, okv, 0);
-    __syncwarp();
-    if (!okv || nops == 0) {
-      if (lane == 0) {
-        if (accepted) accepted[chain] = okv ? 0 : -1;
-        if (counters && !okv) atomicAdd(counters + 1, 1ull);
-      }
-      continue;
-    }
-    int n_raw = 0;
-    for (int o = 0; o < nops; ++o) {
-      const MhOp op = ops[o];
-      for (int i = lane; i < op.cnt && n_raw + i < n_undo; i += 32) {
-        const double old = row[op.off + i];
-        c_off[n_raw + i] = op.off + i;
-        c_old[n_raw + i] = old;
-        double y;
-        switch (op.mode) {
-          case OP_SET: y = op.b; break;
-          case OP_MUL: y = old * op.a; break;
-          case OP_DIV: y = old / op.a; break;
-          case OP_ADD: y = old + op.b; break;
-          default: y = (old - op.b) * op.a + op.b; if (!(y > 0.0)) y = CUDART_NAN; break;
-        }
-        row[op.off + i] = y;
-      }
-      n_raw += op.cnt;
-      __syncwarp();
-    }
-    MCD_ASSERT(n_raw <= n_undo);
-    if (n_raw > n_undo) n_raw = n_undo;
-    __threadfence_block();
-    // evaluate the proposed state: small_tree_fused_kernel's body
-    stage_chain<32>(M, chain, lane, sx, sy, states, nullptr);
-    if (M.lik == 0) {
-      const double* h = sx + 3;
-      const double* r = sx + 5 + N;
-      const double sc = sx[2] * sx[3 + N];
-      for (int i = 1 + lane; i < N; i += 32) {
-        if (i == M.root_r) continue;
-        double e = (h[M.parent[i] & ~LEAF_BIT] - h[i]) * r[i];
-        if (i == 1) e = e + (h[0] - h[M.root_r]) * r[M.root_r];
-        const int kk = i < M.root_r ? i - 1 : i - 2;
-        sdx[kk] = e * sc - M.mu[kk];
-      }
-      __syncwarp();
-      for (int kk = lane; kk < K; kk += 32) {
-        const double* prow = sP + (size_t)kk * K;
-        double a0 = 0.0, a1 = 0.0;
-        int j = 0;
-        for (; j + 2 <= K; j += 2) {
-          a0 = fma(prow[j], sdx[j], a0);
-          a1 = fma(prow[j + 1], sdx[j + 1], a1);
-        }
-        if (j < K) a0 = fma(prow[j], sdx[j], a0);
-        sy[kk] = a0 + a1;
-      }
-      __syncwarp();
-    }
-    process_chain<32, CLOCK, false>(M, Tp, chain, lane, sx, sy, scratch, iscratch, new_out, nullptr, new_status);
-    __syncwarp();
-    int acc = 0;
-    if (lane == 0) {  // lane 0 wrote new_out[chain] / new_status[chain] itself
-      const double* o1 = new_out + (size_t)chain * 8;
-      const double* o0 = cur_out + (size_t)chain * 8;
-      double bp = 1.0, bl = 1.0;
-      if (slot) {
-        const int sl = slot[P.chain_offset + chain];
-        bp = ladder_prior[sl];
-        bl = ladder_lik[sl];
-      }
-      double lr = bp * (o1[3] - o0[3]) + bl * (o1[4] - o0[4]) + lqv;
-      if (P.use_root_jacobian) lr += o1[5] - o0[5];
-      const double u = mh_uniform(P.seed, (uint32_t)(P.chain_offset + chain), P.iteration, 1u);
-      acc = log(u) < lr;
-      if (accepted) accepted[chain] = acc;
-      if (counters && acc) atomicAdd(counters, 1ull);
-      if (acc) {
-        for (int j = 0; j < 8; ++j) cur_out[(size_t)chain * 8 + j] = o1[j];
-        cur_status[chain] = new_status[chain];
-      }
-    }
-    acc = __shfl_sync(0xffffffffu, acc, 0);
-    if (!acc) {  // restore: the first record of an offset holds its old value
-      for (int e = lane; e < n_raw; e += 32) {
-        const int off = c_off[e];
-        bool first = true;
-        for (int e2 = 0; e2 < e; ++e2) first = first && (c_off[e2] != off);
-        if (first) row[off] = c_old[e];
-      }
-    }
+    const MhSmallWarp W{sx, sy, sdx, c_old, c_off, ops, n_undo, nullptr, nullptr, nullptr};
+    mh_small_step<CLOCK>(M, T, Tp, P, sP, W, scratch, iscratch, states, cur_out, cur_status, new_out, new_status, accepted, counters, slot,
+                         ladder_prior, ladder_lik, chain, lane);
     __syncwarp();  // the warp's staging buffers are reused by its next chain
+  }
+}
+
+// The whole proposal cycle of small trees in ONE launch: every warp keeps its chain and walks n_sweeps sweeps over the list
+// (entry e `repeat` times, Philox iteration iteration0 + running step number), exactly the steps mcd_mh_cycle would enqueue one
+// launch at a time -- same draws, same arithmetic, same results -- without ~250 launch latencies per sweep and with the precision
+// matrix staged in shared memory once.  Chains never interact inside a cycle (the MC3 slots change between calls only).
+constexpr int MH_CYCLE_WARP_EXTRA = 16 * 8 + 16;   // per warp: current / proposed output rows [8] + two status words
+struct MhCycleEntry {
+  int kind, node, use_root_jacobian, repeat;
+  double param, tune;
+};
+template <int CLOCK>
+__global__ void __launch_bounds__(POST_THREADS, 2)
+mh_small_cycle_kernel(DevModel M, const MhTopo T, const MhCycleEntry* __restrict__ cycle, int n_entries, int n_sweeps, uint64_t seed,
+                      uint32_t iteration0, int chain_offset, const double* __restrict__ Pm, double* states, double* cur_out,
+                      int* cur_status, double* new_out, int* new_status, int* __restrict__ accepted,
+                      unsigned long long* __restrict__ counters /*[n_entries][2]*/, const int* __restrict__ slot,
+                      const double* __restrict__ ladder_prior, const double* __restrict__ ladder_lik, int B) {
+  extern __shared__ __align__(16) unsigned char smem_p[];
+  double* scratch = reinterpret_cast<double*>(smem_p);
+  int* iscratch = reinterpret_cast<int*>(smem_p + 8 * NRED * 8);
+  double* sP = reinterpret_cast<double*>(smem_p + POST_SMEM_FIXED);   // [K][K]
+  const int K = M.K, N = M.N, S = M.S;
+  double* stage = sP + (size_t)K * K;
+  const int n_undo = 2 * N + 8;
+  const int wpb = blockDim.x >> 5;   // warps (= chains in flight) per CTA: the per-warp areas are sized by it
+  unsigned char* mh_base = reinterpret_cast<unsigned char*>(stage + (size_t)wpb * (S + N + K));
+  const size_t mh_per_warp = sizeof(MhOp) * MH_MAX_OPS + (size_t)n_undo * 16 + MH_CYCLE_WARP_EXTRA;
+  const Topo Tp{M.parent, M.mu, M.var, M.inner, nullptr};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (M.lik == 0) {
+    for (int e = threadIdx.x; e < K * K; e += blockDim.x) sP[e] = Pm[(size_t)(e / K) * M.ldk + (e % K)];
+  }
+  __syncthreads();
+  MhSmallWarp W;
+  W.sx = stage + (size_t)warp * (S + N + K);
+  W.sy = W.sx + S;
+  W.sdx = W.sy + N;
+  W.ops = reinterpret_cast<MhOp*>(mh_base + (size_t)warp * mh_per_warp);
+  W.c_old = reinterpret_cast<double*>(mh_base + (size_t)warp * mh_per_warp + sizeof(MhOp) * MH_MAX_OPS);
+  W.c_off = reinterpret_cast<int*>(W.c_old + n_undo);
+  W.n_undo = n_undo;
+  W.o_cur = reinterpret_cast<double*>(mh_base + (size_t)warp * mh_per_warp + sizeof(MhOp) * MH_MAX_OPS + (size_t)n_undo * 16);
+  W.o_new = W.o_cur + 8;
+  W.st = reinterpret_cast<int*>(W.o_new + 8);
+  for (int chain = blockIdx.x * wpb + warp; chain < B; chain += gridDim.x * wpb) {
+    // the chain moves into shared memory for the whole cycle
+    stage_chain<32>(M, chain, lane, W.sx, W.sy, states, nullptr);
+    if (lane < 8) {
+      W.o_cur[lane] = cur_out[(size_t)chain * 8 + lane];
+      W.o_new[lane] = new_out[(size_t)chain * 8 + lane];
+    }
+    if (lane == 0) { W.st[1] = cur_status[chain]; W.st[0] = new_status[chain]; }
+    __syncwarp();
+    int last = 0;
+    uint32_t it = iteration0;
+    for (int sweep = 0; sweep < n_sweeps; ++sweep) {
+      for (int e = 0; e < n_entries; ++e) {
+        const MhCycleEntry ce = cycle[e];
+        MhParams P;
+        P.kind = ce.kind; P.node = ce.node; P.use_root_jacobian = ce.use_root_jacobian; P.pad = 0; P.param = ce.param; P.tune = ce.tune;
+        P.seed = seed; P.chain_offset = chain_offset;
+        for (int r = 0; r < ce.repeat; ++r) {
+          P.iteration = it++;
+          last = mh_small_step<CLOCK, true>(M, T, Tp, P, sP, W, scratch, iscratch, states, cur_out, cur_status, new_out, new_status,
+                                            accepted, counters + 2 * e, slot, ladder_prior, ladder_lik, chain, lane);
+          __syncwarp();  // the warp's staging buffers are reused by its next step
+        }
+      }
+    }
+    // ... and back: state row, output row, status word, the last step's decision and proposed outputs
+    for (int i = lane; i < S; i += 32) states[(size_t)chain * S + i] = W.sx[i];
+    if (lane < 8) {
+      cur_out[(size_t)chain * 8 + lane] = W.o_cur[lane];
+      new_out[(size_t)chain * 8 + lane] = W.o_new[lane];
+    }
+    if (lane == 0) {
+      cur_status[chain] = W.st[1];
+      new_status[chain] = W.st[0];
+      if (accepted) accepted[chain] = last;
+    }
+    __syncwarp();
   }
 }
 

@@ -680,9 +680,11 @@ def test_every_proposal_of_the_reference_cycle(n_leaves, B, clock):
     ev.close()
 
 
-def test_mh_cycle_equals_single_steps_and_counts():
-    """mcd_mh_cycle = the same proposals enqueued back to back: identical chains, acceptance counts per list entry"""
-    mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r = _mh_setup(60, 96, n_brace=1)
+@pytest.mark.parametrize("n_leaves,B", [(60, 96), (24, 96), (24, 400)])
+def test_mh_cycle_equals_single_steps_and_counts(n_leaves, B):
+    """mcd_mh_cycle = the same proposals enqueued back to back: identical chains, acceptance counts per list entry.  24 leaves: the
+    whole call is ONE launch (mh_small_cycle_kernel; one warp per CTA for 96 chains, eight for 400) against one launch per step"""
+    mh_ref, md, X, ev, orc, parent, braces, Xr, out_r, st_r = _mh_setup(n_leaves, B, n_brace=1)
     R = mh_ref
     props = [(R.SLIDE_NODE, -1, 0.01, 1.0, 0, 3), (R.SCALE_BRANCH, -1, 100.0, 10.0, 0, 2), (R.SCALE_SCALAR, 3, 10.0, 1.0, 0, 1),
              (R.SLIDE_BRACE, 0, 0.01, 0.01, 0, 1), (R.SCALE_NORM_TREE_CONTRA_M, 0, 100.0, 1.0, 1, 1)]
