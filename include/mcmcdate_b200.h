@@ -230,7 +230,8 @@ typedef struct mcd_mh_proposal {
 /* n_iterations sweeps over props[0..n_props) (each `repeat` times, in the given order), enqueued back to back; proposal
  * number s of the call uses Philox iteration iteration0 + s.  accepted / invalid [n_props] (nullable): chains x steps
  * accepted / rejected as invalid per list entry -- what the reference's auto tuner consumes.  *iteration_next (nullable):
- * first unused iteration value.  At most 4096 list entries per call. */
+ * first unused iteration value.  At most 4096 list entries per call.  Small trees (<= 96 nodes): the whole call is ONE kernel launch
+ * (every chain stays in shared memory for all sweeps); same draws and results as one launch per step. */
 int mcd_mh_cycle(mcd_handle* h, int32_t n_props, const mcd_mh_proposal* props, int32_t n_iterations, uint64_t seed,
                  uint32_t iteration0, uint64_t* accepted, uint64_t* invalid, uint32_t* iteration_next);
 
