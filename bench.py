@@ -262,7 +262,7 @@ def roofline(oz_s, K, B, gemm_ms, kms, ncalls, args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    return {"kernel": f"gemm_i8_ozaki_kernel<{oz_s}>", "bound": "tensor", "achieved": achieved, "peak": INT8_NOMINAL_TOPS,
+    return {"kernel": f"gemm_i8_ozaki_v2_kernel<{oz_s}>", "bound": "tensor", "achieved": achieved, "peak": INT8_NOMINAL_TOPS,
             "unit": "TOP/s (int8)", "frac": achieved / INT8_NOMINAL_TOPS, "traffic": traffic,
             "peak_source": "nominal dense INT8 tensor peak (4.5 POP/s); MEASURED_PEAKS.json has no int8 entry -- the figure derived "
                            f"from it is twice its measured bf16 burst, {2 * peaks.get('bf16_tflops', 1662.5):.0f} TOP/s "
@@ -302,8 +302,9 @@ def hbm_kernels(oz_s, K, B, kms, ncalls):
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         out.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                     "algorithmic_bytes_per_launch": nbytes, "kernel_ms": ms, "peak_source": src})
-    out[1]["note"] = ("ncu (profiles/r01_ncu_summary.md): 216 M warp instructions, 60 % of the issue slots, FP64 pipe 37 % -- FP64 "
-                      "transcendentals per node (log, exp, reciprocal) bind this kernel before HBM does")
+    out[1]["note"] = ("ncu (profiles/r02_ncu_summary.md): 199 M warp instructions, 66 % of the issue slots, FP64 pipe 36 % -- the FP64 "
+                      "arithmetic per node (logarithm, exponential, reciprocals) and the CTA-wide barriers between the passes bind "
+                      "this kernel before HBM does")
     return out
 
 
