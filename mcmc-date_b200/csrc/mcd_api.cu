@@ -1349,9 +1349,12 @@ int mh_cycle(mcd_handle* h, int n_props, const mcd_mh_proposal* props, int n_ite
     M.quad_from_z = 0;
     const MhTopo T = mh_topo(h);
     const bool heated = h->mc3_C > 0;
-    // few chains: one warp per CTA spreads them over the SMs (the steps of a chain are a serial dependency chain);
-    // many chains: eight warps per CTA share the staged precision matrix
-    const int wpb = n <= 2 * h->n_sms ? 1 : POST_THREADS / 32;
+    // few chains: four warps per CTA, one per SM sub-partition (the steps of a chain are a serial dependency chain, so a warp wants
+    // a scheduler of its own; four chains walking the same code share the SM's instruction cache: 470 / 478 / 483 / 462
+    // iterations/s with 1 / 2 / 4 / 8 warps per CTA on the 64-chain MC3 set); many chains: eight warps per CTA
+    static const int wpb_forced = getenv("MCD_MH_WPB") ? atoi(getenv("MCD_MH_WPB")) : 0;   // experiment switch (1, 2, 4 or 8)
+    const int wpb = (wpb_forced == 1 || wpb_forced == 2 || wpb_forced == 4 || wpb_forced == 8) ? wpb_forced
+                    : n <= 2 * h->n_sms ? 4 : POST_THREADS / 32;
     const size_t fsmem = POST_SMEM_FIXED + ((size_t)M.K * M.K + (size_t)wpb * (M.S + M.N + M.K)) * 8 +
                          (size_t)wpb * (sizeof(MhOp) * MH_MAX_OPS + (size_t)(2 * M.N + 8) * 16 + MH_CYCLE_WARP_EXTRA);
     const int fgrid = std::min((n + wpb - 1) / wpb, 2 * h->n_sms);
