@@ -605,8 +605,8 @@ def run_gpu(args):
             threads = O.max_threads()
             rate, n, dt = cpu_port_rate(md, X, threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{n} chains of the same workload in {dt:.1f} s (oracle CPU port, "
-                                              "std::thread over chains)",
+                                    "sample": f"{n} chains of the same workload in {dt:.1f} s wall on {threads} threads "
+                                              f"= {dt * threads:.0f} core-seconds (oracle CPU port, std::thread over chains)",
                                     "best_case_blas_contraction": cpu_blas_contraction_rate(md)}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
