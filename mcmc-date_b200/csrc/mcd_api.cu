@@ -96,6 +96,7 @@ struct mcd_handle {
   DevBuf d_mom, d_eps, d_invmass, d_energy, d_status_acc;  // device-resident leapfrog trajectories
   // chains resident in HBM for Metropolis-Hastings moves (mh_kernels.cuh)
   DevBuf d_chain, d_chain_out, d_chain_status, d_new_out, d_new_status, d_undo, d_rng, d_meta, d_lq, d_accepted, d_counters, d_cycle;
+  std::vector<unsigned char> cycle_cache;   // bytes of the proposal list d_cycle holds
   DevBuf d_mh_child1, d_mh_size, d_mh_inner_cnt, d_mh_inner_list;
   int n_resident = 0, chain_cap = 0, n_inner_nonroot = 0, undo_stride = 0;
   std::vector<int32_t> br_off_h, br_node_h, sub_size_h;  // host copies of the brace table (argument checks of the brace proposals)
@@ -1343,8 +1344,13 @@ int mh_cycle(mcd_handle* h, int n_props, const mcd_mh_proposal* props, int n_ite
     steps *= (uint64_t)n_iterations;
     if (steps > 0xffffffffull - iteration0) return fail(h, "mcd_mh_cycle: the Philox iteration counter would wrap");
     if (!h->d_cycle.p) CU_TRY(h, cudaMalloc(&h->d_cycle.p, (size_t)MH_MAX_CYCLE * sizeof(MhCycleEntry)));
-    CU_TRY(h, cudaMemcpyAsync(h->d_cycle.p, tab.data(), tab.size() * sizeof(MhCycleEntry), cudaMemcpyHostToDevice, st));
-    CU_TRY(h, cudaStreamSynchronize(st));  // `tab` is pageable host memory
+    // a sampler calls this with the same list iteration after iteration (it changes when the auto tuner has run): upload on change only
+    const size_t tab_bytes = tab.size() * sizeof(MhCycleEntry);
+    if (h->cycle_cache.size() != tab_bytes || memcmp(h->cycle_cache.data(), tab.data(), tab_bytes) != 0) {
+      CU_TRY(h, cudaMemcpyAsync(h->d_cycle.p, tab.data(), tab_bytes, cudaMemcpyHostToDevice, st));
+      CU_TRY(h, cudaStreamSynchronize(st));  // `tab` is pageable host memory
+      h->cycle_cache.assign(reinterpret_cast<const unsigned char*>(tab.data()), reinterpret_cast<const unsigned char*>(tab.data()) + tab_bytes);
+    }
     DevModel M = h->dm;
     M.quad_from_z = 0;
     const MhTopo T = mh_topo(h);
